@@ -1,0 +1,113 @@
+"""Pin the CPU oracle (oracle/) against outputs of the reference itself (tests/golden/*.npz).
+
+The reference has no tests/golden vectors of its own; the fixtures were produced by
+tests/golden/make_golden.py importing /root/reference in the build container.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle.oracle import Oracle
+
+
+def _max_len(g):
+    ml = int(g["max_len"])
+    return None if ml < 0 else ml
+
+
+def _check_infer(g, sd, dims, dtype, tol_o, tol_lat):
+    orc = Oracle(dtype)
+    o, mask, (z, z_p, m_p, logs_p) = orc.infer(sd, dims, g["mel"], g["lengths"], g["eps"],
+                                               float(g["noise_scale"]), _max_len(g))
+    assert o.shape == g["ref64_o"].shape
+    # integer/bool work: bit-identical
+    assert np.array_equal(mask.astype(np.float32), g["ref32_x_mask"])
+    assert np.abs(o - g["ref64_o"]).max() <= tol_o
+    for name, val in (("z", z), ("z_p", z_p), ("m_p", m_p), ("logs_p", logs_p)):
+        assert np.abs(val - g["ref64_" + name]).max() <= tol_lat, name
+    return o
+
+
+def test_oracle_fp64_matches_reference_fp64_tiny(tiny_sd, tiny_dims):
+    g = load_golden("infer_tiny_b2_t33")
+    # latents are stored as fp32 -> 1e-6; waveform is stored in fp64
+    _check_infer(g, tiny_sd, tiny_dims, np.float64, 1e-10, 2e-6)
+
+
+def test_oracle_fp32_matches_reference_tiny(tiny_sd, tiny_dims):
+    g = load_golden("infer_tiny_b2_t33")
+    o = _check_infer(g, tiny_sd, tiny_dims, np.float32, 5e-5, 5e-5)
+    assert np.abs(o - g["ref32_o"]).max() <= 5e-5
+
+
+def test_oracle_trace_tiny(tiny_sd, tiny_dims):
+    """Per-module intermediates: flow after each coupling, decoder stages, one ResBlock each kernel."""
+    g = load_golden("infer_tiny_b2_t33")
+    orc = Oracle(np.float64)
+    _, m_p, logs_p, mask = orc.mel_encoder(tiny_sd, tiny_dims, g["mel"], g["lengths"])
+    z_p = m_p + g["eps"].astype(np.float64) * np.exp(logs_p) * float(g["noise_scale"])
+    tr = []
+    z = orc.flow_reverse(tiny_sd, tiny_dims, z_p, mask, trace=tr)
+    for n, t in enumerate(tr):
+        assert np.abs(t - g[f"trace_flow{n}"]).max() < 2e-6
+    dtr = {}
+    orc.generator(tiny_sd, tiny_dims, z * mask, trace=dtr)
+    for k, v in dtr.items():
+        assert np.abs(v - g["trace_" + k]).max() < 5e-6, k
+    x0 = g["trace_ups0"].astype(np.float64)
+    for j, (k, dil) in enumerate(zip(tiny_dims.resblock_kernel_sizes, tiny_dims.resblock_dilation_sizes)):
+        r = orc.resblock1(tiny_sd, f"dec.resblocks.{j}", x0, k, dil)
+        assert np.abs(r - g[f"trace_rb{j}"]).max() < 5e-6
+
+
+@pytest.mark.parametrize("name", ["infer_base_b3_t3", "infer_base_b1_t12_maxlen9"])
+def test_oracle_fp64_matches_reference_base(name, base_sd, base_dims):
+    g = load_golden(name)
+    _check_infer(g, base_sd, base_dims, np.float64, 1e-10, 2e-6)
+
+
+def test_oracle_fp32_matches_reference_base_padded_batch(base_sd, base_dims):
+    """Padded batch with unequal lengths: pad region is non-zero and must match."""
+    g = load_golden("infer_base_b2_t40")
+    o = _check_infer(g, base_sd, base_dims, np.float32, 5e-5, 5e-5)
+    # fp32 oracle vs fp32 reference differ only by summation order
+    assert np.abs(o - g["ref32_o"]).max() <= 5e-5
+
+
+def test_flip_and_mask_bit_exact():
+    x = np.arange(2 * 6 * 5, dtype=np.float32).reshape(2, 6, 5)
+    assert np.array_equal(Oracle.flip(x), x[:, ::-1])
+    m = Oracle.sequence_mask(np.array([0, 3, 5, 9]), 5)
+    assert m.shape == (4, 1, 5)
+    assert np.array_equal(m[:, 0].sum(1), [0, 3, 5, 5])
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+def test_spline_matches_reference(inverse):
+    g = load_golden("rq_spline")
+    tag = f"inv{int(inverse)}"
+    y, lad, bins = Oracle(np.float64).rq_spline(g["x"], g["uw"], g["uh"], g["ud"], inverse)
+    assert np.abs(y - g["y64_" + tag]).max() < 1e-9
+    assert np.abs(lad - g["lad64_" + tag]).max() < 1e-9
+    y32, lad32, bins32 = Oracle(np.float32).rq_spline(g["x"], g["uw"], g["uh"], g["ud"], inverse)
+    assert np.abs(y32 - g["y32_" + tag]).max() < 2e-5
+    assert np.abs(lad32 - g["lad32_" + tag]).max() < 2e-4
+    # tails are the identity, bit for bit (transforms.py:77-78)
+    out = np.abs(g["x"]) > 5.0
+    assert np.array_equal(y32[out], g["x"][out]) and np.all(lad32[out] == 0) and np.all(bins32[out] == -1)
+    assert np.all(bins32[~out] >= 0) and np.all(bins32[~out] <= 9)
+
+
+def test_spline_round_trip():
+    g = load_golden("rq_spline")
+    orc = Oracle(np.float64)
+    y, lad, _ = orc.rq_spline(g["x"], g["uw"], g["uh"], g["ud"], False)
+    xr, lad2, _ = orc.rq_spline(y, g["uw"], g["uh"], g["ud"], True)
+    assert np.abs(xr - g["x"]).max() < 1e-9
+    assert np.abs(lad + lad2).max() < 1e-8
+
+
+def test_spline_argument_checks():
+    with pytest.raises(ValueError):
+        Oracle().rq_spline(np.zeros((1,)), np.zeros((1, 10)), np.zeros((1, 10)), np.zeros((1, 9)), False,
+                           min_bin_width=0.2)
