@@ -1,0 +1,167 @@
+/*
+ * svk.h -- C ABI of the B200-native SMART-Vocoder mel->waveform path (libsvk.so).
+ *
+ * The reference (SMART-TTS/SMART-Vocoder) is pure Python and has no FFI of its own; its de-facto
+ * boundary is the nn.Module surface used by inference.ipynb:64-71,118 and train.py:82-86,273
+ * (SURVEY 8b).  Every entry point below names the reference interface it replaces (file:line in
+ * /root/reference).  smart-vocoder_b200/models.py binds these with ctypes and re-exposes the
+ * reference's `SynthesizerTrn` signature on top.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every function returns an int status (SVK_OK == 0); svk_last_error() gives a thread-local
+ *     message; nothing throws across the ABI;
+ *   - tensors are contiguous fp32 [batch, channels, time] ("NCT"), like the reference;
+ *   - "dev" pointers are CUDA device pointers on the handle's device; `stream` is a cudaStream_t
+ *     passed as void* (0 = legacy default stream).  Device entry points are stream-ordered: no
+ *     host synchronisation and no allocation happen inside them;
+ *   - a handle is bound to one device and is not re-entrant (one call at a time per handle).
+ *   - There is NO CPU fallback: every compute entry point fails with SVK_ERR_CUDA when no
+ *     sm_100 device is usable.
+ */
+#ifndef SVK_H_
+#define SVK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVK_ABI_VERSION 1
+
+#define SVK_OK 0
+#define SVK_IGNORED 1            /* svk_load_tensor: key is dead at inference, accepted and dropped */
+#define SVK_ERR_INVALID (-1)     /* bad argument / shape / configuration                            */
+#define SVK_ERR_CUDA (-2)        /* CUDA runtime error, or no usable device                         */
+#define SVK_ERR_UNKNOWN_KEY (-3) /* svk_load_tensor: key is not part of the checkpoint surface      */
+#define SVK_ERR_STATE (-4)       /* call order (e.g. infer before svk_finalize_weights)             */
+#define SVK_ERR_WORKSPACE (-5)   /* workspace too small                                             */
+
+#define SVK_MAX_UPSAMPLES 8
+#define SVK_MAX_RESBLOCK_KERNELS 8
+#define SVK_RESBLOCK_PAIRS 3
+
+/* Arithmetic of the convolution stacks. */
+#define SVK_PRECISION_FP32 0   /* fp32 FFMA everywhere (the 1e-4 parity path)            */
+
+/*
+ * Effective hyper-parameters of SynthesizerTrn.__init__ (reference models.py:266-314).
+ * Values the reference hard-codes (enc_layers 16, flow_layers 8, n_flows 4, wn_kernel 5,
+ * n_mel 80) are explicit here so the library carries no hidden constants.
+ */
+typedef struct svk_config {
+  int32_t n_mel;
+  int32_t spec_channels;   /* only sizes the dead enc_q.* keys */
+  int32_t inter_channels;
+  int32_t hidden_channels;
+  int32_t enc_layers;
+  int32_t flow_layers;
+  int32_t n_flows;
+  int32_t wn_kernel;
+  int32_t gin_channels;    /* only sizes the dead cond keys */
+  int32_t upsample_initial_channel;
+  int32_t n_upsamples;
+  int32_t upsample_rates[SVK_MAX_UPSAMPLES];
+  int32_t upsample_kernel_sizes[SVK_MAX_UPSAMPLES];
+  int32_t n_resblock_kernels;
+  int32_t resblock_kernel_sizes[SVK_MAX_RESBLOCK_KERNELS];
+  int32_t resblock_dilations[SVK_MAX_RESBLOCK_KERNELS][SVK_RESBLOCK_PAIRS];
+  int32_t precision;       /* SVK_PRECISION_* */
+} svk_config;
+
+typedef struct svk_handle svk_handle;
+
+int svk_abi_version(void);
+const char *svk_last_error(void);
+
+/* ---- lifetime ------------------------------------------------------------------------------
+ * Replaces SynthesizerTrn(...).cuda().eval()  (models.py:266-314, inference.ipynb:64-70). */
+int svk_create(const svk_config *cfg, int device, svk_handle **out);
+void svk_destroy(svk_handle *h);
+
+/* ---- weight ingress ------------------------------------------------------------------------
+ * Replaces utils.load_checkpoint -> model.load_state_dict  (utils.py:18-43).
+ * Called once per state_dict entry with the reference key name ("dec.ups.0.weight_v", ...) and a
+ * HOST fp32 tensor.  Keys that are dead at inference (enc_q.*, *.cond_layer.*, dec.cond.*;
+ * SURVEY App. C) are accepted and return SVK_IGNORED.  Shapes are checked. */
+int svk_load_tensor(svk_handle *h, const char *key, const float *host_data, const int64_t *shape,
+                    int ndim);
+/* Folds weight_norm (w = g * v / ||v||, norm over dims != 0; models.py:125, modules.py:128-145,
+ * 191-206 -- the reference recomputes this 172 times per infer), folds the channel
+ * Flip (modules.py:270-277) of odd couplings into the 1x1 pre/post weights, repacks for the
+ * kernels and uploads.  Fails if a live key was never loaded. */
+int svk_finalize_weights(svk_handle *h);
+/* Number of live (inference-relevant) keys and how many of them have been loaded so far. */
+int svk_weight_status(const svk_handle *h, int *n_live, int *n_loaded);
+
+/* ---- the hot path --------------------------------------------------------------------------
+ * Replaces SynthesizerTrn.infer(x, x_lengths, sid, noise_scale, length_scale, noise_scale_w,
+ * max_len)  (models.py:331-339).  sid / length_scale / noise_scale_w are ignored by the
+ * reference and have no counterpart here.
+ *
+ *   mel      [B, n_mel, T]                 lengths [B] int64
+ *   eps      [B, inter, T]  the N(0,1) draw of models.py:336 (caller draws it: SURVEY F11)
+ *   max_len  <= 0 means None;  T' = max_len>0 ? min(T,max_len) : T
+ *   o        [B, 1, hop*T']                x_mask  [B, 1, T]
+ *   z, z_p, m_p, logs_p  [B, inter, T]     (each may be NULL when the caller does not want it)
+ */
+size_t svk_workspace_bytes(const svk_handle *h, int B, int T, int max_len);
+int svk_infer(svk_handle *h, const float *mel_dev, const int64_t *lengths_dev, const float *eps_dev,
+              float noise_scale, int B, int T, int max_len, float *o_dev, float *x_mask_dev,
+              float *z_dev, float *z_p_dev, float *m_p_dev, float *logs_p_dev, void *workspace_dev,
+              size_t workspace_bytes, void *stream);
+/* Same call with HOST buffers (pinned or pageable): H2D of mel/lengths/eps, infer, D2H of o and
+ * x_mask (and latents when non-NULL), then synchronises.  The library owns and caches the device
+ * buffers.  This is what inference.ipynb:114-118 does around infer (`.cuda()` ... `.cpu()`). */
+int svk_infer_host(svk_handle *h, const float *mel, const int64_t *lengths, const float *eps,
+                   float noise_scale, int B, int T, int max_len, float *o, float *x_mask, float *z,
+                   float *z_p, float *m_p, float *logs_p);
+/* Kernels launched by the most recent svk_infer / module call on this handle. */
+int64_t svk_last_launch_count(const svk_handle *h);
+
+/* ---- module-level entry points (use the handle's folded weights; device pointers) -----------
+ * MelEncoder.forward (models.py:35-47): x_out/m/logs [B,hidden|inter,T], mask [B,1,T]. */
+int svk_mel_encoder(svk_handle *h, const float *mel_dev, const int64_t *lengths_dev, int B, int T,
+                    float *x_out_dev, float *m_dev, float *logs_dev, float *mask_dev,
+                    void *workspace_dev, size_t workspace_bytes, void *stream);
+/* ResidualCouplingBlock.forward(reverse=True) (models.py:73-80), in place on z [B,inter,T]. */
+int svk_flow_reverse(svk_handle *h, float *z_dev, const float *mask_dev, int B, int T,
+                     void *workspace_dev, size_t workspace_bytes, void *stream);
+/* Generator.forward(x, g=None) (models.py:141-160): z [B,inter,L] -> o [B,1,hop*L]. */
+int svk_generator(svk_handle *h, const float *z_dev, int B, int L, float *o_dev, void *workspace_dev,
+                  size_t workspace_bytes, void *stream);
+/* ResBlock1.forward(x) (modules.py:210-223) of dec.resblocks[index]: [B,C,L] -> [B,C,L]. */
+int svk_resblock1(svk_handle *h, int index, const float *x_dev, int B, int L, float *y_dev,
+                  void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* ---- stateless operators (weights passed explicitly, reference layouts; device pointers) ----
+ * nn.Conv1d stride 1: w [Cout,Cin,k], bias may be NULL,
+ * pre_slope != 1 applies leaky_relu(x, pre_slope) to the input first (modules.py:212-217). */
+int svk_conv1d(const float *x_dev, int B, int Cin, int L, const float *w_dev, const float *bias_dev,
+               int Cout, int k, int dilation, int padding, float pre_slope, float *y_dev,
+               void *stream);
+/* nn.ConvTranspose1d (models.py:123-127): w [Cin,Cout,k]. */
+int svk_conv_transpose1d(const float *x_dev, int B, int Cin, int L, const float *w_dev,
+                         const float *bias_dev, int Cout, int k, int stride, int padding,
+                         float pre_slope, float *y_dev, void *stream);
+/* commons.sequence_mask(...).to(float) (commons.py:121-125, models.py:40): mask [B,T]. */
+int svk_sequence_mask(const int64_t *lengths_dev, int B, int T, float *mask_dev, void *stream);
+/* modules.Flip (modules.py:270-277): y[b,c,t] = x[b,C-1-c,t]. Bit-exact copy. */
+int svk_flip(const float *x_dev, int B, int C, int T, float *y_dev, void *stream);
+/* torch.nn.utils.weight_norm fold: v [dim0, inner], g [dim0] -> w. */
+int svk_weight_norm(const float *v_dev, const float *g_dev, int64_t dim0, int64_t inner,
+                    float *w_dev, void *stream);
+/* transforms.piecewise_rational_quadratic_transform(tails='linear') (transforms.py:12-193):
+ * n elements, parameters contiguous per element ([n,nb], [n,nb], [n,nb-1]); bin_dev (may be
+ * NULL) receives the searchsorted bin index, -1 outside [-tail_bound, tail_bound]. */
+int svk_rq_spline(const float *x_dev, const float *uw_dev, const float *uh_dev, const float *ud_dev,
+                  int64_t n, int num_bins, int inverse, float tail_bound, float min_bin_width,
+                  float min_bin_height, float min_derivative, float *y_dev, float *logabsdet_dev,
+                  int32_t *bin_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVK_H_ */

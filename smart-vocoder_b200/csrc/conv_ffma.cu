@@ -1,0 +1,292 @@
+// Generic stride-1 Conv1d (dilated, any odd/even tap count) as an implicit GEMM on the fp32 FFMA
+// pipe, with every element-wise neighbour of the reference graph fused into prologue/epilogue:
+//   prologue : leaky_relu on the input (modules.py:212,216; models.py:147,156), input mask and
+//              max_len truncation (models.py:338), conv zero padding;
+//   epilogue : bias, gated tanh*sigmoid (commons.py:100-107), residual add (modules.py:220),
+//              WN's x=(x+res)*mask / out+=skip split (modules.py:169-175), ResBlock sum and /3
+//              (models.py:150-155), tanh (models.py:158), ConvTranspose1d polyphase store
+//              (models.py:149), channel-reversed store (folded Flip).
+//
+// Tiling: one CTA = 8 warps = (WO channel-warps) x (WT time-warps).  A warp owns 8 output channels
+// x 32*TT time steps; a thread owns 8 channels x TT time steps, time strided by 32 so that every
+// shared-memory read of activations is lane-consecutive (conflict free) and every weight read is a
+// warp-wide broadcast LDS.128.  Input channels are consumed in chunks of 8, double buffered:
+// weights by cp.async (LDGSTS), activations through registers (the prologue is applied there).
+//
+// Roofline: FFMA-bound.  Per (channel, tap) a thread issues 2 LDS.128 + TT LDS.32 for 8*TT FFMA.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "svk_kernels.cuh"
+
+namespace svk {
+
+namespace {
+
+constexpr int CC = 8;       // input channels per smem chunk (== warps per CTA: one staging warp per row)
+constexpr int MAXDIL = 8;   // largest dilation an instance can stage (reference uses 1,3,5)
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+template <int K, int WO, int WT, int TT>
+__global__ void __launch_bounds__(WO* WT * 32, 2) conv_ffma_kernel(const ConvArgs a) {
+  static_assert(WO * WT == CC, "one staging warp per input-channel row of a chunk");
+  constexpr int NT = WO * WT * 32;
+  constexpr int OT = WO * 8;
+  constexpr int TILE_T = WT * 32 * TT;
+  constexpr int NX = (TILE_T + (K - 1) * MAXDIL + 31) / 32;
+  extern __shared__ __align__(16) float smem[];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wo = warp % WO, wt = warp / WO;
+  const int XW = TILE_T + (K - 1) * a.dil;
+  const int XWp = (XW + 3) & ~3;
+  float* xs = smem;                 // [2][CC][XWp]
+  float* ws = smem + 2 * CC * XWp;  // [2][CC*K*OT]
+  const int t0 = blockIdx.x * TILE_T, o0 = blockIdx.y * OT, b = blockIdx.z;
+  const int nchunks = a.Cin / CC;
+
+  float acc[8][TT];
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+#pragma unroll
+    for (int i = 0; i < TT; ++i) acc[e][i] = 0.f;
+
+  float xr[NX];
+  const float* mrow = a.in_mask ? a.in_mask + (size_t)b * a.mask_stride : nullptr;
+  const float slope = a.pre_slope;
+
+  auto load_x = [&](int chunk) {
+    const int gch = a.x_ch_off + chunk * CC + warp;
+    const float* xrow = a.x + ((size_t)b * a.x_C + gch) * a.x_stride;
+#pragma unroll
+    for (int n = 0; n < NX; ++n) {
+      const int tt = lane + 32 * n;
+      const int gpos = t0 - a.pad + tt;
+      float v = 0.f;
+      if (tt < XW && gpos >= 0 && gpos < a.Lin) {
+        v = __ldg(xrow + gpos);
+        v = v > 0.f ? v : v * slope;
+        if (mrow) v *= __ldg(mrow + gpos);
+      }
+      xr[n] = v;
+    }
+  };
+  auto store_x = [&](int buf) {
+    float* row = xs + (buf * CC + warp) * XWp;
+#pragma unroll
+    for (int n = 0; n < NX; ++n) {
+      const int tt = lane + 32 * n;
+      if (tt < XWp) row[tt] = xr[n];
+    }
+  };
+  auto load_w = [&](int chunk, int buf) {
+    constexpr int V4 = OT / 4;
+    constexpr int TOTAL = CC * K * V4;
+    const float* src = a.wp + (size_t)chunk * CC * K * a.CoutPad + o0;
+    float* dst = ws + buf * (CC * K * OT);
+    for (int idx = tid; idx < TOTAL; idx += NT) {
+      const int row = idx / V4, v4 = idx % V4;
+      cp_async16(dst + row * OT + 4 * v4, src + (size_t)row * a.CoutPad + 4 * v4);
+    }
+  };
+
+  load_x(0);
+  load_w(0, 0);
+  store_x(0);
+  cp_async_commit_wait_all();
+  __syncthreads();
+
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int cur = ch & 1;
+    const bool more = ch + 1 < nchunks;
+    if (more) {
+      load_x(ch + 1);
+      load_w(ch + 1, cur ^ 1);
+    }
+    const float* xb = xs + cur * CC * XWp + wt * (32 * TT) + lane;
+    const float* wb = ws + cur * (CC * K * OT) + wo * 8;
+#pragma unroll 1
+    for (int c = 0; c < CC; ++c) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const float4 w0 = *reinterpret_cast<const float4*>(wb + (c * K + j) * OT);
+        const float4 w1 = *reinterpret_cast<const float4*>(wb + (c * K + j) * OT + 4);
+        const float* xp = xb + c * XWp + j * a.dil;
+        float xv[TT];
+#pragma unroll
+        for (int i = 0; i < TT; ++i) xv[i] = xp[32 * i];
+#pragma unroll
+        for (int i = 0; i < TT; ++i) {
+          acc[0][i] = fmaf(w0.x, xv[i], acc[0][i]);
+          acc[1][i] = fmaf(w0.y, xv[i], acc[1][i]);
+          acc[2][i] = fmaf(w0.z, xv[i], acc[2][i]);
+          acc[3][i] = fmaf(w0.w, xv[i], acc[3][i]);
+          acc[4][i] = fmaf(w1.x, xv[i], acc[4][i]);
+          acc[5][i] = fmaf(w1.y, xv[i], acc[5][i]);
+          acc[6][i] = fmaf(w1.z, xv[i], acc[6][i]);
+          acc[7][i] = fmaf(w1.w, xv[i], acc[7][i]);
+        }
+      }
+    }
+    if (more) {
+      store_x(cur ^ 1);
+      cp_async_commit_wait_all();
+    }
+    __syncthreads();
+  }
+
+  // ------------------------------------------------------------------ epilogue
+  const int ob = o0 + wo * 8;  // first (virtual) output channel of this thread
+  const int tb = t0 + wt * (32 * TT) + lane;
+  if (ob >= a.Cout) return;
+  const float* omask = a.out_mask ? a.out_mask + (size_t)b * a.mask_stride : nullptr;
+
+  if (a.mode == MODE_GATE) {
+    // packed pairs: e<4 -> tanh half of channel 4*grp+e, e>=4 -> sigmoid half of the same channel
+    const int cbase = (ob >> 3) * 4;
+    const EpiDesc& d = a.e[0];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float bt = __ldg(a.bias + ob + e), bs = __ldg(a.bias + ob + e + 4);
+      float* yrow = d.y + ((size_t)b * d.C + d.ch_off + cbase + e) * a.y_stride;
+#pragma unroll
+      for (int i = 0; i < TT; ++i) {
+        const int t = tb + 32 * i;
+        if (t < a.Lout) yrow[t] = tanhf(acc[e][i] + bt) * sigmoidf_(acc[e + 4][i] + bs);
+      }
+    }
+    return;
+  }
+
+  if (a.mode == MODE_SHUFFLE) {
+    const EpiDesc& d = a.e[0];
+    const int s = a.shuf_s;
+    if ((s & 7) == 0 && (a.shuf_p & 3) == 0) {
+      // 8 consecutive virtual channels = 8 consecutive output samples of one channel
+      const int co = ob / s, r0 = ob % s;
+      float* yrow = d.y + ((size_t)b * d.C + d.ch_off + co) * a.y_stride;
+      float bv[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) bv[e] = __ldg(a.bias + ob + e);
+#pragma unroll
+      for (int i = 0; i < TT; ++i) {
+        const int q = tb + 32 * i;
+        if (q >= a.Lout) continue;
+        const int t = s * q + r0 - a.shuf_p;
+        if (t >= 0 && t + 3 < a.shuf_Lout)
+          *reinterpret_cast<float4*>(yrow + t) =
+              make_float4(acc[0][i] + bv[0], acc[1][i] + bv[1], acc[2][i] + bv[2], acc[3][i] + bv[3]);
+        if (t + 4 >= 0 && t + 7 < a.shuf_Lout)
+          *reinterpret_cast<float4*>(yrow + t + 4) =
+              make_float4(acc[4][i] + bv[4], acc[5][i] + bv[5], acc[6][i] + bv[6], acc[7][i] + bv[7]);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int o = ob + e;
+        if (o >= a.Cout) break;
+        const int co = o / s, r = o % s;
+        const float bv = __ldg(a.bias + o);
+        float* yrow = d.y + ((size_t)b * d.C + d.ch_off + co) * a.y_stride;
+#pragma unroll
+        for (int i = 0; i < TT; ++i) {
+          const int q = tb + 32 * i;
+          const int t = s * q + r - a.shuf_p;
+          if (q < a.Lout && t >= 0 && t < a.shuf_Lout) yrow[t] = acc[e][i] + bv;
+        }
+      }
+    }
+    return;
+  }
+
+  // MODE_STORE (split is a multiple of 8, so the side is uniform per thread)
+  const int side = ob < a.split ? 0 : 1;
+  const EpiDesc d = a.e[side];
+  const int rel0 = ob - (side ? a.split : 0);
+  const bool use_mask = d.use_mask && omask;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int o = ob + e;
+    if (o >= a.Cout) break;
+    const float bv = __ldg(a.bias + o);
+    const size_t rowoff = ((size_t)b * d.C + d.ch_off + d.ch_sign * (rel0 + e)) * a.y_stride;
+    const float* rrow = d.res ? d.res + rowoff : nullptr;
+    const float* arow = d.acc_in ? d.acc_in + rowoff : nullptr;
+    float* yrow = d.y + rowoff;
+#pragma unroll
+    for (int i = 0; i < TT; ++i) {
+      const int t = tb + 32 * i;
+      if (t >= a.Lout) continue;
+      float v = acc[e][i] + bv;
+      if (rrow) v += rrow[t];
+      if (arow) v += arow[t];
+      if (a.post_div != 1.0f) v = v / a.post_div;
+      if (use_mask) v *= omask[t];
+      if (a.act_tanh) v = tanhf(v);
+      yrow[t] = v;
+    }
+  }
+}
+
+template <int K, int WO, int WT, int TT>
+cudaError_t launch_instance(const ConvArgs& a, cudaStream_t stream) {
+  constexpr int OT = WO * 8;
+  constexpr int TILE_T = WT * 32 * TT;
+  if (a.dil > MAXDIL || a.dil < 1) return cudaErrorInvalidValue;
+  if (a.Cin % CC != 0 || a.CoutPad % OT != 0) return cudaErrorInvalidValue;
+  const int XWp = (TILE_T + (K - 1) * a.dil + 3) & ~3;
+  const size_t smem = sizeof(float) * 2 * (size_t)(CC * XWp + CC * K * OT);
+  static size_t configured[64] = {0};  // per device: opt-in dynamic smem already granted
+  auto kern = conv_ffma_kernel<K, WO, WT, TT>;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (smem > configured[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured[dev & 63] = smem;
+  }
+  dim3 grid((a.Lout + TILE_T - 1) / TILE_T, (a.Cout + OT - 1) / OT, a.B);
+  if (grid.x == 0 || grid.y == 0 || grid.z == 0) return cudaSuccess;
+  kern<<<grid, WO * WT * 32, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+template <int K>
+cudaError_t launch_k(const ConvArgs& a, cudaStream_t stream) {
+  const int ot = conv_ffma_channel_tile(a.Cout);
+  if (ot == 64) return launch_instance<K, 8, 1, 8>(a, stream);
+  if (ot == 32) return launch_instance<K, 4, 2, 8>(a, stream);
+  return launch_instance<K, 1, 8, 4>(a, stream);
+}
+
+}  // namespace
+
+int conv_ffma_channel_tile(int cout) { return cout >= 64 ? 64 : (cout >= 32 ? 32 : 8); }
+
+bool conv_ffma_supports_k(int k) {
+  return k == 1 || k == 2 || k == 3 || k == 5 || k == 7 || k == 9 || k == 11;
+}
+
+cudaError_t launch_conv_ffma(const ConvArgs& a, cudaStream_t stream) {
+  switch (a.K) {
+    case 1: return launch_k<1>(a, stream);
+    case 2: return launch_k<2>(a, stream);
+    case 3: return launch_k<3>(a, stream);
+    case 5: return launch_k<5>(a, stream);
+    case 7: return launch_k<7>(a, stream);
+    case 9: return launch_k<9>(a, stream);
+    case 11: return launch_k<11>(a, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace svk

@@ -1,0 +1,206 @@
+// Small memory-bound kernels of the path: sequence mask, latent sampling, Flip, weight-norm fold,
+// and the rational-quadratic spline operator.  All are one pass over their operands, coalesced
+// along time, grid sized in multiples of the SM count where the problem is large enough.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "svk_kernels.cuh"
+
+namespace svk {
+namespace {
+
+constexpr int EW_THREADS = 256;
+
+inline int ew_blocks(int64_t n) {
+  int64_t b = (n + EW_THREADS - 1) / EW_THREADS;
+  const int64_t cap = 148 * 16;  // grid-stride beyond 16 CTAs per SM
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// commons.sequence_mask (commons.py:121-125) + .to(x.dtype) (models.py:40)
+__global__ void sequence_mask_kernel(const int64_t* __restrict__ lengths, int B, int T,
+                                     float* __restrict__ mask) {
+  const int64_t n = (int64_t)B * T;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / T);
+    const int64_t t = i - (int64_t)b * T;
+    mask[i] = t < lengths[b] ? 1.0f : 0.0f;
+  }
+}
+
+// modules.Flip (modules.py:272): torch.flip(x, [1])
+__global__ void flip_kernel(const float* __restrict__ x, int B, int C, int T, float* __restrict__ y) {
+  const int64_t n = (int64_t)B * C * T;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = i % T;
+    const int64_t bc = i / T;
+    const int64_t c = bc % C, b = bc / C;
+    y[i] = x[(b * C + (C - 1 - c)) * T + t];
+  }
+}
+
+// models.py:336: z_p = m_p + randn * exp(logs_p) * noise_scale  (randn injected as eps).
+// Evaluated in the reference's order: ((eps * exp(logs)) * noise_scale) + m.
+__global__ void sample_kernel(const float* __restrict__ m, const float* __restrict__ logs,
+                              const float* __restrict__ eps, float noise_scale, float* __restrict__ z_p,
+                              float* __restrict__ z, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = __fadd_rn(m[i], __fmul_rn(__fmul_rn(eps[i], expf(logs[i])), noise_scale));
+    if (z_p) z_p[i] = v;
+    if (z) z[i] = v;
+  }
+}
+
+// weight_norm fold: one CTA per dim-0 slice.
+__global__ void weight_norm_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                   int64_t inner, float* __restrict__ w) {
+  __shared__ float red[32];
+  const int64_t i = blockIdx.x;
+  const float* vr = v + i * inner;
+  float s = 0.f;
+  for (int64_t j = threadIdx.x; j < inner; j += blockDim.x) s = fmaf(vr[j], vr[j], s);
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  const float scale = g[i] / sqrtf(red[0]);
+  for (int64_t j = threadIdx.x; j < inner; j += blockDim.x) w[i * inner + j] = vr[j] * scale;
+}
+
+// transforms.py:12-193, one thread per element; parameters are read once (29 floats / element).
+constexpr int MAX_BINS = 32;
+
+__global__ void rq_spline_kernel(const float* __restrict__ x, const float* __restrict__ uw,
+                                 const float* __restrict__ uh, const float* __restrict__ ud, int64_t n,
+                                 int nb, int inverse, float tail_bound, float min_bw, float min_bh,
+                                 float min_d, float* __restrict__ y, float* __restrict__ lad,
+                                 int32_t* __restrict__ bins) {
+  const float left = -tail_bound, right = tail_bound;
+  // transforms.py:72-75 (computed in double by numpy, then stored into an fp32 tensor)
+  const float cst = (float)log(exp(1.0 - (double)min_d) - 1.0);
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const float xin = x[e];
+    if (!(xin >= left && xin <= right)) {  // transforms.py:65-78: identity tails
+      y[e] = xin;
+      lad[e] = 0.f;
+      if (bins) bins[e] = -1;
+      continue;
+    }
+    float cw[MAX_BINS + 1], chh[MAX_BINS + 1];
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const float* pu = (pass == 0 ? uw : uh) + e * nb;
+      float* cum = pass == 0 ? cw : chh;
+      const float minb = pass == 0 ? min_bw : min_bh;
+      float mx = pu[0];
+      for (int i = 1; i < nb; ++i) mx = fmaxf(mx, pu[i]);
+      float sum = 0.f;
+      for (int i = 0; i < nb; ++i) {
+        cum[i + 1] = expf(pu[i] - mx);
+        sum += cum[i + 1];
+      }
+      const float scale = (float)(1.0 - (double)minb * nb);
+      float run = 0.f;
+      for (int i = 0; i < nb; ++i) {
+        const float sm = cum[i + 1] / sum;
+        run = __fadd_rn(run, __fadd_rn(minb, __fmul_rn(scale, sm)));
+        cum[i + 1] = __fadd_rn(__fmul_rn(right - left, run), left);
+      }
+      cum[0] = left;
+      cum[nb] = right;
+    }
+    const float* knots = inverse ? chh : cw;
+    int bin = -1;
+    for (int i = 0; i <= nb; ++i) {
+      float kn = knots[i];
+      if (i == nb) kn = __fadd_rn(kn, 1e-6f);
+      bin += (xin >= kn) ? 1 : 0;
+    }
+    if (bins) bins[e] = bin;
+    const int bi = bin < 0 ? 0 : (bin > nb - 1 ? nb - 1 : bin);
+    const float in_cw = cw[bi], in_w = cw[bi + 1] - cw[bi];
+    const float in_ch = chh[bi], in_h = chh[bi + 1] - chh[bi];
+    const float delta = in_h / in_w;
+    const float* pd = ud + e * (nb - 1);
+    const float u0 = bi == 0 ? cst : pd[bi - 1];
+    const float u1 = bi + 1 == nb ? cst : pd[bi];
+    const float d0 = min_d + (u0 > 20.f ? u0 : log1pf(expf(u0)));
+    const float d1 = min_d + (u1 > 20.f ? u1 : log1pf(expf(u1)));
+    const float s2 = d0 + d1 - 2.f * delta;
+    if (inverse) {  // transforms.py:152-177
+      const float dy = xin - in_ch;
+      const float a = dy * s2 + in_h * (delta - d0);
+      const float b = in_h * d0 - dy * s2;
+      const float c = -delta * dy;
+      const float disc = b * b - 4.f * a * c;
+      const float root = (2.f * c) / (-b - sqrtf(disc));
+      y[e] = root * in_w + in_cw;
+      const float tomt = root * (1.f - root);
+      const float den = delta + s2 * tomt;
+      const float num =
+          delta * delta * (d1 * root * root + 2.f * delta * tomt + d0 * (1.f - root) * (1.f - root));
+      lad[e] = -(logf(num) - 2.f * logf(den));
+    } else {  // transforms.py:178-193
+      const float theta = (xin - in_cw) / in_w;
+      const float tomt = theta * (1.f - theta);
+      const float numr = in_h * (delta * theta * theta + d0 * tomt);
+      const float den = delta + s2 * tomt;
+      y[e] = in_ch + numr / den;
+      const float num =
+          delta * delta * (d1 * theta * theta + 2.f * delta * tomt + d0 * (1.f - theta) * (1.f - theta));
+      lad[e] = logf(num) - 2.f * logf(den);
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_sequence_mask(const int64_t* lengths, int B, int T, float* mask, cudaStream_t s) {
+  if ((int64_t)B * T == 0) return cudaSuccess;
+  sequence_mask_kernel<<<ew_blocks((int64_t)B * T), EW_THREADS, 0, s>>>(lengths, B, T, mask);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_flip(const float* x, int B, int C, int T, float* y, cudaStream_t s) {
+  const int64_t n = (int64_t)B * C * T;
+  if (n == 0) return cudaSuccess;
+  flip_kernel<<<ew_blocks(n), EW_THREADS, 0, s>>>(x, B, C, T, y);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sample(const float* m, const float* logs, const float* eps, float noise_scale,
+                          float* z_p, float* z, int64_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  sample_kernel<<<ew_blocks(n), EW_THREADS, 0, s>>>(m, logs, eps, noise_scale, z_p, z, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_weight_norm(const float* v, const float* g, int64_t dim0, int64_t inner, float* w,
+                               cudaStream_t s) {
+  if (dim0 == 0) return cudaSuccess;
+  weight_norm_kernel<<<(unsigned)dim0, 256, 0, s>>>(v, g, inner, w);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rq_spline(const float* x, const float* uw, const float* uh, const float* ud,
+                             int64_t n, int nb, int inverse, float tail_bound, float min_bw,
+                             float min_bh, float min_d, float* y, float* lad, int32_t* bins,
+                             cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  if (nb < 1 || nb > MAX_BINS) return cudaErrorInvalidValue;
+  rq_spline_kernel<<<ew_blocks(n), 128, 0, s>>>(x, uw, uh, ud, n, nb, inverse, tail_bound, min_bw,
+                                                min_bh, min_d, y, lad, bins);
+  return cudaGetLastError();
+}
+
+}  // namespace svk

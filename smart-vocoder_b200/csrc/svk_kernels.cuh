@@ -1,0 +1,77 @@
+// Internal kernel interfaces of libsvk (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace svk {
+
+// One side of a (possibly split) epilogue: where an output-channel range is written and what is
+// folded into it.  Used e.g. by WN's res_skip conv (modules.py:169-175): channels [0,H) update
+// x = (x + r) * mask in place, channels [H,2H) accumulate out += r.
+struct EpiDesc {
+  const float* res;     // added element-wise (same [B, C, L] geometry as y), may be null
+  const float* acc_in;  // added element-wise after res (running sum), may be null
+  float* y;             // destination tensor [B, C, y_stride]
+  int C;                // channels of the destination tensor
+  int ch_off;           // destination channel = ch_off + ch_sign * (o - first o of this side)
+  int ch_sign;          // +1, or -1 to write channels in reversed order (folded Flip)
+  int use_mask;         // multiply by out_mask[b, t]
+};
+
+enum ConvMode : int {
+  MODE_STORE = 0,    // plain conv epilogue
+  MODE_GATE = 1,     // tanh(a[c]) * sigmoid(a[c+H]) (commons.py:100-107); packed channel pairs
+  MODE_SHUFFLE = 2,  // ConvTranspose1d polyphase store
+};
+
+// Generic stride-1 Conv1d as implicit GEMM on the fp32 FFMA pipe.
+//   y[b,o,t] = bias[o] + sum_c sum_j wp[c][j][o] * f(x[b, x_ch_off + c, t - pad + j*dil])
+// with f = leaky_relu(pre_slope) then * in_mask.  Weights are pre-packed [Cin][K][CoutPad].
+struct ConvArgs {
+  const float* x;
+  int x_C;          // channels of the tensor x lives in
+  int x_ch_off;     // first input channel used
+  int x_stride;     // row stride in floats (>= Lin)
+  int Lin;          // logical input length (zero padding outside [0, Lin))
+  const float* in_mask;  // [B, mask_stride] or null
+  int mask_stride;
+  float pre_slope;  // 1.0f = none
+  const float* wp;
+  const float* bias;  // [CoutPad] (zeros when the layer has no bias)
+  int Cin;
+  int Cout;     // logical output channels (virtual channels for GATE / SHUFFLE)
+  int CoutPad;  // packed row length (multiple of the CTA's channel tile)
+  int K;
+  int dil;
+  int pad;
+  int Lout;      // outputs computed per row (virtual positions q for SHUFFLE)
+  int y_stride;  // row stride of destination tensors
+  int mode;
+  int split;     // o < split -> e[0], else e[1]
+  EpiDesc e[2];
+  float post_div;  // 1.0f = none
+  int act_tanh;
+  const float* out_mask;  // [B, mask_stride] or null
+  int shuf_s, shuf_p, shuf_Lout;  // MODE_SHUFFLE: t = s*q + r - p, valid in [0, shuf_Lout)
+  int B;
+};
+
+// Channel tile (in output channels) the FFMA kernel will use for a layer with `cout` outputs.
+int conv_ffma_channel_tile(int cout);
+// true when a kernel instance exists for this tap count
+bool conv_ffma_supports_k(int k);
+cudaError_t launch_conv_ffma(const ConvArgs& a, cudaStream_t stream);
+
+// elementwise / small kernels
+cudaError_t launch_sequence_mask(const int64_t* lengths, int B, int T, float* mask, cudaStream_t s);
+cudaError_t launch_flip(const float* x, int B, int C, int T, float* y, cudaStream_t s);
+cudaError_t launch_sample(const float* m, const float* logs, const float* eps, float noise_scale,
+                          float* z_p, float* z, int64_t n, cudaStream_t s);
+cudaError_t launch_weight_norm(const float* v, const float* g, int64_t dim0, int64_t inner, float* w,
+                               cudaStream_t s);
+cudaError_t launch_rq_spline(const float* x, const float* uw, const float* uh, const float* ud,
+                             int64_t n, int nb, int inverse, float tail_bound, float min_bw,
+                             float min_bh, float min_d, float* y, float* lad, int32_t* bins,
+                             cudaStream_t s);
+
+}  // namespace svk

@@ -1,0 +1,874 @@
+// Host side of libsvk: checkpoint-key surface, weight folding / packing, workspace planning and
+// the launch sequence of SynthesizerTrn.infer (reference models.py:331-339).  Everything numeric
+// runs in the CUDA kernels of conv_ffma.cu / elementwise.cu; there is no CPU compute fallback.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <array>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/svk.h"
+#include "svk_kernels.cuh"
+
+using namespace svk;
+
+// ------------------------------------------------------------------------------------- errors
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+// used by svk_ops.cu, which shares this translation unit's thread-local error string
+extern "C" int svk__set_error(int code, const char* msg) { return fail(code, "%s", msg); }
+
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return fail(SVK_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                  __LINE__);                                                                  \
+  } while (0)
+
+#define SVK_TRY(expr)       \
+  do {                      \
+    int _s = (expr);        \
+    if (_s < 0) return _s;  \
+  } while (0)
+
+// ------------------------------------------------------------------------------------ structs
+namespace {
+
+struct KeySpec {
+  std::vector<int64_t> shape;
+  bool dead;
+};
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+};
+
+// A layer packed for conv_ffma: weights [Cin][K][CoutPad] + bias [CoutPad] inside the device blob.
+struct PackedConv {
+  size_t w_off = 0, b_off = 0;  // float offsets into the blob
+  int Cin = 0, Cout = 0, CoutPad = 0, K = 0;
+  // ConvTranspose1d only
+  int s = 0, p = 0, k = 0, pad_virtual = 0;
+};
+
+struct FlowLayers {
+  PackedConv pre, post;
+  std::vector<PackedConv> in, rs;
+  int orient = 0;  // 1: this coupling sees the channel-reversed view (odd number of Flips before it)
+};
+
+struct ResBlock {
+  PackedConv c1[SVK_RESBLOCK_PAIRS], c2[SVK_RESBLOCK_PAIRS];
+  int k = 0, C = 0;
+  int dil[SVK_RESBLOCK_PAIRS] = {1, 1, 1};
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct svk_handle {
+  svk_config cfg;
+  int device = 0;
+  std::vector<std::string> key_order;
+  std::map<std::string, KeySpec> spec;
+  std::map<std::string, HostTensor> raw;
+  int n_live = 0;
+  bool finalized = false;
+
+  float* d_blob = nullptr;
+  size_t blob_floats = 0;
+  std::vector<float> h_blob;  // staging while packing
+
+  PackedConv pre_enc, proj, conv_pre, conv_post;
+  std::vector<PackedConv> enc_in, enc_rs, ups;
+  std::vector<FlowLayers> flows;
+  std::vector<ResBlock> resblocks;
+
+  int64_t launches = 0;
+
+  // svk_infer_host state
+  cudaStream_t host_stream = nullptr;
+  void* host_dev = nullptr;
+  size_t host_dev_bytes = 0;
+
+  int hop() const {
+    int h = 1;
+    for (int i = 0; i < cfg.n_upsamples; ++i) h *= cfg.upsample_rates[i];
+    return h;
+  }
+  int stage_channels(int i) const { return cfg.upsample_initial_channel >> (i + 1); }
+};
+
+// ------------------------------------------------------------------------ checkpoint key surface
+namespace {
+
+void add_key(svk_handle* h, const std::string& key, std::vector<int64_t> shape) {
+  const bool dead = key.rfind("enc_q.", 0) == 0 || key.find(".cond_layer.") != std::string::npos ||
+                    key.rfind("dec.cond.", 0) == 0;
+  h->key_order.push_back(key);
+  h->spec[key] = KeySpec{std::move(shape), dead};
+  if (!dead) h->n_live++;
+}
+
+void add_wn_keys(svk_handle* h, const std::string& prefix, int hidden, int kernel, int n_layers, int gin) {
+  for (int i = 0; i < n_layers; ++i) {
+    const std::string p = prefix + ".in_layers." + std::to_string(i);
+    add_key(h, p + ".bias", {2 * hidden});
+    add_key(h, p + ".weight_g", {2 * hidden, 1, 1});
+    add_key(h, p + ".weight_v", {2 * hidden, hidden, kernel});
+  }
+  for (int i = 0; i < n_layers; ++i) {
+    const int rs = i < n_layers - 1 ? 2 * hidden : hidden;
+    const std::string p = prefix + ".res_skip_layers." + std::to_string(i);
+    add_key(h, p + ".bias", {rs});
+    add_key(h, p + ".weight_g", {rs, 1, 1});
+    add_key(h, p + ".weight_v", {rs, hidden, 1});
+  }
+  if (gin != 0) {
+    const std::string p = prefix + ".cond_layer";
+    const int c = 2 * hidden * n_layers;
+    add_key(h, p + ".bias", {c});
+    add_key(h, p + ".weight_g", {c, 1, 1});
+    add_key(h, p + ".weight_v", {c, gin, 1});
+  }
+}
+
+// Same ordered surface as SynthesizerTrn(...).state_dict() of the reference.
+void build_key_spec(svk_handle* h) {
+  const svk_config& c = h->cfg;
+  const int H = c.hidden_channels, C = c.inter_channels, gin = c.gin_channels, U = c.upsample_initial_channel;
+  add_wn_keys(h, "enc_p.encoder", H, c.wn_kernel, c.enc_layers, gin);
+  add_key(h, "enc_p.pre_enc.weight", {H, c.n_mel, 1});
+  add_key(h, "enc_p.pre_enc.bias", {H});
+  add_key(h, "enc_p.proj.weight", {2 * C, H, 1});
+  add_key(h, "enc_p.proj.bias", {2 * C});
+  add_key(h, "dec.conv_pre.weight", {U, C, 7});
+  add_key(h, "dec.conv_pre.bias", {U});
+  for (int i = 0; i < c.n_upsamples; ++i) {
+    const int cin = U >> i, cout = U >> (i + 1);
+    const std::string p = "dec.ups." + std::to_string(i);
+    add_key(h, p + ".bias", {cout});
+    add_key(h, p + ".weight_g", {cin, 1, 1});
+    add_key(h, p + ".weight_v", {cin, cout, c.upsample_kernel_sizes[i]});
+  }
+  for (int i = 0; i < c.n_upsamples; ++i) {
+    const int ch = U >> (i + 1);
+    for (int j = 0; j < c.n_resblock_kernels; ++j) {
+      const int n = i * c.n_resblock_kernels + j;
+      for (const char* grp : {"convs1", "convs2"})
+        for (int l = 0; l < SVK_RESBLOCK_PAIRS; ++l) {
+          const std::string p = "dec.resblocks." + std::to_string(n) + "." + grp + "." + std::to_string(l);
+          add_key(h, p + ".bias", {ch});
+          add_key(h, p + ".weight_g", {ch, 1, 1});
+          add_key(h, p + ".weight_v", {ch, ch, c.resblock_kernel_sizes[j]});
+        }
+    }
+  }
+  add_key(h, "dec.conv_post.weight", {1, U >> c.n_upsamples, 7});
+  if (gin != 0) {
+    add_key(h, "dec.cond.weight", {U, gin, 1});
+    add_key(h, "dec.cond.bias", {U});
+  }
+  add_key(h, "enc_q.pre.weight", {H, c.spec_channels, 1});
+  add_key(h, "enc_q.pre.bias", {H});
+  add_wn_keys(h, "enc_q.enc", H, 5, 16, gin);
+  add_key(h, "enc_q.proj.weight", {2 * C, H, 1});
+  add_key(h, "enc_q.proj.bias", {2 * C});
+  for (int f = 0; f < c.n_flows; ++f) {
+    const std::string p = "flow.flows." + std::to_string(2 * f);
+    add_key(h, p + ".pre.weight", {H, C / 2, 1});
+    add_key(h, p + ".pre.bias", {H});
+    add_wn_keys(h, p + ".enc", H, c.wn_kernel, c.flow_layers, gin);
+    add_key(h, p + ".post.weight", {C / 2, H, 1});
+    add_key(h, p + ".post.bias", {C / 2});
+  }
+}
+
+// ------------------------------------------------------------------------------ fold and pack
+struct Folded {
+  std::vector<float> w;  // [d0][d1][k]
+  std::vector<float> b;  // may be empty
+  int d0 = 0, d1 = 0, k = 0;
+};
+
+// weight_norm fold: norm over dims != 0, accumulated in double, rounded once.
+int fold_layer(svk_handle* h, const std::string& prefix, Folded* out) {
+  auto itv = h->raw.find(prefix + ".weight_v");
+  const HostTensor* wt = nullptr;
+  if (itv != h->raw.end()) {
+    auto itg = h->raw.find(prefix + ".weight_g");
+    if (itg == h->raw.end()) return fail(SVK_ERR_STATE, "missing %s.weight_g", prefix.c_str());
+    const HostTensor& v = itv->second;
+    out->d0 = (int)v.shape[0], out->d1 = (int)v.shape[1], out->k = (int)v.shape[2];
+    const size_t inner = (size_t)out->d1 * out->k;
+    out->w.resize(v.data.size());
+    for (int i = 0; i < out->d0; ++i) {
+      double s = 0;
+      for (size_t j = 0; j < inner; ++j) s += (double)v.data[i * inner + j] * (double)v.data[i * inner + j];
+      const float scale = (float)((double)itg->second.data[i] / sqrt(s));
+      for (size_t j = 0; j < inner; ++j) out->w[i * inner + j] = v.data[i * inner + j] * scale;
+    }
+  } else {
+    auto itw = h->raw.find(prefix + ".weight");
+    if (itw == h->raw.end()) return fail(SVK_ERR_STATE, "missing %s.weight", prefix.c_str());
+    wt = &itw->second;
+    out->d0 = (int)wt->shape[0], out->d1 = (int)wt->shape[1], out->k = (int)wt->shape[2];
+    out->w = wt->data;
+  }
+  auto itb = h->raw.find(prefix + ".bias");
+  if (itb != h->raw.end()) out->b = itb->second.data;
+  return SVK_OK;
+}
+
+// Reserve blob space and write a virtual conv: wv(o,c,j), bv(o) -> [Cin][K][CoutPad] + [CoutPad].
+template <class WF, class BF>
+PackedConv pack_virtual(svk_handle* h, int Cin, int Cout, int K, WF wv, BF bv) {
+  PackedConv pc;
+  pc.Cin = Cin, pc.Cout = Cout, pc.K = K;
+  const int ot = conv_ffma_channel_tile(Cout);
+  pc.CoutPad = (Cout + ot - 1) / ot * ot;
+  pc.w_off = align_up(h->h_blob.size(), 64);
+  h->h_blob.resize(pc.w_off + (size_t)Cin * K * pc.CoutPad, 0.f);
+  for (int c = 0; c < Cin; ++c)
+    for (int j = 0; j < K; ++j)
+      for (int o = 0; o < Cout; ++o) h->h_blob[pc.w_off + ((size_t)c * K + j) * pc.CoutPad + o] = wv(o, c, j);
+  pc.b_off = align_up(h->h_blob.size(), 64);
+  h->h_blob.resize(pc.b_off + pc.CoutPad, 0.f);
+  for (int o = 0; o < Cout; ++o) h->h_blob[pc.b_off + o] = bv(o);
+  return pc;
+}
+
+PackedConv pack_plain(svk_handle* h, const Folded& f) {
+  return pack_virtual(
+      h, f.d1, f.d0, f.k, [&](int o, int c, int j) { return f.w[((size_t)o * f.d1 + c) * f.k + j]; },
+      [&](int o) { return f.b.empty() ? 0.f : f.b[o]; });
+}
+
+// WN in_layer: interleave tanh/sigmoid halves so one thread owns both halves of 4 channels.
+PackedConv pack_gate(svk_handle* h, const Folded& f, int H) {
+  auto real = [H](int o) {
+    const int grp = o >> 3, e = o & 7;
+    return e < 4 ? 4 * grp + e : H + 4 * grp + (e - 4);
+  };
+  return pack_virtual(
+      h, f.d1, f.d0, f.k, [&](int o, int c, int j) { return f.w[((size_t)real(o) * f.d1 + c) * f.k + j]; },
+      [&](int o) { return f.b.empty() ? 0.f : f.b[real(o)]; });
+}
+
+// ConvTranspose1d as a K'=ceil(k/s)-tap conv over the input producing s*Cout virtual channels
+// (polyphase form): o' = co*s + r, tap jj <-> x[q-(K'-1)+jj], j = r + (K'-1-jj)*s.
+PackedConv pack_transposed(svk_handle* h, const Folded& f, int s, int p) {
+  const int Cin = f.d0, Cout = f.d1, k = f.k;
+  const int Kv = (k + s - 1) / s;
+  PackedConv pc = pack_virtual(
+      h, Cin, Cout * s, Kv,
+      [&](int o, int c, int jj) {
+        const int co = o / s, r = o % s;
+        const int j = r + (Kv - 1 - jj) * s;
+        return j < k ? f.w[((size_t)c * Cout + co) * k + j] : 0.f;
+      },
+      [&](int o) { return f.b.empty() ? 0.f : f.b[o / s]; });
+  pc.s = s, pc.p = p, pc.k = k, pc.pad_virtual = Kv - 1;
+  return pc;
+}
+
+int pack_wn(svk_handle* h, const std::string& prefix, int n_layers, std::vector<PackedConv>* in,
+            std::vector<PackedConv>* rs) {
+  const int H = h->cfg.hidden_channels;
+  for (int i = 0; i < n_layers; ++i) {
+    Folded f;
+    SVK_TRY(fold_layer(h, prefix + ".in_layers." + std::to_string(i), &f));
+    in->push_back(pack_gate(h, f, H));
+    Folded g;
+    SVK_TRY(fold_layer(h, prefix + ".res_skip_layers." + std::to_string(i), &g));
+    rs->push_back(pack_plain(h, g));
+  }
+  return SVK_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ lifetime
+extern "C" int svk_abi_version(void) { return SVK_ABI_VERSION; }
+extern "C" const char* svk_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int svk_create(const svk_config* cfg, int device, svk_handle** out) {
+  if (!cfg || !out) return fail(SVK_ERR_INVALID, "svk_create: null argument");
+  *out = nullptr;
+  const svk_config& c = *cfg;
+  // reference asserts: modules.py:308 (channels % 2), modules.py:114 (odd WN kernel)
+  if (c.inter_channels <= 0 || c.inter_channels % 2) return fail(SVK_ERR_INVALID, "channels should be divisible by 2");
+  if (c.wn_kernel % 2 != 1) return fail(SVK_ERR_INVALID, "WN kernel_size must be odd");
+  if (c.n_upsamples < 1 || c.n_upsamples > SVK_MAX_UPSAMPLES) return fail(SVK_ERR_INVALID, "n_upsamples out of range");
+  if (c.n_resblock_kernels < 1 || c.n_resblock_kernels > SVK_MAX_RESBLOCK_KERNELS)
+    return fail(SVK_ERR_INVALID, "n_resblock_kernels out of range");
+  if (c.precision != SVK_PRECISION_FP32) return fail(SVK_ERR_INVALID, "unsupported precision %d", c.precision);
+  if (c.hidden_channels % 8 || c.inter_channels % 16 || c.n_mel % 8)
+    return fail(SVK_ERR_INVALID, "n_mel, hidden_channels must be multiples of 8 and inter_channels of 16");
+  if ((c.upsample_initial_channel >> c.n_upsamples) < 8 || (c.upsample_initial_channel >> c.n_upsamples) % 8)
+    return fail(SVK_ERR_INVALID, "decoder channel widths must stay multiples of 8");
+  if (!conv_ffma_supports_k(c.wn_kernel)) return fail(SVK_ERR_INVALID, "unsupported WN kernel size %d", c.wn_kernel);
+  for (int i = 0; i < c.n_upsamples; ++i) {
+    const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
+    if (u < 1 || k < u || (k - u) % 2) return fail(SVK_ERR_INVALID, "upsample %d: need k >= u and (k-u) even", i);
+    if (!conv_ffma_supports_k((k + u - 1) / u)) return fail(SVK_ERR_INVALID, "upsample %d: unsupported k/u ratio", i);
+  }
+  for (int j = 0; j < c.n_resblock_kernels; ++j) {
+    if (c.resblock_kernel_sizes[j] % 2 != 1 || !conv_ffma_supports_k(c.resblock_kernel_sizes[j]))
+      return fail(SVK_ERR_INVALID, "unsupported resblock kernel size %d", c.resblock_kernel_sizes[j]);
+    for (int l = 0; l < SVK_RESBLOCK_PAIRS; ++l)
+      if (c.resblock_dilations[j][l] < 1 || c.resblock_dilations[j][l] > 8)
+        return fail(SVK_ERR_INVALID, "resblock dilation must be in [1,8]");
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(SVK_ERR_CUDA, "svk_create: CUDA device %d not available (%d visible); libsvk has no CPU path", device, ndev);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(SVK_ERR_CUDA, "svk_create: device %d is sm_%d%d; libsvk is built for sm_100a only", device, prop.major, prop.minor);
+  svk_handle* h = new svk_handle();
+  h->cfg = c;
+  h->device = device;
+  build_key_spec(h);
+  *out = h;
+  return SVK_OK;
+}
+
+extern "C" void svk_destroy(svk_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->d_blob) cudaFree(h->d_blob);
+  if (h->host_dev) cudaFree(h->host_dev);
+  if (h->host_stream) cudaStreamDestroy(h->host_stream);
+  delete h;
+}
+
+// ------------------------------------------------------------------------------- weight ingress
+extern "C" int svk_load_tensor(svk_handle* h, const char* key, const float* host_data, const int64_t* shape,
+                               int ndim) {
+  if (!h || !key || !host_data || !shape) return fail(SVK_ERR_INVALID, "svk_load_tensor: null argument");
+  auto it = h->spec.find(key);
+  if (it == h->spec.end()) return fail(SVK_ERR_UNKNOWN_KEY, "unexpected key '%s'", key);
+  const KeySpec& ks = it->second;
+  bool same = (int)ks.shape.size() == ndim;
+  for (int i = 0; same && i < ndim; ++i) same = ks.shape[i] == shape[i];
+  if (!same) {
+    std::string want, got;
+    for (auto v : ks.shape) want += std::to_string(v) + ",";
+    for (int i = 0; i < ndim; ++i) got += std::to_string(shape[i]) + ",";
+    return fail(SVK_ERR_INVALID, "size mismatch for %s: checkpoint [%s] vs model [%s]", key, got.c_str(), want.c_str());
+  }
+  if (ks.dead) return SVK_IGNORED;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= (size_t)shape[i];
+  HostTensor t;
+  t.shape.assign(shape, shape + ndim);
+  t.data.assign(host_data, host_data + n);
+  h->raw[key] = std::move(t);
+  h->finalized = false;
+  return SVK_OK;
+}
+
+extern "C" int svk_weight_status(const svk_handle* h, int* n_live, int* n_loaded) {
+  if (!h) return fail(SVK_ERR_INVALID, "null handle");
+  if (n_live) *n_live = h->n_live;
+  if (n_loaded) *n_loaded = (int)h->raw.size();
+  return SVK_OK;
+}
+
+extern "C" int svk_finalize_weights(svk_handle* h) {
+  if (!h) return fail(SVK_ERR_INVALID, "null handle");
+  for (const auto& key : h->key_order)
+    if (!h->spec[key].dead && !h->raw.count(key)) return fail(SVK_ERR_STATE, "missing key '%s'", key.c_str());
+  const svk_config& c = h->cfg;
+  const int half = c.inter_channels / 2;
+  h->h_blob.clear();
+  h->enc_in.clear(), h->enc_rs.clear(), h->ups.clear(), h->flows.clear(), h->resblocks.clear();
+
+  Folded f;
+  SVK_TRY(fold_layer(h, "enc_p.pre_enc", &f));
+  h->pre_enc = pack_plain(h, f);
+  SVK_TRY(pack_wn(h, "enc_p.encoder", c.enc_layers, &h->enc_in, &h->enc_rs));
+  SVK_TRY(fold_layer(h, "enc_p.proj", &f));
+  h->proj = pack_plain(h, f);
+
+  for (int fl = 0; fl < c.n_flows; ++fl) {
+    FlowLayers L;
+    // reverse pass applies [Flip, RCL_{n-1}, Flip, RCL_{n-2}, ...] (models.py:77-79): coupling fl has
+    // seen (n_flows - fl) Flips.  Odd -> it operates on the channel-reversed view; we keep storage
+    // fixed and reverse the 1x1 weights instead (pure index permutation, bit-exact on x0).
+    L.orient = (c.n_flows - fl) & 1;
+    const std::string p = "flow.flows." + std::to_string(2 * fl);
+    SVK_TRY(fold_layer(h, p + ".pre", &f));
+    if (L.orient) {
+      const Folded& g = f;
+      L.pre = pack_virtual(
+          h, g.d1, g.d0, 1, [&](int o, int cc, int) { return g.w[(size_t)o * g.d1 + (half - 1 - cc)]; },
+          [&](int o) { return g.b[o]; });
+    } else {
+      L.pre = pack_plain(h, f);
+    }
+    SVK_TRY(pack_wn(h, p + ".enc", c.flow_layers, &L.in, &L.rs));
+    SVK_TRY(fold_layer(h, p + ".post", &f));
+    {
+      // x1 = (x1 - m) * mask  ==  (x1 + (-m)) * mask: negate weights/bias (exact), add as residual.
+      const Folded& g = f;
+      L.post = pack_virtual(
+          h, g.d1, g.d0, 1, [&](int o, int cc, int) { return -g.w[(size_t)o * g.d1 + cc]; },
+          [&](int o) { return -g.b[o]; });
+    }
+    h->flows.push_back(std::move(L));
+  }
+
+  SVK_TRY(fold_layer(h, "dec.conv_pre", &f));
+  h->conv_pre = pack_plain(h, f);
+  for (int i = 0; i < c.n_upsamples; ++i) {
+    SVK_TRY(fold_layer(h, "dec.ups." + std::to_string(i), &f));
+    const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
+    h->ups.push_back(pack_transposed(h, f, u, (k - u) / 2));
+  }
+  for (int i = 0; i < c.n_upsamples; ++i)
+    for (int j = 0; j < c.n_resblock_kernels; ++j) {
+      ResBlock rb;
+      rb.k = c.resblock_kernel_sizes[j];
+      rb.C = h->stage_channels(i);
+      const std::string p = "dec.resblocks." + std::to_string(i * c.n_resblock_kernels + j);
+      for (int l = 0; l < SVK_RESBLOCK_PAIRS; ++l) {
+        rb.dil[l] = c.resblock_dilations[j][l];
+        SVK_TRY(fold_layer(h, p + ".convs1." + std::to_string(l), &f));
+        rb.c1[l] = pack_plain(h, f);
+        SVK_TRY(fold_layer(h, p + ".convs2." + std::to_string(l), &f));
+        rb.c2[l] = pack_plain(h, f);
+      }
+      h->resblocks.push_back(rb);
+    }
+  SVK_TRY(fold_layer(h, "dec.conv_post", &f));
+  h->conv_post = pack_plain(h, f);
+
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (h->d_blob) cudaFree(h->d_blob);
+  h->d_blob = nullptr;
+  h->blob_floats = h->h_blob.size();
+  CUDA_TRY(cudaMalloc(&h->d_blob, h->blob_floats * sizeof(float)));
+  CUDA_TRY(cudaMemcpy(h->d_blob, h->h_blob.data(), h->blob_floats * sizeof(float), cudaMemcpyHostToDevice));
+  h->h_blob.clear();
+  h->h_blob.shrink_to_fit();
+  h->finalized = true;
+  return SVK_OK;
+}
+
+// ------------------------------------------------------------------------------ launch helpers
+namespace {
+
+struct Runner {
+  svk_handle* h;
+  cudaStream_t stream;
+  int B;
+  cudaError_t err = cudaSuccess;
+
+  ConvArgs base(const PackedConv& pc, const float* x, int x_C, int x_ch_off, int x_stride, int Lin, int dil,
+                int pad, int Lout, int y_stride) const {
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x, a.x_C = x_C, a.x_ch_off = x_ch_off, a.x_stride = x_stride, a.Lin = Lin;
+    a.pre_slope = 1.0f;
+    a.wp = h->d_blob + pc.w_off, a.bias = h->d_blob + pc.b_off;
+    a.Cin = pc.Cin, a.Cout = pc.Cout, a.CoutPad = pc.CoutPad, a.K = pc.K;
+    a.dil = dil, a.pad = pad, a.Lout = Lout, a.y_stride = y_stride;
+    a.mode = MODE_STORE;
+    a.split = 1 << 30;
+    a.post_div = 1.0f;
+    a.B = B;
+    a.e[0].ch_sign = a.e[1].ch_sign = 1;
+    return a;
+  }
+  void run(const ConvArgs& a) {
+    if (err != cudaSuccess) return;
+    err = launch_conv_ffma(a, stream);
+    h->launches++;
+  }
+  void note(cudaError_t e) {
+    if (err == cudaSuccess) err = e;
+    h->launches++;
+  }
+
+  // modules.WN.forward, g=None (modules.py:148-176).  x is updated in place, result in `out`.
+  void wn(const std::vector<PackedConv>& in, const std::vector<PackedConv>& rs, float* x, float* acts,
+          float* out, const float* mask, int T) {
+    const int H = h->cfg.hidden_channels, n = (int)in.size(), k = h->cfg.wn_kernel;
+    for (int i = 0; i < n; ++i) {
+      ConvArgs a = base(in[i], x, H, 0, T, T, 1, (k - 1) / 2, T, T);
+      a.mode = MODE_GATE;
+      a.e[0].y = acts, a.e[0].C = H;
+      run(a);
+      ConvArgs r = base(rs[i], acts, H, 0, T, T, 1, 0, T, T);
+      r.out_mask = mask, r.mask_stride = T;
+      if (i < n - 1) {
+        r.split = H;
+        r.e[0].res = x, r.e[0].y = x, r.e[0].C = H, r.e[0].use_mask = 1;       // x = (x + res) * mask
+        r.e[1].acc_in = i ? out : nullptr, r.e[1].y = out, r.e[1].C = H;      // out += skip
+      } else {
+        r.e[0].acc_in = i ? out : nullptr, r.e[0].y = out, r.e[0].C = H, r.e[0].use_mask = 1;  // (out + rs) * mask
+      }
+      run(r);
+    }
+  }
+
+  // ResBlock1.forward (modules.py:210-223).  `dst` receives x_out (+ acc_in) / post_div.
+  void resblock(const ResBlock& rb, const float* x, float* xt, float* cur, float* dst, const float* acc_in,
+                float post_div, int L) {
+    const int C = rb.C;
+    for (int l = 0; l < SVK_RESBLOCK_PAIRS; ++l) {
+      const float* src = l == 0 ? x : cur;
+      const int d = rb.dil[l];
+      ConvArgs a = base(rb.c1[l], src, C, 0, L, L, d, (rb.k * d - d) / 2, L, L);
+      a.pre_slope = 0.1f;
+      a.e[0].y = xt, a.e[0].C = C;
+      run(a);
+      ConvArgs b = base(rb.c2[l], xt, C, 0, L, L, 1, (rb.k - 1) / 2, L, L);
+      b.pre_slope = 0.1f;
+      b.e[0].res = src, b.e[0].C = C;
+      if (l < SVK_RESBLOCK_PAIRS - 1) {
+        b.e[0].y = cur;
+      } else {
+        b.e[0].y = dst, b.e[0].acc_in = acc_in, b.post_div = post_div;
+      }
+      run(b);
+    }
+  }
+};
+
+struct DecoderPlan {
+  size_t buf_floats;  // each of the 4 rotating stage buffers
+};
+
+DecoderPlan plan_decoder(const svk_handle* h, int B, int L) {
+  size_t mx = (size_t)h->cfg.upsample_initial_channel * L;
+  int64_t len = L;
+  for (int i = 0; i < h->cfg.n_upsamples; ++i) {
+    len *= h->cfg.upsample_rates[i];
+    const size_t v = (size_t)h->stage_channels(i) * len;
+    if (v > mx) mx = v;
+  }
+  return DecoderPlan{align_up(mx * (size_t)B, 64)};
+}
+
+// Generator.forward (models.py:141-160).  z rows have stride z_stride; in_mask (optional) fuses
+// the `(z * x_mask)[:, :, :max_len]` of models.py:338.
+void run_decoder(Runner& R, const float* z, int z_stride, const float* in_mask, int L, float* o, float* ws) {
+  svk_handle* h = R.h;
+  const svk_config& c = h->cfg;
+  const DecoderPlan plan = plan_decoder(h, R.B, L);
+  float* buf[4] = {ws, ws + plan.buf_floats, ws + 2 * plan.buf_floats, ws + 3 * plan.buf_floats};
+  const int U = c.upsample_initial_channel;
+  {
+    ConvArgs a = R.base(h->conv_pre, z, c.inter_channels, 0, z_stride, L, 1, 3, L, L);
+    a.in_mask = in_mask, a.mask_stride = z_stride;
+    a.e[0].y = buf[1], a.e[0].C = U;
+    R.run(a);
+  }
+  const float* prev = buf[1];
+  int prevC = U, len = L;
+  for (int i = 0; i < c.n_upsamples; ++i) {
+    const PackedConv& up = h->ups[i];
+    const int C = h->stage_channels(i);
+    const int Lout = (len - 1) * up.s - 2 * up.p + up.k;
+    float* X = buf[0];
+    float* XT = buf[1];
+    float* CUR = buf[2];
+    float* XS = buf[3];
+    if (prev == XS) {  // previous stage summed into buf[3]; rotate so it is not overwritten early
+      XS = buf[1], XT = buf[3];
+    }
+    // ups[i](leaky_relu(x, 0.1)) (models.py:147-149)
+    {
+      const int nq = (Lout - 1 + up.p) / up.s + 1;
+      ConvArgs a = R.base(up, prev, prevC, 0, len, len, 1, up.pad_virtual, nq, Lout);
+      a.pre_slope = 0.1f;
+      a.mode = MODE_SHUFFLE;
+      a.shuf_s = up.s, a.shuf_p = up.p, a.shuf_Lout = Lout;
+      a.e[0].y = X, a.e[0].C = C;
+      R.run(a);
+    }
+    // xs = sum_j resblock_j(x); x = xs / num_kernels (models.py:150-155)
+    const int nk = c.n_resblock_kernels;
+    for (int j = 0; j < nk; ++j) {
+      const ResBlock& rb = h->resblocks[i * nk + j];
+      R.resblock(rb, X, XT, CUR, XS, j ? XS : nullptr, j == nk - 1 ? (float)nk : 1.0f, Lout);
+    }
+    prev = XS, prevC = C, len = Lout;
+  }
+  // tanh(conv_post(leaky_relu(x)))  -- default slope 0.01 (models.py:156-158)
+  {
+    ConvArgs a = R.base(h->conv_post, prev, prevC, 0, len, len, 1, 3, len, len);
+    a.pre_slope = 0.01f;
+    a.act_tanh = 1;
+    a.e[0].y = o, a.e[0].C = 1;
+    R.run(a);
+  }
+}
+
+struct InferPlan {
+  size_t mask, hbuf, acts, out, lat[4], dec, total;  // float offsets
+};
+
+InferPlan plan_infer(const svk_handle* h, int B, int T, int max_len) {
+  const svk_config& c = h->cfg;
+  const int Tp = max_len > 0 && max_len < T ? max_len : T;
+  InferPlan p;
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    size_t o = off;
+    off = align_up(off + n, 64);
+    return o;
+  };
+  p.mask = take((size_t)B * T);
+  p.hbuf = take((size_t)B * c.hidden_channels * T);
+  p.acts = take((size_t)B * c.hidden_channels * T);
+  p.out = take((size_t)B * c.hidden_channels * T);
+  for (int i = 0; i < 4; ++i) p.lat[i] = take((size_t)B * c.inter_channels * T);
+  p.dec = take(4 * plan_decoder(h, B, Tp).buf_floats);
+  p.total = off;
+  return p;
+}
+
+int check_ready(const svk_handle* h, const char* who) {
+  if (!h) return fail(SVK_ERR_INVALID, "%s: null handle", who);
+  if (!h->finalized) return fail(SVK_ERR_STATE, "%s: weights not finalized (svk_finalize_weights)", who);
+  return SVK_OK;
+}
+
+void run_mel_encoder(Runner& R, const float* mel, const float* mask, int T, float* hbuf, float* acts, float* out,
+                     float* m, float* logs) {
+  svk_handle* h = R.h;
+  const svk_config& c = h->cfg;
+  const int H = c.hidden_channels, C = c.inter_channels;
+  // x = pre_enc(mel); encoder(x * x_mask, x_mask) (models.py:38-42)
+  ConvArgs a = R.base(h->pre_enc, mel, c.n_mel, 0, T, T, 1, 0, T, T);
+  a.out_mask = mask, a.mask_stride = T;
+  a.e[0].y = hbuf, a.e[0].C = H, a.e[0].use_mask = 1;
+  R.run(a);
+  R.wn(h->enc_in, h->enc_rs, hbuf, acts, out, mask, T);
+  // stats = proj(x) * x_mask; m, logs = split(stats) (models.py:44-46)
+  ConvArgs p = R.base(h->proj, out, H, 0, T, T, 1, 0, T, T);
+  p.out_mask = mask, p.mask_stride = T;
+  p.split = C;
+  p.e[0].y = m, p.e[0].C = C, p.e[0].use_mask = 1;
+  p.e[1].y = logs, p.e[1].C = C, p.e[1].use_mask = 1;
+  R.run(p);
+}
+
+// ResidualCouplingBlock.forward(reverse=True) in place on z (models.py:77-79, modules.py:324-343).
+void run_flow_reverse(Runner& R, float* z, const float* mask, int T, float* hbuf, float* acts, float* out) {
+  svk_handle* h = R.h;
+  const svk_config& c = h->cfg;
+  const int H = c.hidden_channels, C = c.inter_channels, half = C / 2;
+  for (int fl = c.n_flows - 1; fl >= 0; --fl) {
+    const FlowLayers& L = h->flows[fl];
+    // h = pre(x0) * mask : x0 is the first half of the (possibly reversed) view
+    ConvArgs a = R.base(L.pre, z, C, L.orient ? half : 0, T, T, 1, 0, T, T);
+    a.out_mask = mask, a.mask_stride = T;
+    a.e[0].y = hbuf, a.e[0].C = H, a.e[0].use_mask = 1;
+    R.run(a);
+    R.wn(L.in, L.rs, hbuf, acts, out, mask, T);
+    // x1 = (x1 - post(h) * mask) * mask, written over x1's storage channels
+    ConvArgs p = R.base(L.post, out, H, 0, T, T, 1, 0, T, T);
+    p.out_mask = mask, p.mask_stride = T;
+    p.e[0].res = z, p.e[0].y = z, p.e[0].C = C, p.e[0].use_mask = 1;
+    if (L.orient) {
+      p.e[0].ch_off = half - 1, p.e[0].ch_sign = -1;
+    } else {
+      p.e[0].ch_off = half, p.e[0].ch_sign = 1;
+    }
+    R.run(p);
+  }
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------------------- the hot path
+extern "C" size_t svk_workspace_bytes(const svk_handle* h, int B, int T, int max_len) {
+  if (!h || B <= 0 || T <= 0) return 0;
+  return plan_infer(h, B, T, max_len).total * sizeof(float);
+}
+
+extern "C" int64_t svk_last_launch_count(const svk_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int svk_infer(svk_handle* h, const float* mel, const int64_t* lengths, const float* eps,
+                         float noise_scale, int B, int T, int max_len, float* o, float* x_mask, float* z,
+                         float* z_p, float* m_p, float* logs_p, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  SVK_TRY(check_ready(h, "svk_infer"));
+  if (!mel || !lengths || !eps || !o) return fail(SVK_ERR_INVALID, "svk_infer: null mel/lengths/eps/o");
+  if (B <= 0 || T <= 0) return fail(SVK_ERR_INVALID, "svk_infer: B and T must be positive");
+  const InferPlan p = plan_infer(h, B, T, max_len);
+  if (!workspace || workspace_bytes < p.total * sizeof(float))
+    return fail(SVK_ERR_WORKSPACE, "svk_infer: workspace %zu < %zu bytes", workspace_bytes, p.total * sizeof(float));
+  CUDA_TRY(cudaSetDevice(h->device));
+  const svk_config& c = h->cfg;
+  float* ws = (float*)workspace;
+  float* mask = x_mask ? x_mask : ws + p.mask;
+  float* lat_z = z ? z : ws + p.lat[0];
+  float* lat_zp = z_p ? z_p : nullptr;
+  float* lat_m = m_p ? m_p : ws + p.lat[2];
+  float* lat_logs = logs_p ? logs_p : ws + p.lat[3];
+  const int Tp = max_len > 0 && max_len < T ? max_len : T;
+
+  h->launches = 0;
+  Runner R{h, (cudaStream_t)stream, B};
+  R.note(launch_sequence_mask(lengths, B, T, mask, R.stream));
+  run_mel_encoder(R, mel, mask, T, ws + p.hbuf, ws + p.acts, ws + p.out, lat_m, lat_logs);
+  // z_p = m_p + eps * exp(logs_p) * noise_scale (models.py:336)
+  R.note(launch_sample(lat_m, lat_logs, eps, noise_scale, lat_zp, lat_z, (int64_t)B * c.inter_channels * T, R.stream));
+  run_flow_reverse(R, lat_z, mask, T, ws + p.hbuf, ws + p.acts, ws + p.out);
+  if (c.n_flows & 1) {  // odd number of Flips leaves storage reversed: materialise the last Flip
+    float* tmp = ws + p.lat[1];
+    R.note(launch_flip(lat_z, B, c.inter_channels, T, tmp, R.stream));
+    if (R.err == cudaSuccess)
+      R.err = cudaMemcpyAsync(lat_z, tmp, sizeof(float) * (size_t)B * c.inter_channels * T, cudaMemcpyDeviceToDevice, R.stream);
+  }
+  // o = dec((z * x_mask)[:, :, :max_len]) (models.py:338)
+  run_decoder(R, lat_z, T, mask, Tp, o, ws + p.dec);
+  if (R.err != cudaSuccess) return fail(SVK_ERR_CUDA, "svk_infer: launch failed: %s", cudaGetErrorString(R.err));
+  return SVK_OK;
+}
+
+extern "C" int svk_infer_host(svk_handle* h, const float* mel, const int64_t* lengths, const float* eps,
+                              float noise_scale, int B, int T, int max_len, float* o, float* x_mask, float* z,
+                              float* z_p, float* m_p, float* logs_p) {
+  SVK_TRY(check_ready(h, "svk_infer_host"));
+  if (!mel || !lengths || !eps || !o) return fail(SVK_ERR_INVALID, "svk_infer_host: null mel/lengths/eps/o");
+  if (B <= 0 || T <= 0) return fail(SVK_ERR_INVALID, "svk_infer_host: B and T must be positive");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->host_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+  const svk_config& c = h->cfg;
+  const int Tp = max_len > 0 && max_len < T ? max_len : T;
+  const size_t n_mel = (size_t)B * c.n_mel * T, n_lat = (size_t)B * c.inter_channels * T, n_o = (size_t)B * h->hop() * Tp;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o2 = off;
+    off = align_up(off + bytes, 256);
+    return o2;
+  };
+  const size_t o_mel = take(n_mel * 4), o_len = take((size_t)B * 8), o_eps = take(n_lat * 4), o_o = take(n_o * 4),
+               o_mask = take((size_t)B * T * 4);
+  size_t o_lat[4];
+  for (int i = 0; i < 4; ++i) o_lat[i] = take(n_lat * 4);
+  const size_t ws_bytes = svk_workspace_bytes(h, B, T, max_len);
+  const size_t o_ws = take(ws_bytes);
+  if (off > h->host_dev_bytes) {
+    if (h->host_dev) CUDA_TRY(cudaFree(h->host_dev));
+    h->host_dev = nullptr, h->host_dev_bytes = 0;
+    CUDA_TRY(cudaMalloc(&h->host_dev, off));
+    h->host_dev_bytes = off;
+  }
+  char* d = (char*)h->host_dev;
+  cudaStream_t s = h->host_stream;
+  CUDA_TRY(cudaMemcpyAsync(d + o_mel, mel, n_mel * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(d + o_len, lengths, (size_t)B * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(d + o_eps, eps, n_lat * 4, cudaMemcpyHostToDevice, s));
+  float* dl[4];
+  float* hl[4] = {z, z_p, m_p, logs_p};
+  for (int i = 0; i < 4; ++i) dl[i] = hl[i] ? (float*)(d + o_lat[i]) : nullptr;
+  SVK_TRY(svk_infer(h, (const float*)(d + o_mel), (const int64_t*)(d + o_len), (const float*)(d + o_eps), noise_scale,
+                    B, T, max_len, (float*)(d + o_o), (float*)(d + o_mask), dl[0], dl[1], dl[2], dl[3], d + o_ws,
+                    ws_bytes, s));
+  CUDA_TRY(cudaMemcpyAsync(o, d + o_o, n_o * 4, cudaMemcpyDeviceToHost, s));
+  if (x_mask) CUDA_TRY(cudaMemcpyAsync(x_mask, d + o_mask, (size_t)B * T * 4, cudaMemcpyDeviceToHost, s));
+  for (int i = 0; i < 4; ++i)
+    if (hl[i]) CUDA_TRY(cudaMemcpyAsync(hl[i], dl[i], n_lat * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return SVK_OK;
+}
+
+// ----------------------------------------------------------------------------- module-level ops
+extern "C" int svk_mel_encoder(svk_handle* h, const float* mel, const int64_t* lengths, int B, int T, float* x_out,
+                               float* m, float* logs, float* mask, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  SVK_TRY(check_ready(h, "svk_mel_encoder"));
+  if (!mel || !lengths || !x_out || !m || !logs || !mask || B <= 0 || T <= 0)
+    return fail(SVK_ERR_INVALID, "svk_mel_encoder: bad argument");
+  const size_t n = align_up((size_t)B * h->cfg.hidden_channels * T, 64);
+  if (!workspace || workspace_bytes < 2 * n * sizeof(float)) return fail(SVK_ERR_WORKSPACE, "svk_mel_encoder: workspace too small");
+  CUDA_TRY(cudaSetDevice(h->device));
+  float* ws = (float*)workspace;
+  h->launches = 0;
+  Runner R{h, (cudaStream_t)stream, B};
+  R.note(launch_sequence_mask(lengths, B, T, mask, R.stream));
+  run_mel_encoder(R, mel, mask, T, ws, ws + n, x_out, m, logs);
+  if (R.err != cudaSuccess) return fail(SVK_ERR_CUDA, "svk_mel_encoder: %s", cudaGetErrorString(R.err));
+  return SVK_OK;
+}
+
+extern "C" int svk_flow_reverse(svk_handle* h, float* z, const float* mask, int B, int T, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  SVK_TRY(check_ready(h, "svk_flow_reverse"));
+  if (!z || !mask || B <= 0 || T <= 0) return fail(SVK_ERR_INVALID, "svk_flow_reverse: bad argument");
+  const svk_config& c = h->cfg;
+  const size_t n = align_up((size_t)B * c.hidden_channels * T, 64), nl = align_up((size_t)B * c.inter_channels * T, 64);
+  if (!workspace || workspace_bytes < (3 * n + nl) * sizeof(float)) return fail(SVK_ERR_WORKSPACE, "svk_flow_reverse: workspace too small");
+  CUDA_TRY(cudaSetDevice(h->device));
+  float* ws = (float*)workspace;
+  h->launches = 0;
+  Runner R{h, (cudaStream_t)stream, B};
+  run_flow_reverse(R, z, mask, T, ws, ws + n, ws + 2 * n);
+  if (c.n_flows & 1) {
+    float* tmp = ws + 3 * n;
+    R.note(launch_flip(z, B, c.inter_channels, T, tmp, R.stream));
+    if (R.err == cudaSuccess)
+      R.err = cudaMemcpyAsync(z, tmp, sizeof(float) * (size_t)B * c.inter_channels * T, cudaMemcpyDeviceToDevice, R.stream);
+  }
+  if (R.err != cudaSuccess) return fail(SVK_ERR_CUDA, "svk_flow_reverse: %s", cudaGetErrorString(R.err));
+  return SVK_OK;
+}
+
+extern "C" int svk_generator(svk_handle* h, const float* z, int B, int L, float* o, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  SVK_TRY(check_ready(h, "svk_generator"));
+  if (!z || !o || B <= 0 || L <= 0) return fail(SVK_ERR_INVALID, "svk_generator: bad argument");
+  const size_t need = 4 * plan_decoder(h, B, L).buf_floats * sizeof(float);
+  if (!workspace || workspace_bytes < need) return fail(SVK_ERR_WORKSPACE, "svk_generator: workspace %zu < %zu", workspace_bytes, need);
+  CUDA_TRY(cudaSetDevice(h->device));
+  h->launches = 0;
+  Runner R{h, (cudaStream_t)stream, B};
+  run_decoder(R, z, L, nullptr, L, o, (float*)workspace);
+  if (R.err != cudaSuccess) return fail(SVK_ERR_CUDA, "svk_generator: %s", cudaGetErrorString(R.err));
+  return SVK_OK;
+}
+
+extern "C" int svk_resblock1(svk_handle* h, int index, const float* x, int B, int L, float* y, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  SVK_TRY(check_ready(h, "svk_resblock1"));
+  if (index < 0 || index >= (int)h->resblocks.size()) return fail(SVK_ERR_INVALID, "svk_resblock1: index out of range");
+  if (!x || !y || B <= 0 || L <= 0) return fail(SVK_ERR_INVALID, "svk_resblock1: bad argument");
+  const ResBlock& rb = h->resblocks[index];
+  const size_t n = align_up((size_t)B * rb.C * L, 64);
+  if (!workspace || workspace_bytes < 2 * n * sizeof(float)) return fail(SVK_ERR_WORKSPACE, "svk_resblock1: workspace too small");
+  CUDA_TRY(cudaSetDevice(h->device));
+  float* ws = (float*)workspace;
+  h->launches = 0;
+  Runner R{h, (cudaStream_t)stream, B};
+  R.resblock(rb, x, ws, ws + n, y, nullptr, 1.0f, L);
+  if (R.err != cudaSuccess) return fail(SVK_ERR_CUDA, "svk_resblock1: %s", cudaGetErrorString(R.err));
+  return SVK_OK;
+}

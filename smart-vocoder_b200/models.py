@@ -1,0 +1,325 @@
+"""Drop-in for the reference's ``models.SynthesizerTrn`` on the inference path (B200, libsvk).
+
+Put this directory ahead of the reference checkout on ``sys.path`` and ``inference.ipynb`` runs
+unchanged: ``from models import SynthesizerTrn`` resolves here, while ``commons``, ``utils``,
+``mel_processing`` ... keep coming from the reference.
+
+What is mirrored (reference file:line):
+  * constructor signature and ignored keys            models.py:266-314   
+  * ``state_dict()`` / ``load_state_dict()`` surface   utils.py:18-43      (659 keys)
+  * ``infer(x, x_lengths, sid, noise_scale, length_scale, noise_scale_w, max_len)``
+        -> ``(o, x_mask, (z, z_p, m_p, logs_p))``      models.py:331-339
+  * sub-module calls ``dec(z)``, ``enc_p(x, x_lengths)``, ``flow(z, mask, reverse=True)``
+                                                       models.py:141-160, 35-47, 73-80
+
+All arithmetic runs in hand-written CUDA behind the C ABI of include/svk.h; PyTorch only owns the
+device buffers, the RNG draw and the stream.  Training-time methods are out of scope and raise.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict, namedtuple
+from typing import Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+import svk_runtime as rt
+import svk_weights as W
+
+_IncompatibleKeys = namedtuple("_IncompatibleKeys", ["missing_keys", "unexpected_keys"])
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class _Workspace:
+    """Grow-only device scratch, one per module."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+
+    def get(self, nbytes: int, device) -> torch.Tensor:
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = None
+            self.buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        return self.buf
+
+
+class _SubModule:
+    """Callable view of one stage, for callers that use ``net_g.dec(...)`` style access."""
+
+    def __init__(self, parent: "SynthesizerTrn", fn):
+        self._parent, self._fn = parent, fn
+
+    def __call__(self, *a, **k):
+        return self._fn(*a, **k)
+
+    forward = __call__
+
+
+class SynthesizerTrn(nn.Module):
+    """
+    Synthesizer for Training  (inference path only; see module docstring)
+    """
+
+    def __init__(self,
+                 spec_channels,
+                 segment_size,
+                 inter_channels,
+                 hidden_channels,
+                 filter_channels,
+                 n_heads,
+                 n_layers,
+                 kernel_size,
+                 p_dropout,
+                 resblock,
+                 resblock_kernel_sizes,
+                 resblock_dilation_sizes,
+                 upsample_rates,
+                 upsample_initial_channel,
+                 upsample_kernel_sizes,
+                 n_speakers=0,
+                 gin_channels=0,
+                 **kwargs):
+        super().__init__()
+        # stored exactly like the reference does (models.py:287-303), even the ignored ones
+        self.spec_channels = spec_channels
+        self.inter_channels = inter_channels
+        self.hidden_channels = hidden_channels
+        self.filter_channels = filter_channels
+        self.n_heads = n_heads
+        self.n_layers = n_layers
+        self.kernel_size = kernel_size
+        self.p_dropout = p_dropout
+        self.resblock = resblock
+        self.resblock_kernel_sizes = resblock_kernel_sizes
+        self.resblock_dilation_sizes = resblock_dilation_sizes
+        self.upsample_rates = upsample_rates
+        self.upsample_initial_channel = upsample_initial_channel
+        self.upsample_kernel_sizes = upsample_kernel_sizes
+        self.segment_size = segment_size
+        self.n_speakers = n_speakers
+        self.gin_channels = gin_channels
+
+        self.dims = W.dims_from_model_kwargs(
+            spec_channels, inter_channels=inter_channels, hidden_channels=hidden_channels, resblock=resblock,
+            resblock_kernel_sizes=resblock_kernel_sizes, resblock_dilation_sizes=resblock_dilation_sizes,
+            upsample_rates=upsample_rates, upsample_initial_channel=upsample_initial_channel,
+            upsample_kernel_sizes=upsample_kernel_sizes, gin_channels=gin_channels)
+        self.dims.validate()
+        self._spec = W.state_dict_spec(self.dims)
+        # Same key surface as the reference; values are a seeded stand-in for torch's random init
+        # (flow.*.post zero like modules.py:321-322).  Real use loads a checkpoint over them.
+        init = W.make_state_dict(self.dims, seed=int(kwargs.get("init_seed", 0)), alive=False)
+        self._sd = OrderedDict((k, torch.from_numpy(v)) for k, v in init.items())
+        self._handle: Optional[rt.Handle] = None
+        self._device: Optional[torch.device] = None
+        self._ws = _Workspace()
+
+        self.dec = _SubModule(self, self._dec_forward)
+        self.enc_p = _SubModule(self, self._enc_p_forward)
+        self.flow = _SubModule(self, self._flow_forward)
+
+    # ------------------------------------------------------------------ nn.Module surface
+    def _apply(self, fn, *args, **kwargs):
+        probe = fn(torch.empty(0, dtype=torch.float32))
+        if probe.dtype != torch.float32:
+            raise TypeError("SynthesizerTrn (B200) computes in fp32; .half()/.double() are not supported")
+        if probe.device.type == "cuda":
+            self._bind(probe.device)
+        elif probe.device.type == "cpu":
+            self._release()
+        return self
+
+    def _release(self):
+        if self._handle is not None:
+            self._handle.close()
+        self._handle, self._device = None, None
+
+    def _bind(self, device: torch.device):
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        device = torch.device("cuda", idx)
+        if self._handle is not None and self._device == device:
+            return
+        self._release()
+        self._handle = rt.Handle(self.dims, idx)
+        self._device = device
+        self._upload()
+
+    def _upload(self):
+        h = self._handle
+        for k, v in self._sd.items():
+            if not W.is_dead_key(k):
+                h.load_tensor(k, v.detach().cpu().numpy())
+        h.finalize()
+
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
+        out = OrderedDict() if destination is None else destination
+        for k, v in self._sd.items():
+            out[prefix + k] = v if keep_vars else v.detach()
+        return out
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        missing = [k for k in self._sd if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in self._sd]
+        errors = []
+        for k, v in state_dict.items():
+            if k in self._sd and tuple(v.shape) != tuple(self._sd[k].shape):
+                errors.append(f"size mismatch for {k}: copying a param with shape {tuple(v.shape)} from checkpoint, "
+                              f"the shape in current model is {tuple(self._sd[k].shape)}.")
+        if strict and (missing or unexpected):
+            if missing:
+                errors.append("Missing key(s) in state_dict: " + ", ".join(f'"{k}"' for k in missing) + ".")
+            if unexpected:
+                errors.append("Unexpected key(s) in state_dict: " + ", ".join(f'"{k}"' for k in unexpected) + ".")
+        if errors:
+            raise RuntimeError("Error(s) in loading state_dict for SynthesizerTrn:\n\t" + "\n\t".join(errors))
+        for k, v in state_dict.items():
+            if k in self._sd:
+                self._sd[k] = v.detach().to("cpu", torch.float32).contiguous().clone()
+        if self._handle is not None:
+            self._upload()
+        return _IncompatibleKeys(missing, unexpected)
+
+    def parameters(self, recurse: bool = True):
+        return iter(self._sd.values())
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError("training is out of scope of the B200 inference path")
+        return super().train(False)
+
+    # ------------------------------------------------------------------ helpers
+    def _need_cuda(self, *tensors):
+        if self._handle is None:
+            raise RuntimeError("SynthesizerTrn (B200) has no CPU path: call .cuda() first "
+                               "(libsvk runs on sm_100a only)")
+        for t in tensors:
+            if t is not None and t.device != self._device:
+                raise RuntimeError(f"Expected all tensors to be on the same device, but found {t.device} and {self._device}")
+
+    @staticmethod
+    def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"{name}: expected a float32 tensor but found {t.dtype}")
+        return t.contiguous()
+
+    def _stream(self):
+        return torch.cuda.current_stream(self._device).cuda_stream
+
+    @staticmethod
+    def _clip_len(T: int, max_len) -> int:
+        """Python slice semantics of ``[:, :, :max_len]`` (models.py:338)."""
+        if max_len is None:
+            return T
+        max_len = int(max_len)
+        return max(T + max_len, 0) if max_len < 0 else min(max_len, T)
+
+    # ------------------------------------------------------------------ the hot path
+    def infer(self, x, x_lengths, sid=None, noise_scale=1, length_scale=1, noise_scale_w=1., max_len=None):
+        # sid, length_scale, noise_scale_w are accepted and ignored, exactly like models.py:331-339
+        self._need_cuda(x, x_lengths)
+        x = self._f32(x, "x")
+        if x.dim() != 3 or x.shape[1] != self.dims.n_mel:
+            raise RuntimeError(f"expected input[B, {self.dims.n_mel}, T], got {list(x.shape)}")
+        B, _, T = x.shape
+        lengths = x_lengths.to(torch.int64).contiguous()
+        C, dev = self.dims.inter_channels, self._device
+        Tp = self._clip_len(T, max_len)
+        if B == 0 or T == 0 or Tp == 0:
+            raise ValueError("infer: empty batch / zero frames")
+        m_p = torch.empty(B, C, T, device=dev, dtype=torch.float32)
+        # the only RNG consumer of the path (models.py:336); drawn by torch so that a seeded
+        # generator -- or a patched randn_like -- feeds this path exactly like the reference
+        eps = torch.randn_like(m_p).contiguous()
+        logs_p = torch.empty_like(m_p)
+        z_p = torch.empty_like(m_p)
+        z = torch.empty_like(m_p)
+        x_mask = torch.empty(B, 1, T, device=dev, dtype=torch.float32)
+        o = torch.empty(B, 1, self.dims.hop * Tp, device=dev, dtype=torch.float32)
+        nbytes = self._handle.workspace_bytes(B, T, Tp)
+        ws = self._ws.get(nbytes, dev)
+        with torch.cuda.device(dev):
+            rt.check(rt.lib().svk_infer(self._handle.ptr, _ptr(x), _ptr(lengths), _ptr(eps), float(noise_scale),
+                                        B, T, Tp, _ptr(o), _ptr(x_mask), _ptr(z), _ptr(z_p), _ptr(m_p), _ptr(logs_p),
+                                        _ptr(ws), nbytes, self._stream()))
+        return o, x_mask, (z, z_p, m_p, logs_p)
+
+    def infer_host(self, mel: np.ndarray, lengths: np.ndarray, eps: np.ndarray, noise_scale=1.0, max_len=None,
+                   out: Optional[np.ndarray] = None, want_latents: bool = False):
+        """Host-buffer entry (svk_infer_host): what inference.ipynb:114-118 does around ``infer``
+        (``.cuda()`` ... ``.cpu()``), copies included.  Arrays should live in pinned memory."""
+        self._need_cuda()
+        B, _, T = mel.shape
+        Tp = self._clip_len(T, max_len)
+        if out is None:
+            out = np.empty((B, 1, self.dims.hop * Tp), np.float32)
+        mask = np.empty((B, 1, T), np.float32)
+        lat = [np.empty((B, self.dims.inter_channels, T), np.float32) if want_latents else None for _ in range(4)]
+        vp = lambda a: None if a is None else a.ctypes.data  # noqa: E731
+        rt.check(rt.lib().svk_infer_host(self._handle.ptr, vp(mel), vp(lengths), vp(eps), float(noise_scale), B, T, Tp,
+                                         vp(out), vp(mask), vp(lat[0]), vp(lat[1]), vp(lat[2]), vp(lat[3])))
+        return out, mask, tuple(lat)
+
+    def last_launch_count(self) -> int:
+        return self._handle.last_launch_count() if self._handle else 0
+
+    # ------------------------------------------------------------------ sub-module views
+    def _dec_forward(self, x, g=None):
+        """Generator.forward(x, g=None) (models.py:141-160)."""
+        self._need_cuda(x)
+        x = self._f32(x, "x")
+        B, C, L = x.shape
+        if C != self.dims.inter_channels:
+            raise RuntimeError(f"expected input[B, {self.dims.inter_channels}, L], got {list(x.shape)}")
+        o = torch.empty(B, 1, self.dims.hop * L, device=self._device, dtype=torch.float32)
+        nbytes = self._handle.workspace_bytes(B, L, L)
+        ws = self._ws.get(nbytes, self._device)
+        with torch.cuda.device(self._device):
+            rt.check(rt.lib().svk_generator(self._handle.ptr, _ptr(x), B, L, _ptr(o), _ptr(ws), nbytes, self._stream()))
+        return o
+
+    def _enc_p_forward(self, x, x_lengths, g=None):
+        """MelEncoder.forward (models.py:35-47) -> (x, m, logs, x_mask)."""
+        self._need_cuda(x, x_lengths)
+        x = self._f32(x, "x")
+        B, _, T = x.shape
+        dev, H, C = self._device, self.dims.hidden_channels, self.dims.inter_channels
+        lengths = x_lengths.to(torch.int64).contiguous()
+        xo = torch.empty(B, H, T, device=dev, dtype=torch.float32)
+        m = torch.empty(B, C, T, device=dev, dtype=torch.float32)
+        logs = torch.empty_like(m)
+        mask = torch.empty(B, 1, T, device=dev, dtype=torch.float32)
+        nbytes = self._handle.workspace_bytes(B, T, T)
+        ws = self._ws.get(nbytes, dev)
+        with torch.cuda.device(dev):
+            rt.check(rt.lib().svk_mel_encoder(self._handle.ptr, _ptr(x), _ptr(lengths), B, T, _ptr(xo), _ptr(m),
+                                              _ptr(logs), _ptr(mask), _ptr(ws), nbytes, self._stream()))
+        return xo, m, logs, mask
+
+    def _flow_forward(self, x, x_mask, g=None, reverse=False):
+        """ResidualCouplingBlock.forward (models.py:73-80); only reverse=True is on the path."""
+        if not reverse:
+            raise NotImplementedError("flow forward (training direction) is out of scope; use reverse=True")
+        self._need_cuda(x, x_mask)
+        z = self._f32(x, "x").clone()
+        mask = self._f32(x_mask, "x_mask")
+        B, C, T = z.shape
+        nbytes = self._handle.workspace_bytes(B, T, T)
+        ws = self._ws.get(nbytes, self._device)
+        with torch.cuda.device(self._device):
+            rt.check(rt.lib().svk_flow_reverse(self._handle.ptr, _ptr(z), _ptr(mask), B, T, _ptr(ws), nbytes,
+                                               self._stream()))
+        return z
+
+    # ------------------------------------------------------------------ out of scope (training)
+    def forward(self, x, x_lengths, y, y_lengths, sid=None):
+        raise NotImplementedError("SynthesizerTrn.forward is the training graph (models.py:317-329); "
+                                  "out of scope of the B200 inference path")
+
+    def voice_conversion(self, y, y_lengths, sid_src, sid_tgt):
+        # the reference asserts, then dies on the never-created emb_g (models.py:342-343)
+        assert self.n_speakers > 0, "n_speakers have to be larger than 0."
+        raise AttributeError("'SynthesizerTrn' object has no attribute 'emb_g'")

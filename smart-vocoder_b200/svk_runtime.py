@@ -1,0 +1,185 @@
+"""ctypes binding of libsvk.so (include/svk.h).  No compute happens in Python.
+
+The library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  Importing this module
+never falls back to another implementation: if libsvk.so is missing or a CUDA device is absent,
+calls raise ``SvkError``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsvk.so")
+
+SVK_OK = 0
+SVK_IGNORED = 1
+SVK_ERR_INVALID = -1
+SVK_ERR_CUDA = -2
+SVK_ERR_UNKNOWN_KEY = -3
+SVK_ERR_STATE = -4
+SVK_ERR_WORKSPACE = -5
+
+SVK_MAX_UPSAMPLES = 8
+SVK_MAX_RESBLOCK_KERNELS = 8
+SVK_RESBLOCK_PAIRS = 3
+
+PRECISION_FP32 = 0
+
+
+class SvkError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libsvk error {code}: {message}")
+        self.code = code
+
+
+class SvkConfig(ctypes.Structure):
+    _fields_ = [
+        ("n_mel", ctypes.c_int32),
+        ("spec_channels", ctypes.c_int32),
+        ("inter_channels", ctypes.c_int32),
+        ("hidden_channels", ctypes.c_int32),
+        ("enc_layers", ctypes.c_int32),
+        ("flow_layers", ctypes.c_int32),
+        ("n_flows", ctypes.c_int32),
+        ("wn_kernel", ctypes.c_int32),
+        ("gin_channels", ctypes.c_int32),
+        ("upsample_initial_channel", ctypes.c_int32),
+        ("n_upsamples", ctypes.c_int32),
+        ("upsample_rates", ctypes.c_int32 * SVK_MAX_UPSAMPLES),
+        ("upsample_kernel_sizes", ctypes.c_int32 * SVK_MAX_UPSAMPLES),
+        ("n_resblock_kernels", ctypes.c_int32),
+        ("resblock_kernel_sizes", ctypes.c_int32 * SVK_MAX_RESBLOCK_KERNELS),
+        ("resblock_dilations", (ctypes.c_int32 * SVK_RESBLOCK_PAIRS) * SVK_MAX_RESBLOCK_KERNELS),
+        ("precision", ctypes.c_int32),
+    ]
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+_vp, _i, _i64, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/svk.h one to one (tests check every symbol loads)
+SIGNATURES = {
+    "svk_abi_version": (_i, []),
+    "svk_last_error": (ctypes.c_char_p, []),
+    "svk_create": (_i, [ctypes.POINTER(SvkConfig), _i, ctypes.POINTER(_vp)]),
+    "svk_destroy": (None, [_vp]),
+    "svk_load_tensor": (_i, [_vp, ctypes.c_char_p, _vp, ctypes.POINTER(_i64), _i]),
+    "svk_finalize_weights": (_i, [_vp]),
+    "svk_weight_status": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
+    "svk_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
+    "svk_infer": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "svk_infer_host": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "svk_last_launch_count": (_i64, [_vp]),
+    "svk_mel_encoder": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "svk_flow_reverse": (_i, [_vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
+    "svk_generator": (_i, [_vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
+    "svk_resblock1": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _sz, _vp]),
+    "svk_conv1d": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
+    "svk_conv_transpose1d": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
+    "svk_sequence_mask": (_i, [_vp, _i, _i, _vp, _vp]),
+    "svk_flip": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "svk_weight_norm": (_i, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "svk_rq_spline": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp]),
+}
+
+
+def lib() -> ctypes.CDLL:
+    """Load libsvk.so; raises if the CUDA extension has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SvkError(SVK_ERR_STATE, f"{LIB_PATH} not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        if l.svk_abi_version() != 1:
+            raise SvkError(SVK_ERR_STATE, "libsvk ABI version mismatch")
+        _lib = l
+    return _lib
+
+
+def check(status: int) -> int:
+    if status < 0:
+        raise SvkError(status, lib().svk_last_error().decode("utf-8", "replace"))
+    return status
+
+
+def make_config(dims, precision: int = PRECISION_FP32) -> SvkConfig:
+    """ModelDims (svk_weights.py) -> svk_config."""
+    c = SvkConfig()
+    c.n_mel = dims.n_mel
+    c.spec_channels = dims.spec_channels
+    c.inter_channels = dims.inter_channels
+    c.hidden_channels = dims.hidden_channels
+    c.enc_layers = dims.enc_layers
+    c.flow_layers = dims.flow_layers
+    c.n_flows = dims.n_flows
+    c.wn_kernel = dims.wn_kernel
+    c.gin_channels = dims.gin_channels
+    c.upsample_initial_channel = dims.upsample_initial_channel
+    if len(dims.upsample_rates) > SVK_MAX_UPSAMPLES or len(dims.resblock_kernel_sizes) > SVK_MAX_RESBLOCK_KERNELS:
+        raise SvkError(SVK_ERR_INVALID, "too many upsample stages / resblock kernels")
+    c.n_upsamples = len(dims.upsample_rates)
+    for i, (u, k) in enumerate(zip(dims.upsample_rates, dims.upsample_kernel_sizes)):
+        c.upsample_rates[i] = int(u)
+        c.upsample_kernel_sizes[i] = int(k)
+    c.n_resblock_kernels = len(dims.resblock_kernel_sizes)
+    for j, (k, ds) in enumerate(zip(dims.resblock_kernel_sizes, dims.resblock_dilation_sizes)):
+        c.resblock_kernel_sizes[j] = int(k)
+        if len(ds) != SVK_RESBLOCK_PAIRS:
+            raise SvkError(SVK_ERR_INVALID, "ResBlock1 needs exactly 3 dilations per kernel size")
+        for l, dil in enumerate(ds):
+            c.resblock_dilations[j][l] = int(dil)
+    c.precision = precision
+    return c
+
+
+class Handle:
+    """Owns one svk_handle (one device)."""
+
+    def __init__(self, dims, device: int, precision: int = PRECISION_FP32):
+        self._h = _vp()
+        self.cfg = make_config(dims, precision)
+        check(lib().svk_create(ctypes.byref(self.cfg), int(device), ctypes.byref(self._h)))
+        self.device = int(device)
+
+    @property
+    def ptr(self):
+        return self._h
+
+    def close(self):
+        if self._h:
+            lib().svk_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_tensor(self, key: str, array) -> int:
+        """array: C-contiguous float32 numpy array (host)."""
+        import numpy as np
+        a = np.ascontiguousarray(array, dtype=np.float32)
+        shape = (_i64 * a.ndim)(*a.shape)
+        return check(lib().svk_load_tensor(self._h, key.encode(), a.ctypes.data_as(_vp), shape, a.ndim))
+
+    def finalize(self):
+        check(lib().svk_finalize_weights(self._h))
+
+    def weight_status(self):
+        a, b = _i(), _i()
+        check(lib().svk_weight_status(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def workspace_bytes(self, B: int, T: int, max_len: int) -> int:
+        return int(lib().svk_workspace_bytes(self._h, B, T, max_len))
+
+    def last_launch_count(self) -> int:
+        return int(lib().svk_last_launch_count(self._h))
