@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native SMART-Vocoder mel->waveform path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU PyTorch path (rank 0 only)
+
+One "step" = one pass of SynthesizerTrn.infer (MelEncoder + inverse flow + HiFi-GAN decoder) over one
+batch of synthetic 80 x T mels per GPU.  Workload at N=1: BASELINE.json configs[2] -- iitp_base.json,
+batch 16, 80x1024 mel, fp32, full path (configs[1] is a single-kernel case and configs[0] the CPU
+plumbing case; both are parity tests, not bench lines).  For N>1 every rank runs the same per-GPU batch
+(weak scaling, utterance sharding, no data-path collective).
+
+Prints ONE JSON line (rank 0).  `value` = whole-job audio samples/s with inputs resident in HBM;
+`e2e` = the same through the reference-facing `SynthesizerTrn.infer` call from pinned HOST buffers
+(H2D of mel+lengths and D2H of the PCM inside the timed region; NCCL scatter/gather for N>1);
+`roofline` = the dominant kernel against the pipe it runs on; `cpu_baseline` = oracle/torch_port.py
+(the reference's torch-CPU operators restated) on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "smart-vocoder_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import svk_weights as W  # noqa: E402
+
+SAMPLE_RATE = 22050
+FLOP_PER_FRAME = 657_479_680       # 2 x 328,739,840 MACs, convolutions only (SURVEY 8(d) / BASELINE.md 3)
+BYTES_MIN_PER_FRAME = 2112         # mel 320 + eps 768 + PCM 1024
+WEIGHT_BYTES_FP32 = 142_603_776
+METRIC = "audio_samples_per_sec_22.05kHz_mel80_to_wav"
+UNIT = "samples/s"
+NOISE_SCALE = 0.667                # inference.ipynb:118
+
+
+def load_cfg():
+    return json.load(open(os.path.join(ROOT, "configs", "iitp_base.json")))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        d["_source"] = "measured (MEASURED_PEAKS.json)"
+        return d
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0,
+            "_source": "fallback (B200_PROFILING.md)"}
+
+
+def synth_inputs(B, T, seed=0):
+    """mel ~ N(-5, 2) like real log-mels, full-length utterances."""
+    g = torch.Generator().manual_seed(seed)
+    mel = torch.randn(B, 80, T, generator=g) * 2.0 - 5.0
+    lengths = torch.full((B,), T, dtype=torch.int64)
+    return mel, lengths
+
+
+# ----------------------------------------------------------------------------------- CPU side
+def cpu_reference_run(B, T, steps, warmup, threads=None):
+    """Time oracle/torch_port.infer (reference operators on torch CPU) -> list of seconds per step."""
+    from oracle import torch_port
+    if threads:
+        torch.set_num_threads(threads)
+    cfg = load_cfg()
+    dims = W.dims_from_model_kwargs(513, **cfg["model"])
+    sd = {k: torch.from_numpy(v) for k, v in W.make_state_dict(dims, seed=1234).items()}
+    mel, lengths = synth_inputs(B, T)
+    torch.manual_seed(1)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        o = torch_port.infer(sd, dims, mel, lengths, None, NOISE_SCALE, None)[0]
+        dt = time.perf_counter() - t0
+        assert o.shape == (B, 1, 256 * T)
+        if i >= warmup:
+            times.append(dt)
+    return times
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference's own CPU implementation of the path, all host threads, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B, T = 1, args.frames  # bounded sample: one utterance of the per-GPU batch (utterances are independent)
+    times = cpu_reference_run(B, T, args.steps, max(args.warmup, 1), cores)
+    total = sum(times)
+    value = B * 256 * T * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "rtf": (total / len(times)) / (B * 256 * T / SAMPLE_RATE),
+        "config": {"workload": f"iitp_base.json full path, {args.batch_per_gpu}x80x{T} mel per GPU, fp32 "
+                               f"(BASELINE configs[2]); reference arm times a 1x80x{T} sample of it per step",
+                   "frames": T, "batch_per_gpu": args.batch_per_gpu},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"oracle/torch_port.py (reference torch-CPU operators, weight_norm recomputed per "
+                                   f"call) on 1x80x{T} mel, mean of {len(times)} steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.proc, self.path = None, f"/tmp/svk_clocks_{os.getpid()}.csv"
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            ident = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ident, f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, smax, power, reasons = [], [], [], set()
+        for ln in open(self.path):
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[0])), smax.append(float(p[1])), power.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(power))
+        return out
+
+
+# ----------------------------------------------------------------------------------- our arm
+def aggregate_profile(records, steps):
+    """Group per-launch records by kernel configuration; pick the group with the largest device time."""
+    groups = {}
+    for r in records:
+        key = (r["layer"], r["cin"], r["cout"], r["k"], r["dilation"])
+        g = groups.setdefault(key, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
+        g["ms"] += r["ms"]
+        g["n"] += 1
+        g["flops"] += r["flops"]
+        g["bytes"] += r["bytes"]
+    total_ms = sum(g["ms"] for g in groups.values())
+    # the "dominant kernel" is one template (conv_ffma_kernel); report the instantiation family with most time:
+    fam = {}
+    for (layer, cin, cout, k, dil), g in groups.items():
+        f = fam.setdefault((layer.startswith("resblock"), cin, k), {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0,
+                                                                    "layers": set()})
+        for q in ("ms", "n", "flops", "bytes"):
+            f[q] += g[q]
+        f["layers"].add(layer)
+    top_key, top = max(fam.items(), key=lambda kv: kv[1]["ms"])
+    by_layer = {}
+    for (layer, *_), g in groups.items():
+        by_layer[layer] = by_layer.get(layer, 0.0) + g["ms"]
+    return total_ms, top_key, top, by_layer
+
+
+def run_b200_arm(args):
+    import torch.distributed as dist
+
+    import svk_parallel as P
+    from models import SynthesizerTrn
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch ourselves the way the driver does
+        port = os.environ.get("MASTER_PORT", "29577")
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", port, os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: the B200 arm has no CPU fallback"}), flush=True)
+        return 2
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    cfg = load_cfg()
+    dims = W.dims_from_model_kwargs(513, **cfg["model"])
+    net = SynthesizerTrn(513, cfg["train"]["segment_size"] // cfg["data"]["hop_length"], n_speakers=cfg["data"]["n_speakers"],
+                         **cfg["model"])
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in W.make_state_dict(dims, seed=1234).items()})
+    net = net.cuda().eval()
+
+    B, T, K, Wm = args.batch_per_gpu, args.frames, args.steps, max(args.warmup, 3)
+    mel_h, len_h = synth_inputs(B, T, seed=rank)
+    mel_d, len_d = mel_h.to(dev), len_h.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    torch.manual_seed(1 + rank)
+    samples_per_step_rank = B * dims.hop * T
+
+    with torch.no_grad():
+        for _ in range(Wm):
+            o = net.infer(mel_d, len_d, noise_scale=NOISE_SCALE)[0]
+        torch.cuda.synchronize()
+        launches_per_step = net.last_launch_count()
+
+        # ---------------- timed region: K steps, inputs resident in HBM ----------------
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        net._handle.profile_begin(max_records=(launches_per_step + 8) * K)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        torch.cuda.synchronize()
+        ev0.record()
+        for i in range(K):
+            flush.fill_(i & 0xFF)  # evict L2 between steps
+            o = net.infer(mel_d, len_d, noise_scale=NOISE_SCALE)[0]
+        ev1.record()
+        torch.cuda.synchronize()
+        barrier()
+        elapsed_ms = ev0.elapsed_time(ev1)
+        records = net._handle.profile_end()
+        clocks = sampler.stop() if sampler else None
+        assert torch.isfinite(o).all()
+
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+
+        # ---------------- e2e: pinned host -> (scatter) -> infer -> (gather) -> pinned host ----------------
+        Ke = max(1, min(K, args.e2e_steps))
+        N_total = B * world
+        if rank == 0:
+            mel_all_h = torch.cat([synth_inputs(B, T, seed=r)[0] for r in range(world)]).pin_memory()
+            len_all_h = torch.full((N_total,), T, dtype=torch.int64).pin_memory()
+            pcm_h = torch.empty(N_total, 1, dims.hop * T).pin_memory()
+        infer_fn = lambda m, l: net.infer(m, l, noise_scale=NOISE_SCALE)[0]  # noqa: E731
+
+        def e2e_step():
+            if world == 1:
+                m = mel_all_h.to(dev, non_blocking=True)
+                l = len_all_h.to(dev, non_blocking=True)
+                pcm_h.copy_(infer_fn(m, l), non_blocking=True)
+            else:
+                m = mel_all_h.to(dev, non_blocking=True) if rank == 0 else None
+                l = len_all_h.to(dev, non_blocking=True) if rank == 0 else None
+                full = P.sharded_infer(infer_fn, m, l, N_total, 80, T, dims.hop, dev)
+                if rank == 0:
+                    pcm_h.copy_(full, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_step()  # warm (allocator, NCCL channels)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(Ke):
+            e2e_step()
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        e2e_wall = time.perf_counter() - t0
+        te = torch.tensor([max(e0.elapsed_time(e1) / 1e3, 0.0), e2e_wall], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te[1].item())  # wall clock bracketed by syncs: includes the host-side copies' latency
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------- report ----------------
+    peaks = measured_peaks()
+    prop = torch.cuda.get_device_properties(dev)
+    n_sm = prop.multi_processor_count
+    sm_max_mhz = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    ffma_peak_tf = n_sm * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+    total_samples = samples_per_step_rank * world * K
+    value = total_samples / (elapsed_ms / 1e3)
+    ms_per_step = elapsed_ms / K
+
+    prof_total_ms, top_key, top, by_layer = aggregate_profile(records, K)
+    avg_ms = top["ms"] / top["n"]
+    achieved_tf = (top["flops"] / top["n"]) / (avg_ms / 1e3) / 1e12
+    hbm_gbs = (top["bytes"] / top["n"]) / (avg_ms / 1e3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "fp32_ffma", "kernel": f"conv_ffma_kernel<K={top_key[2]}> Cin={top_key[1]} ({'+'.join(sorted(top['layers']))})",
+        "achieved": achieved_tf, "peak": ffma_peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / ffma_peak_tf,
+        "peak_source": f"{n_sm} SMs x 128 FFMA lanes x 2 x {sm_max_mhz:.0f} MHz (clocks.max.sm); the path is compute-bound "
+                       f"on the fp32 pipe (SURVEY F13), tensor pipe not used in this precision",
+        "traffic": traffic,
+        "launches_in_group": top["n"], "avg_launch_ms": avg_ms, "share_of_step": top["ms"] / prof_total_ms,
+        "algorithmic_flops_per_launch": top["flops"] / top["n"], "algorithmic_bytes_per_launch": top["bytes"] / top["n"],
+        "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": peaks["hbm_gbs"], "frac": hbm_gbs / peaks["hbm_gbs"],
+                "peak_source": peaks["_source"]},
+        "whole_step": {"tflops": FLOP_PER_FRAME * B * T / (ms_per_step / 1e3) / 1e12,
+                       "frac_of_ffma_peak": FLOP_PER_FRAME * B * T / (ms_per_step / 1e3) / 1e12 / ffma_peak_tf,
+                       "hbm_compulsory_frac": (BYTES_MIN_PER_FRAME * B * T + WEIGHT_BYTES_FP32) / (ms_per_step / 1e3) / 1e9 / peaks["hbm_gbs"],
+                       "kernel_time_share_by_layer": {k: v / prof_total_ms for k, v in sorted(by_layer.items(), key=lambda kv: -kv[1])}},
+    }
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        times = cpu_reference_run(1, T, steps=args.cpu_steps, warmup=1, threads=cores)
+        best = min(times)
+        cpu_baseline = {"value": 256 * T / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"oracle/torch_port.py (reference torch-CPU operators) on 1x80x{T} mel = 1/{B} of the step; "
+                                  f"best of {len(times)} after 1 warm-up; mean {statistics.mean(times):.2f}s",
+                        "rtf": best / (256 * T / SAMPLE_RATE)}
+
+    h2d = (mel_all_h.numel() * 4 + len_all_h.numel() * 8)
+    d2h = pcm_h.numel() * 4
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "rtf": (ms_per_step / 1e3) / (samples_per_step_rank / SAMPLE_RATE),
+        "config": {"workload": f"iitp_base.json full path (MelEncoder+flow^-1+Generator), {B}x80x{T} mel per GPU, fp32 "
+                               f"(BASELINE configs[2]{'; configs[4] sharding, weak' if world > 1 else ''})",
+                   "batch_per_gpu": B, "global_batch": B * world, "frames": T, "noise_scale": NOISE_SCALE,
+                   "weights": "seeded recipe svk_weights.make_state_dict(seed=1234), random init (no checkpoint exists)",
+                   "sharding": "utterances, no data-path collective" if world > 1 else "none",
+                   "l2": "256 MiB device write between steps (inside the timed region, <0.1 ms each); per-step working "
+                         "set ~2.3 GB >> 126 MB L2"},
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "e2e": {"value": N_total * dims.hop * T * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke,
+                "path": "pinned host -> H2D" + (" -> NCCL scatter" if world > 1 else "") + " -> SynthesizerTrn.infer (libsvk) -> "
+                        + ("NCCL gather -> " if world > 1 else "") + "D2H pinned host, eps drawn on device (models.py:336)"},
+        "gpu_launches": int(launches_per_step * K * world),
+        "clocks": clocks,
+        "device": prop.name,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch-per-gpu", type=int, default=16)
+    ap.add_argument("--frames", type=int, default=1024)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -121,6 +121,38 @@ int svk_infer_host(svk_handle *h, const float *mel, const int64_t *lengths, cons
 /* Kernels launched by the most recent svk_infer / module call on this handle. */
 int64_t svk_last_launch_count(const svk_handle *h);
 
+/* ---- per-launch timing (bench.py's roofline leg) ---------------------------------------------
+ * Between svk_profile_begin and svk_profile_end every kernel the handle launches is bracketed by
+ * CUDA events on the launching stream.  svk_profile_end synchronises those events and returns one
+ * record per launch with its ALGORITHMIC work (convolution MACs*2 as SURVEY 8(d) counts them;
+ * compulsory bytes = inputs + outputs + weights of that launch).  No reference counterpart
+ * (the reference has no profiler). */
+#define SVK_LAYER_OTHER 0      /* mask / sample / flip */
+#define SVK_LAYER_PRE_ENC 1
+#define SVK_LAYER_WN_IN 2      /* k=5 conv + gate */
+#define SVK_LAYER_WN_RES_SKIP 3
+#define SVK_LAYER_PROJ 4
+#define SVK_LAYER_FLOW_PRE 5
+#define SVK_LAYER_FLOW_POST 6
+#define SVK_LAYER_CONV_PRE 7
+#define SVK_LAYER_UPSAMPLE 8
+#define SVK_LAYER_RESBLOCK_CONV1 9   /* dilated */
+#define SVK_LAYER_RESBLOCK_CONV2 10
+#define SVK_LAYER_CONV_POST 11
+typedef struct svk_launch_record {
+  int32_t layer;      /* SVK_LAYER_* */
+  int32_t cin, cout;  /* logical channels */
+  int32_t k, dilation;
+  int32_t batch;
+  int64_t length;     /* output positions per row */
+  double flops;       /* algorithmic */
+  double bytes;       /* algorithmic (compulsory) */
+  float ms;           /* device time between the bracketing events */
+  int32_t reserved;
+} svk_launch_record;
+int svk_profile_begin(svk_handle *h, int max_records);
+int svk_profile_end(svk_handle *h, svk_launch_record *out, int max_records, int *n_records);
+
 /* ---- module-level entry points (use the handle's folded weights; device pointers) -----------
  * MelEncoder.forward (models.py:35-47): x_out/m/logs [B,hidden|inter,T], mask [B,1,T]. */
 int svk_mel_encoder(svk_handle *h, const float *mel_dev, const int64_t *lengths_dev, int B, int T,

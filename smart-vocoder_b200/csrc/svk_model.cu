@@ -105,6 +105,12 @@ struct svk_handle {
 
   int64_t launches = 0;
 
+  // svk_profile_begin/end state
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;   // 2 per record
+  std::vector<svk_launch_record> prof_records;
+  size_t prof_cap = 0;
+
   // svk_infer_host state
   cudaStream_t host_stream = nullptr;
   void* host_dev = nullptr;
@@ -212,6 +218,7 @@ struct Folded {
 
 // weight_norm fold: norm over dims != 0, accumulated in double, rounded once.
 int fold_layer(svk_handle* h, const std::string& prefix, Folded* out) {
+  *out = Folded();
   auto itv = h->raw.find(prefix + ".weight_v");
   const HostTensor* wt = nullptr;
   if (itv != h->raw.end()) {
@@ -360,6 +367,7 @@ extern "C" void svk_destroy(svk_handle* h) {
   if (h->d_blob) cudaFree(h->d_blob);
   if (h->host_dev) cudaFree(h->host_dev);
   if (h->host_stream) cudaStreamDestroy(h->host_stream);
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   delete h;
 }
 
@@ -502,9 +510,40 @@ struct Runner {
     a.e[0].ch_sign = a.e[1].ch_sign = 1;
     return a;
   }
-  void run(const ConvArgs& a) {
+  // algorithmic work of one conv launch (MACs*2 over the convolution only)
+  bool prof_open(int layer, const ConvArgs& a, int cout_logical, int64_t out_len, double macs) {
+    if (!h->profiling || h->prof_records.size() >= h->prof_cap) return false;
+    svk_launch_record r;
+    memset(&r, 0, sizeof(r));
+    r.layer = layer, r.cin = a.Cin, r.cout = cout_logical, r.k = a.K, r.dilation = a.dil, r.batch = B;
+    r.length = out_len;
+    r.flops = 2.0 * macs;
+    double bytes = 4.0 * ((double)B * a.Cin * a.Lin + (double)B * cout_logical * out_len + (double)a.Cin * a.K * a.Cout);
+    for (int s = 0; s < 2; ++s) {
+      if (a.e[s].res) bytes += 4.0 * B * (double)out_len * (s == 0 ? (a.split < a.Cout ? a.split : a.Cout) : a.Cout - a.split);
+      if (a.e[s].acc_in) bytes += 4.0 * B * (double)out_len * (s == 0 ? (a.split < a.Cout ? a.split : a.Cout) : a.Cout - a.split);
+    }
+    r.bytes = bytes;
+    h->prof_records.push_back(r);
+    cudaEventRecord(h->prof_events[2 * (h->prof_records.size() - 1)], stream);
+    return true;
+  }
+  void prof_close(bool open) {
+    if (open) cudaEventRecord(h->prof_events[2 * (h->prof_records.size() - 1) + 1], stream);
+  }
+  void run(const ConvArgs& a, int layer = SVK_LAYER_OTHER) {
     if (err != cudaSuccess) return;
+    int cout_logical = a.Cout;
+    int64_t out_len = a.Lout;
+    double macs = (double)B * a.Lout * (double)a.Cout * a.Cin * a.K;
+    if (a.mode == MODE_GATE) cout_logical = a.Cout / 2;
+    if (a.mode == MODE_SHUFFLE) {  // counted as L_in * Cin * Cout * k
+      cout_logical = a.Cout / a.shuf_s, out_len = a.shuf_Lout;
+      macs = (double)B * a.Lin * (double)a.Cin * a.Cout * a.K;
+    }
+    const bool open = prof_open(layer, a, cout_logical, out_len, macs);
     err = launch_conv_ffma(a, stream);
+    prof_close(open);
     h->launches++;
   }
   void note(cudaError_t e) {
@@ -520,7 +559,7 @@ struct Runner {
       ConvArgs a = base(in[i], x, H, 0, T, T, 1, (k - 1) / 2, T, T);
       a.mode = MODE_GATE;
       a.e[0].y = acts, a.e[0].C = H;
-      run(a);
+      run(a, SVK_LAYER_WN_IN);
       ConvArgs r = base(rs[i], acts, H, 0, T, T, 1, 0, T, T);
       r.out_mask = mask, r.mask_stride = T;
       if (i < n - 1) {
@@ -530,7 +569,7 @@ struct Runner {
       } else {
         r.e[0].acc_in = i ? out : nullptr, r.e[0].y = out, r.e[0].C = H, r.e[0].use_mask = 1;  // (out + rs) * mask
       }
-      run(r);
+      run(r, SVK_LAYER_WN_RES_SKIP);
     }
   }
 
@@ -544,7 +583,7 @@ struct Runner {
       ConvArgs a = base(rb.c1[l], src, C, 0, L, L, d, (rb.k * d - d) / 2, L, L);
       a.pre_slope = 0.1f;
       a.e[0].y = xt, a.e[0].C = C;
-      run(a);
+      run(a, SVK_LAYER_RESBLOCK_CONV1);
       ConvArgs b = base(rb.c2[l], xt, C, 0, L, L, 1, (rb.k - 1) / 2, L, L);
       b.pre_slope = 0.1f;
       b.e[0].res = src, b.e[0].C = C;
@@ -553,7 +592,7 @@ struct Runner {
       } else {
         b.e[0].y = dst, b.e[0].acc_in = acc_in, b.post_div = post_div;
       }
-      run(b);
+      run(b, SVK_LAYER_RESBLOCK_CONV2);
     }
   }
 };
@@ -585,7 +624,7 @@ void run_decoder(Runner& R, const float* z, int z_stride, const float* in_mask, 
     ConvArgs a = R.base(h->conv_pre, z, c.inter_channels, 0, z_stride, L, 1, 3, L, L);
     a.in_mask = in_mask, a.mask_stride = z_stride;
     a.e[0].y = buf[1], a.e[0].C = U;
-    R.run(a);
+    R.run(a, SVK_LAYER_CONV_PRE);
   }
   const float* prev = buf[1];
   int prevC = U, len = L;
@@ -608,7 +647,7 @@ void run_decoder(Runner& R, const float* z, int z_stride, const float* in_mask, 
       a.mode = MODE_SHUFFLE;
       a.shuf_s = up.s, a.shuf_p = up.p, a.shuf_Lout = Lout;
       a.e[0].y = X, a.e[0].C = C;
-      R.run(a);
+      R.run(a, SVK_LAYER_UPSAMPLE);
     }
     // xs = sum_j resblock_j(x); x = xs / num_kernels (models.py:150-155)
     const int nk = c.n_resblock_kernels;
@@ -624,7 +663,7 @@ void run_decoder(Runner& R, const float* z, int z_stride, const float* in_mask, 
     a.pre_slope = 0.01f;
     a.act_tanh = 1;
     a.e[0].y = o, a.e[0].C = 1;
-    R.run(a);
+    R.run(a, SVK_LAYER_CONV_POST);
   }
 }
 
@@ -667,7 +706,7 @@ void run_mel_encoder(Runner& R, const float* mel, const float* mask, int T, floa
   ConvArgs a = R.base(h->pre_enc, mel, c.n_mel, 0, T, T, 1, 0, T, T);
   a.out_mask = mask, a.mask_stride = T;
   a.e[0].y = hbuf, a.e[0].C = H, a.e[0].use_mask = 1;
-  R.run(a);
+  R.run(a, SVK_LAYER_PRE_ENC);
   R.wn(h->enc_in, h->enc_rs, hbuf, acts, out, mask, T);
   // stats = proj(x) * x_mask; m, logs = split(stats) (models.py:44-46)
   ConvArgs p = R.base(h->proj, out, H, 0, T, T, 1, 0, T, T);
@@ -675,7 +714,7 @@ void run_mel_encoder(Runner& R, const float* mel, const float* mask, int T, floa
   p.split = C;
   p.e[0].y = m, p.e[0].C = C, p.e[0].use_mask = 1;
   p.e[1].y = logs, p.e[1].C = C, p.e[1].use_mask = 1;
-  R.run(p);
+  R.run(p, SVK_LAYER_PROJ);
 }
 
 // ResidualCouplingBlock.forward(reverse=True) in place on z (models.py:77-79, modules.py:324-343).
@@ -689,7 +728,7 @@ void run_flow_reverse(Runner& R, float* z, const float* mask, int T, float* hbuf
     ConvArgs a = R.base(L.pre, z, C, L.orient ? half : 0, T, T, 1, 0, T, T);
     a.out_mask = mask, a.mask_stride = T;
     a.e[0].y = hbuf, a.e[0].C = H, a.e[0].use_mask = 1;
-    R.run(a);
+    R.run(a, SVK_LAYER_FLOW_PRE);
     R.wn(L.in, L.rs, hbuf, acts, out, mask, T);
     // x1 = (x1 - post(h) * mask) * mask, written over x1's storage channels
     ConvArgs p = R.base(L.post, out, H, 0, T, T, 1, 0, T, T);
@@ -700,7 +739,7 @@ void run_flow_reverse(Runner& R, float* z, const float* mask, int T, float* hbuf
     } else {
       p.e[0].ch_off = half, p.e[0].ch_sign = 1;
     }
-    R.run(p);
+    R.run(p, SVK_LAYER_FLOW_POST);
   }
 }
 
@@ -713,6 +752,37 @@ extern "C" size_t svk_workspace_bytes(const svk_handle* h, int B, int T, int max
 }
 
 extern "C" int64_t svk_last_launch_count(const svk_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int svk_profile_begin(svk_handle* h, int max_records) {
+  if (!h || max_records <= 0) return fail(SVK_ERR_INVALID, "svk_profile_begin: bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  while (h->prof_events.size() < 2 * (size_t)max_records) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreate(&e));
+    h->prof_events.push_back(e);
+  }
+  h->prof_records.clear();
+  h->prof_cap = (size_t)max_records;
+  h->profiling = true;
+  return SVK_OK;
+}
+
+extern "C" int svk_profile_end(svk_handle* h, svk_launch_record* out, int max_records, int* n_records) {
+  if (!h || !n_records) return fail(SVK_ERR_INVALID, "svk_profile_end: bad argument");
+  h->profiling = false;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t n = h->prof_records.size();
+  for (size_t i = 0; i < n; ++i) {
+    CUDA_TRY(cudaEventSynchronize(h->prof_events[2 * i + 1]));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->prof_events[2 * i], h->prof_events[2 * i + 1]));
+    h->prof_records[i].ms = ms;
+  }
+  int m = 0;
+  for (size_t i = 0; i < n && out && m < max_records; ++i) out[m++] = h->prof_records[i];
+  *n_records = (int)n;
+  return SVK_OK;
+}
 
 extern "C" int svk_infer(svk_handle* h, const float* mel, const int64_t* lengths, const float* eps,
                          float noise_scale, int B, int T, int max_len, float* o, float* x_mask, float* z,

@@ -56,6 +56,16 @@ class SvkConfig(ctypes.Structure):
     ]
 
 
+class SvkLaunchRecord(ctypes.Structure):
+    _fields_ = [("layer", ctypes.c_int32), ("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("k", ctypes.c_int32),
+                ("dilation", ctypes.c_int32), ("batch", ctypes.c_int32), ("length", ctypes.c_int64),
+                ("flops", ctypes.c_double), ("bytes", ctypes.c_double), ("ms", ctypes.c_float),
+                ("reserved", ctypes.c_int32)]
+
+
+LAYER_NAMES = {0: "other", 1: "pre_enc", 2: "wn_in", 3: "wn_res_skip", 4: "proj", 5: "flow_pre", 6: "flow_post",
+               7: "conv_pre", 8: "upsample", 9: "resblock_conv1", 10: "resblock_conv2", 11: "conv_post"}
+
 _lib: Optional[ctypes.CDLL] = None
 
 _vp, _i, _i64, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
@@ -73,6 +83,8 @@ SIGNATURES = {
     "svk_infer": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "svk_infer_host": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "svk_last_launch_count": (_i64, [_vp]),
+    "svk_profile_begin": (_i, [_vp, _i]),
+    "svk_profile_end": (_i, [_vp, _vp, _i, ctypes.POINTER(_i)]),
     "svk_mel_encoder": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "svk_flow_reverse": (_i, [_vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "svk_generator": (_i, [_vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
@@ -183,3 +195,18 @@ class Handle:
 
     def last_launch_count(self) -> int:
         return int(lib().svk_last_launch_count(self._h))
+
+    def profile_begin(self, max_records: int = 8192):
+        self._prof_cap = int(max_records)
+        check(lib().svk_profile_begin(self._h, self._prof_cap))
+
+    def profile_end(self):
+        """-> list of dicts (layer, cin, cout, k, dilation, batch, length, flops, bytes, ms)."""
+        buf = (SvkLaunchRecord * self._prof_cap)()
+        n = _i()
+        check(lib().svk_profile_end(self._h, buf, self._prof_cap, ctypes.byref(n)))
+        out = []
+        for r in buf[:min(n.value, self._prof_cap)]:
+            out.append(dict(layer=LAYER_NAMES.get(r.layer, str(r.layer)), cin=r.cin, cout=r.cout, k=r.k,
+                            dilation=r.dilation, batch=r.batch, length=r.length, flops=r.flops, bytes=r.bytes, ms=r.ms))
+        return out

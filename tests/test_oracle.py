@@ -111,3 +111,19 @@ def test_spline_argument_checks():
     with pytest.raises(ValueError):
         Oracle().rq_spline(np.zeros((1,)), np.zeros((1, 10)), np.zeros((1, 10)), np.zeros((1, 9)), False,
                            min_bin_width=0.2)
+
+
+def test_torch_port_matches_reference_golden(base_sd, base_dims):
+    """oracle/torch_port.py (the CPU-baseline leg of bench.py) reproduces the reference's fp32 output."""
+    import torch
+    from oracle import torch_port
+    g = load_golden("infer_base_b2_t40")
+    sd = {k: torch.from_numpy(v) for k, v in base_sd.items()}
+    o, mask, (z, z_p, m_p, logs_p) = torch_port.infer(sd, base_dims, torch.from_numpy(g["mel"]),
+                                                      torch.from_numpy(g["lengths"]), torch.from_numpy(g["eps"]),
+                                                      float(g["noise_scale"]), _max_len(g))
+    assert np.array_equal(mask.numpy(), g["ref32_x_mask"])
+    # same operators, same order, same threads -> identical up to MKL-DNN blocking choices
+    assert np.abs(o.numpy() - g["ref32_o"]).max() <= 1e-5
+    assert np.abs(o.numpy() - g["ref64_o"]).max() <= 5e-5
+    assert np.abs(z.numpy() - g["ref64_z"]).max() <= 5e-5

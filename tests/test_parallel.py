@@ -1,0 +1,72 @@
+"""world_size-2 gloo tests (CPU) for the utterance sharding plumbing used by bench.py --gpus N."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import PKG, ROOT
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _fake_infer(mel, lengths):
+    # deterministic stand-in with the right shape: 4 samples per frame, depends on mel and length
+    B, C, T = mel.shape
+    pcm = mel.sum(1, keepdim=True).repeat_interleave(4, dim=2)
+    return pcm + lengths.view(B, 1, 1).float()
+
+
+def _worker(rank, world, port, n_utt, q):
+    import sys
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import svk_parallel as P
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        T, C = 6, 3
+        g = torch.Generator().manual_seed(0)
+        mel = torch.randn(n_utt, C, T, generator=g)
+        lengths = torch.arange(n_utt, dtype=torch.int64) + 1
+        out = P.sharded_infer(_fake_infer, mel if rank == 0 else None, lengths if rank == 0 else None, n_utt, C, T, 4,
+                              torch.device("cpu"))
+        if rank == 0:
+            q.put(bool(torch.equal(out, _fake_infer(mel, lengths))))
+        else:
+            assert out is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_utt", [4, 5, 1])
+def test_sharded_infer_gloo_world2(n_utt):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_utt, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
+
+
+def test_shard_bounds():
+    import svk_parallel as P
+    assert P.shard_bounds(512, 8) == [(64 * i, 64 * (i + 1)) for i in range(8)]
+    assert P.shard_bounds(5, 2) == [(0, 3), (3, 5)]
+    assert P.shard_bounds(1, 4) == [(0, 1), (1, 1), (1, 1), (1, 1)]
+    for n in range(0, 20):
+        for w in range(1, 9):
+            b = P.shard_bounds(n, w)
+            assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
