@@ -62,6 +62,25 @@ int conv_ffma_channel_tile(int cout);
 bool conv_ffma_supports_k(int k);
 cudaError_t launch_conv_ffma(const ConvArgs& a, cudaStream_t stream);
 
+// ---- tcgen05 path (conv_tc.cu): same ConvArgs semantics, weights pre-split into fp16 hi/lo images.
+constexpr int TC_KC = 32;  // input channels per staged chunk (Cin must be a multiple)
+struct ConvTcArgs {
+  ConvArgs c;           // c.wp unused; c.bias = fp32 bias [Cout] (unscaled)
+  const uint16_t* wtc;  // packed image, see conv_tc_pack
+  float unscale;        // 1 / weight scale (power of two)
+  int N;                // output channels per CTA (multiple of 16, <= 256)
+  int nsub;             // 128-row time sub-tiles per CTA (1 or 2)
+  int sep_cross;        // keep the hi*lo cross terms in their own TMEM accumulator
+  int nw;               // weight pipeline stages
+  int rows, tmem_cols;  // filled by launch_conv_tc
+};
+int conv_tc_rows(int K, int dil, int nsub);
+size_t conv_tc_smem_bytes(int N, int K, int dil, int nsub, int nw);
+size_t conv_tc_packed_halves(int Cin, int Cout, int K, int N);
+float conv_tc_weight_scale(const float* w, size_t n);
+void conv_tc_pack(const float* w_ock, int Cout, int Cin, int K, int N, float scale, uint16_t* out);
+cudaError_t launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream);
+
 // elementwise / small kernels
 cudaError_t launch_sequence_mask(const int64_t* lengths, int B, int T, float* mask, cudaStream_t s);
 cudaError_t launch_flip(const float* x, int B, int C, int T, float* y, cudaStream_t s);
