@@ -44,7 +44,11 @@ extern "C" {
 #define SVK_RESBLOCK_PAIRS 3
 
 /* Arithmetic of the convolution stacks. */
-#define SVK_PRECISION_FP32 0   /* fp32 FFMA everywhere (the 1e-4 parity path)            */
+#define SVK_PRECISION_FP32 0   /* fp32 FFMA everywhere                                    */
+#define SVK_PRECISION_TC 1     /* fp32-class results on the tensor cores: every conv whose widths
+                                  allow it runs as a 3-product fp16 split (hi*hi + hi*lo + lo*hi,
+                                  fp32 accumulate in TMEM) on tcgen05; the rest stays on FFMA.
+                                  Meets the same 1e-4 bar as SVK_PRECISION_FP32.            */
 
 /*
  * Effective hyper-parameters of SynthesizerTrn.__init__ (reference models.py:266-314).
@@ -178,6 +182,15 @@ int svk_conv1d(const float *x_dev, int B, int Cin, int L, const float *w_dev, co
 int svk_conv_transpose1d(const float *x_dev, int B, int Cin, int L, const float *w_dev,
                          const float *bias_dev, int Cout, int k, int stride, int padding,
                          float pre_slope, float *y_dev, void *stream);
+/* The same two operators on the tcgen05 engine (SVK_PRECISION_TC arithmetic: fp16 hi/lo split,
+ * fp32 accumulate in TMEM).  Cin must be a multiple of 32.  Weight images are rebuilt per call
+ * (these are parity-test entry points; the hot path packs once in svk_finalize_weights). */
+int svk_conv1d_tc(const float *x_dev, int B, int Cin, int L, const float *w_dev, const float *bias_dev,
+                  int Cout, int k, int dilation, int padding, float pre_slope, float *y_dev,
+                  void *stream);
+int svk_conv_transpose1d_tc(const float *x_dev, int B, int Cin, int L, const float *w_dev,
+                            const float *bias_dev, int Cout, int k, int stride, int padding,
+                            float pre_slope, float *y_dev, void *stream);
 /* commons.sequence_mask(...).to(float) (commons.py:121-125, models.py:40): mask [B,T]. */
 int svk_sequence_mask(const int64_t *lengths_dev, int B, int T, float *mask_dev, void *stream);
 /* modules.Flip (modules.py:270-277): y[b,c,t] = x[b,C-1-c,t]. Bit-exact copy. */

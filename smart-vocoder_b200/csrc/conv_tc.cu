@@ -35,7 +35,7 @@ namespace {
 
 constexpr int KC = TC_KC;  // input channels per A chunk
 constexpr int KG = KC / 8;  // 16-byte k-groups per chunk
-constexpr int NA = 2;       // A ring depth
+constexpr int NA = 2;       // A ring depth (max)
 constexpr int MAXNW = 6;    // weight ring depth limit
 constexpr int THREADS = 192;
 constexpr int PRODUCERS = 128;
@@ -149,12 +149,12 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 }
 
 // ------------------------------------------------------------------------------------- kernel
-__global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta) {
+__global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcArgs ta) {
   extern __shared__ __align__(128) uint8_t smem[];
   const ConvArgs& a = ta.c;
   SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int N = ta.N, nsub = ta.nsub, nw = ta.nw;
+  const int N = ta.N, nsub = ta.nsub, nw = ta.nw, na = ta.na;
   const int nacc = ta.sep_cross ? 2 : 1;
   const int K = a.K, dil = a.dil;
   const int rows = ta.rows;                      // staged time rows per chunk (multiple of 8)
@@ -163,13 +163,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta
   const uint32_t w_plane = (uint32_t)N * 16u;
   const uint32_t w_stage = w_plane * KG * 2u;
   uint8_t* a_smem = smem + HEADER_BYTES;
-  uint8_t* w_smem = a_smem + NA * a_stage;
+  uint8_t* w_smem = a_smem + na * a_stage;
   const int t0 = blockIdx.x * (128 * nsub), ntile = blockIdx.y, b = blockIdx.z;
   const int nchunks = a.Cin / KC;
   const uint32_t tmem_cols = ta.tmem_cols;
 
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < NA; ++i) mbar_init(&hdr->a_full[i], PRODUCERS), mbar_init(&hdr->a_empty[i], 1);
+    for (int i = 0; i < na; ++i) mbar_init(&hdr->a_full[i], PRODUCERS), mbar_init(&hdr->a_empty[i], 1);
     for (int i = 0; i < nw; ++i) mbar_init(&hdr->w_full[i], 1), mbar_init(&hdr->w_empty[i], 1);
     mbar_init(&hdr->acc_full, 1);
     fence_barrier_init();
@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta
       int wst = 0;
       uint32_t wph = 0;
       for (int ch = 0; ch < nchunks; ++ch) {
-        const int as = ch & 1;
-        mbar_wait(&hdr->a_full[as], (ch >> 1) & 1);
+        const int as = ch % na;
+        mbar_wait(&hdr->a_full[as], (ch / na) & 1);
         tc_fence_after();
         const uint32_t a_hi = smem_u32(a_smem + (size_t)as * a_stage), a_lo = a_hi + a_plane * KG;
         for (int j = 0; j < K; ++j) {
@@ -238,35 +238,37 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta
     __syncwarp();
   } else {
     // ------------------------------------------------ activation producers (128 threads)
+    // One task = one time row x all KC channels of the chunk: 32 independent coalesced loads in
+    // flight per thread, then leaky_relu / mask / fp16 hi-lo split and 2 x 4 conflict-free 16 B stores.
     const int rp = tid - 64;
     const float slope = a.pre_slope;
     const float* mrow = a.in_mask ? a.in_mask + (size_t)b * a.mask_stride : nullptr;
     for (int ch = 0; ch < nchunks; ++ch) {
-      const int as = ch & 1;
-      mbar_wait(&hdr->a_empty[as], ((ch >> 1) & 1) ^ 1);
+      const int as = ch % na;
+      mbar_wait(&hdr->a_empty[as], ((ch / na) & 1) ^ 1);
       uint4* Ahi = reinterpret_cast<uint4*>(a_smem + (size_t)as * a_stage);
       uint4* Alo = Ahi + KG * rows;
-#pragma unroll 1
-      for (int kg = 0; kg < KG; ++kg) {
-        const float* xb = a.x + ((size_t)b * a.x_C + a.x_ch_off + ch * KC + kg * 8) * a.x_stride;
-        for (int r = rp; r < rows; r += PRODUCERS) {
-          const int t = t0 - a.pad + r;
-          const bool ok = t >= 0 && t < a.Lin;
-          float v[8];
+      const float* xb = a.x + ((size_t)b * a.x_C + a.x_ch_off + ch * KC) * a.x_stride;
+      for (int r = rp; r < rows; r += PRODUCERS) {
+        const int t = t0 - a.pad + r;
+        const bool ok = t >= 0 && t < a.Lin;
+        float v[KC];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = ok ? __ldg(xb + (size_t)e * a.x_stride + t) : 0.f;
-          const float mk = (ok && mrow) ? __ldg(mrow + t) : 1.0f;
+        for (int c = 0; c < KC; ++c) v[c] = ok ? __ldg(xb + (size_t)c * a.x_stride + t) : 0.f;
+        const float mk = (ok && mrow) ? __ldg(mrow + t) : 1.0f;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float q = v[e];
-            q = q > 0.f ? q : q * slope;
-            v[e] = mrow ? q * mk : q;
-          }
+        for (int c = 0; c < KC; ++c) {
+          float q = v[c];
+          q = q > 0.f ? q : q * slope;
+          v[c] = mrow ? q * mk : q;
+        }
+#pragma unroll
+        for (int kg = 0; kg < KG; ++kg) {
           uint4 h, l;
-          split2(v[0], v[1], h.x, l.x);
-          split2(v[2], v[3], h.y, l.y);
-          split2(v[4], v[5], h.z, l.z);
-          split2(v[6], v[7], h.w, l.w);
+          split2(v[kg * 8 + 0], v[kg * 8 + 1], h.x, l.x);
+          split2(v[kg * 8 + 2], v[kg * 8 + 3], h.y, l.y);
+          split2(v[kg * 8 + 4], v[kg * 8 + 5], h.z, l.z);
+          split2(v[kg * 8 + 6], v[kg * 8 + 7], h.w, l.w);
           Ahi[kg * rows + r] = h;
           Alo[kg * rows + r] = l;
         }
@@ -286,36 +288,157 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta
     const int o_tile = ntile * N;
     for (int sub = 0; sub < nsub; ++sub) {
       const int t = t0 + sub * 128 + row;
-      const bool tin = t < a.Lout;
-      const float mv = (omask && tin) ? omask[t] : 1.0f;
-      for (int n0 = 0; n0 < N; n0 += 16) {
-        uint32_t m[16], c[16];
-        tmem_ld16(tlane + (uint32_t)(sub * nacc * N + n0), m);
-        if (nacc == 2) tmem_ld16(tlane + (uint32_t)((sub * nacc + 1) * N + n0), c);
-        tmem_wait_ld();
-        if (a.mode == MODE_STORE) {
+      const uint32_t tsub = tlane + (uint32_t)(sub * nacc * N);
+
+      if (a.mode == MODE_STORE) {
+        // y = ((acc/s + bias) + (res + acc_in)) / post_div * mask, tanh; res / acc_in of the NEXT 16
+        // channels are in flight while the current 16 are finished (same element is read then
+        // written by the same thread only, so in-place operation is safe).
+        const bool tin = t < a.Lout;
+        const float mv = (omask && tin) ? omask[t] : 1.0f;
+        const float* res_c = nullptr;
+        const float* acc_c = nullptr;
+        float* y_c = nullptr;
+        ptrdiff_t step_c = 0;
+        int um_c = 0, nv_c = 0;
+        float r1[16];
+        auto chunk_params = [&](int n0, const float*& res, const float*& accin, float*& y, ptrdiff_t& step, int& um,
+                                int& nvalid) {
+          const int o0 = o_tile + n0;
+          const bool s1 = o0 >= a.split;
+          const int rel0 = s1 ? o0 - a.split : o0;
+          const int dC = s1 ? a.e[1].C : a.e[0].C, dch = s1 ? a.e[1].ch_off : a.e[0].ch_off;
+          const int dsg = s1 ? a.e[1].ch_sign : a.e[0].ch_sign;
+          const size_t off = ((size_t)b * dC + dch + dsg * rel0) * a.y_stride + t;
+          const float* rs = s1 ? a.e[1].res : a.e[0].res;
+          const float* ai = s1 ? a.e[1].acc_in : a.e[0].acc_in;
+          res = rs ? rs + off : nullptr;
+          accin = ai ? ai + off : nullptr;
+          y = (s1 ? a.e[1].y : a.e[0].y) + off;
+          step = (ptrdiff_t)dsg * a.y_stride;
+          um = s1 ? a.e[1].use_mask : a.e[0].use_mask;
+          nvalid = tin ? min(16, a.Cout - o0) : 0;
+        };
+        auto load16 = [&](const float* res, const float* accin, ptrdiff_t step, int nvalid, float (&q1)[16]) {
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const int o = o_tile + n0 + e;
-            if (o < a.Cout && tin) {
+            const float u1 = (res && e < nvalid) ? res[e * step] : 0.f;
+            const float u2 = (accin && e < nvalid) ? accin[e * step] : 0.f;
+            q1[e] = u1 + u2;
+          }
+        };
+        chunk_params(0, res_c, acc_c, y_c, step_c, um_c, nv_c);
+        load16(res_c, acc_c, step_c, nv_c, r1);
+        for (int n0 = 0; n0 < N; n0 += 16) {
+          const float* res_n = nullptr;
+          const float* acc_n = nullptr;
+          float* y_n = nullptr;
+          ptrdiff_t step_n = 0;
+          int um_n = 0, nv_n = 0;
+          float p1[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) p1[e] = 0.f;
+          if (n0 + 16 < N) {
+            chunk_params(n0 + 16, res_n, acc_n, y_n, step_n, um_n, nv_n);
+            load16(res_n, acc_n, step_n, nv_n, p1);
+          }
+          uint32_t m[16], c[16];
+          tmem_ld16(tsub + (uint32_t)n0, m);
+          if (nacc == 2) tmem_ld16(tsub + (uint32_t)(N + n0), c);
+          tmem_wait_ld();
+          const float* bptr = a.bias + o_tile + n0;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            if (e < nv_c) {
               float v = __uint_as_float(m[e]);
               if (nacc == 2) v += __uint_as_float(c[e]);
-              v = fmaf(v, unscale, __ldg(a.bias + o));
-              const bool s1 = o >= a.split;
-              const int rel = s1 ? o - a.split : o;
-              const int dC = s1 ? a.e[1].C : a.e[0].C, dch = s1 ? a.e[1].ch_off : a.e[0].ch_off;
-              const int dsg = s1 ? a.e[1].ch_sign : a.e[0].ch_sign;
-              const float* res = s1 ? a.e[1].res : a.e[0].res;
-              const float* acc_in = s1 ? a.e[1].acc_in : a.e[0].acc_in;
-              float* y = s1 ? a.e[1].y : a.e[0].y;
-              const int um = s1 ? a.e[1].use_mask : a.e[0].use_mask;
-              const size_t off = ((size_t)b * dC + dch + dsg * rel) * a.y_stride + t;
-              if (res) v += res[off];
-              if (acc_in) v += acc_in[off];
+              v = fmaf(v, unscale, __ldg(bptr + e));
+              v += r1[e];
               if (a.post_div != 1.0f) v = v / a.post_div;
-              if (um && omask) v *= mv;
+              if (um_c && omask) v *= mv;
               if (a.act_tanh) v = tanhf(v);
-              y[off] = v;
+              y_c[e * step_c] = v;
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 16; ++e) r1[e] = p1[e];
+          res_c = res_n, acc_c = acc_n, y_c = y_n, step_c = step_n, um_c = um_n, nv_c = nv_n;
+        }
+      } else if (a.mode == MODE_GATE) {
+        // columns [0, N/2) hold the tanh half, [N/2, N) the sigmoid half of channels
+        // ntile*N/2 + [0, N/2) (commons.py:100-107); bias is in the same virtual order.
+        const bool tin = t < a.Lout;
+        const int half = N >> 1;
+        const float* bptr = a.bias + o_tile;
+        float* ybase = a.e[0].y + ((size_t)b * a.e[0].C + a.e[0].ch_off + ntile * half) * a.y_stride + t;
+        for (int n0 = 0; n0 < half; n0 += 16) {
+          uint32_t mt[16], ms[16], ct[16], cs[16];
+          tmem_ld16(tsub + (uint32_t)n0, mt);
+          tmem_ld16(tsub + (uint32_t)(half + n0), ms);
+          if (nacc == 2) {
+            tmem_ld16(tsub + (uint32_t)(N + n0), ct);
+            tmem_ld16(tsub + (uint32_t)(N + half + n0), cs);
+          }
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int cidx = ntile * half + n0 + e;
+            if (tin && cidx < (a.Cout >> 1)) {
+              float vt = __uint_as_float(mt[e]), vs = __uint_as_float(ms[e]);
+              if (nacc == 2) vt += __uint_as_float(ct[e]), vs += __uint_as_float(cs[e]);
+              vt = fmaf(vt, unscale, __ldg(bptr + n0 + e));
+              vs = fmaf(vs, unscale, __ldg(bptr + half + n0 + e));
+              ybase[(size_t)(n0 + e) * a.y_stride] = tanhf(vt) * sigmoidf_(vs);
+            }
+          }
+        }
+      } else {
+        // MODE_SHUFFLE: virtual channel o' = co*s + r of time row q lands at y[co, s*q + r - p]
+        // (ConvTranspose1d polyphase form).
+        const int s = a.shuf_s;
+        const bool qin = t < a.Lout;
+        float* ybase = a.e[0].y + ((size_t)b * a.e[0].C + a.e[0].ch_off) * a.y_stride;
+        for (int n0 = 0; n0 < N; n0 += 16) {
+          uint32_t m[16], c[16];
+          tmem_ld16(tsub + (uint32_t)n0, m);
+          if (nacc == 2) tmem_ld16(tsub + (uint32_t)(N + n0), c);
+          tmem_wait_ld();
+          const int o0 = o_tile + n0;
+          float v[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            float q = __uint_as_float(m[e]);
+            if (nacc == 2) q += __uint_as_float(c[e]);
+            v[e] = fmaf(q, unscale, (o0 + e < a.Cout) ? __ldg(a.bias + o0 + e) : 0.f);
+          }
+          if (!qin) continue;
+          if (s == 8 && (a.shuf_p & 3) == 0) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const int co = (o0 >> 3) + g;
+              if (o0 + 8 * g >= a.Cout) break;
+              float* yrow = ybase + (size_t)co * a.y_stride;
+              const int tt = 8 * t - a.shuf_p;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int th = tt + 4 * h;
+                if (th >= 0 && th + 3 < a.shuf_Lout) {
+                  *reinterpret_cast<float4*>(yrow + th) =
+                      make_float4(v[8 * g + 4 * h], v[8 * g + 4 * h + 1], v[8 * g + 4 * h + 2], v[8 * g + 4 * h + 3]);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i)
+                    if (th + i >= 0 && th + i < a.shuf_Lout) yrow[th + i] = v[8 * g + 4 * h + i];
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int o = o0 + e;
+              const int co = o / s, r = o - co * s;
+              const int tt = s * t + r - a.shuf_p;
+              if (o < a.Cout && tt >= 0 && tt < a.shuf_Lout) ybase[(size_t)co * a.y_stride + tt] = v[e];
             }
           }
         }
@@ -333,8 +456,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta
 // ------------------------------------------------------------------------------- host helpers
 int conv_tc_rows(int K, int dil, int nsub) { return (128 * nsub + (K - 1) * dil + 7) & ~7; }
 
-size_t conv_tc_smem_bytes(int N, int K, int dil, int nsub, int nw) {
-  return HEADER_BYTES + (size_t)NA * conv_tc_rows(K, dil, nsub) * 16 * KG * 2 + (size_t)nw * N * 16 * KG * 2;
+size_t conv_tc_smem_bytes(int N, int K, int dil, int nsub, int nw, int na) {
+  return HEADER_BYTES + (size_t)na * conv_tc_rows(K, dil, nsub) * 16 * KG * 2 + (size_t)nw * N * 16 * KG * 2;
 }
 
 size_t conv_tc_packed_halves(int Cin, int Cout, int K, int N) {
@@ -381,7 +504,9 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
   const ConvArgs& a = ta.c;
   if (a.Cin % KC != 0 || ta.N % 16 != 0 || ta.N < 16 || ta.N > 256) return cudaErrorInvalidValue;
   if (ta.nsub < 1 || ta.nsub > 2 || ta.nw < 2 || ta.nw > MAXNW) return cudaErrorInvalidValue;
-  if (a.mode != MODE_STORE) return cudaErrorInvalidValue;
+  if (a.split != (1 << 30) && (a.split % 16 != 0 || a.mode != MODE_STORE)) return cudaErrorInvalidValue;
+  if (a.mode == MODE_GATE && (ta.N % 32 != 0 || a.Cout % 2)) return cudaErrorInvalidValue;
+  ta.na = (a.Cin / KC) > 1 ? NA : 1;
   const int nacc = ta.sep_cross ? 2 : 1;
   const int need = ta.nsub * nacc * ta.N;
   if (need > 512) return cudaErrorInvalidValue;
@@ -389,7 +514,7 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
   while (cols < need) cols <<= 1;
   ta.tmem_cols = cols;
   ta.rows = conv_tc_rows(a.K, a.dil, ta.nsub);
-  const size_t smem = conv_tc_smem_bytes(ta.N, a.K, a.dil, ta.nsub, ta.nw);
+  const size_t smem = conv_tc_smem_bytes(ta.N, a.K, a.dil, ta.nsub, ta.nw, ta.na);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   static size_t configured[64] = {0};
   int dev = 0;

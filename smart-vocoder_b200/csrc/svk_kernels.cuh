@@ -72,10 +72,10 @@ struct ConvTcArgs {
   int nsub;             // 128-row time sub-tiles per CTA (1 or 2)
   int sep_cross;        // keep the hi*lo cross terms in their own TMEM accumulator
   int nw;               // weight pipeline stages
-  int rows, tmem_cols;  // filled by launch_conv_tc
+  int rows, tmem_cols, na;  // filled by launch_conv_tc
 };
 int conv_tc_rows(int K, int dil, int nsub);
-size_t conv_tc_smem_bytes(int N, int K, int dil, int nsub, int nw);
+size_t conv_tc_smem_bytes(int N, int K, int dil, int nsub, int nw, int na);
 size_t conv_tc_packed_halves(int Cin, int Cout, int K, int N);
 float conv_tc_weight_scale(const float* w, size_t n);
 void conv_tc_pack(const float* w_ock, int Cout, int Cin, int K, int N, float scale, uint16_t* out);

@@ -67,6 +67,11 @@ struct PackedConv {
   int Cin = 0, Cout = 0, CoutPad = 0, K = 0;
   // ConvTranspose1d only
   int s = 0, p = 0, k = 0, pad_virtual = 0;
+  // tcgen05 image (conv_tc.cu): fp16 hi/lo planes in the half blob, bias in TC channel order
+  bool tc = false;
+  size_t tc_off = 0, tc_b_off = 0;  // half offset into d_tcblob; float offset into d_blob
+  int tc_N = 0;
+  float tc_unscale = 1.0f;
 };
 
 struct FlowLayers {
@@ -97,6 +102,8 @@ struct svk_handle {
   float* d_blob = nullptr;
   size_t blob_floats = 0;
   std::vector<float> h_blob;  // staging while packing
+  uint16_t* d_tcblob = nullptr;  // fp16 hi/lo weight images of the tcgen05 path
+  std::vector<uint16_t> h_tcblob;
 
   PackedConv pre_enc, proj, conv_pre, conv_post;
   std::vector<PackedConv> enc_in, enc_rs, ups;
@@ -246,9 +253,52 @@ int fold_layer(svk_handle* h, const std::string& prefix, Folded* out) {
   return SVK_OK;
 }
 
+// Output channels per CTA of the tcgen05 kernel: as few equal tiles of <= 128 channels as possible.
+int tc_tile_n(int Cout, int granule) {
+  const int ntiles = (Cout + 127) / 128;
+  const int per = (Cout + ntiles - 1) / ntiles;
+  return (per + granule - 1) / granule * granule;
+}
+
+// tcgen05 image of a virtual conv.  `gate_half` > 0: WN in_layer, each N-tile holds N/2 tanh
+// channels followed by the matching N/2 sigmoid channels (real channel + gate_half).
+template <class WF, class BF>
+void pack_tc(svk_handle* h, PackedConv* pc, WF wv, BF bv, int gate_half) {
+  const int Cin = pc->Cin, Cout = pc->Cout, K = pc->K;
+  if (h->cfg.precision != SVK_PRECISION_TC || Cin % TC_KC != 0 || Cout < 16) return;
+  const int N = tc_tile_n(Cout, gate_half ? 32 : 16);
+  const int ntiles = (Cout + N - 1) / N;
+  const int CoutV = ntiles * N;
+  auto real = [&](int ov) -> int {  // virtual TC channel -> logical channel (-1: padding)
+    if (!gate_half) return ov < Cout ? ov : -1;
+    const int nt = ov / N, n = ov % N, hf = N / 2;
+    const int c = nt * hf + (n < hf ? n : n - hf);
+    if (c >= gate_half) return -1;
+    return n < hf ? c : gate_half + c;
+  };
+  std::vector<float> w((size_t)CoutV * Cin * K, 0.f);
+  for (int ov = 0; ov < CoutV; ++ov) {
+    const int o = real(ov);
+    if (o < 0) continue;
+    for (int c = 0; c < Cin; ++c)
+      for (int j = 0; j < K; ++j) w[((size_t)ov * Cin + c) * K + j] = wv(o, c, j);
+  }
+  const float scale = conv_tc_weight_scale(w.data(), w.size());
+  pc->tc_off = align_up(h->h_tcblob.size(), 64);
+  h->h_tcblob.resize(pc->tc_off + conv_tc_packed_halves(Cin, CoutV, K, N));
+  conv_tc_pack(w.data(), CoutV, Cin, K, N, scale, h->h_tcblob.data() + pc->tc_off);
+  pc->tc_b_off = align_up(h->h_blob.size(), 64);
+  h->h_blob.resize(pc->tc_b_off + CoutV, 0.f);
+  for (int ov = 0; ov < CoutV; ++ov) {
+    const int o = real(ov);
+    if (o >= 0) h->h_blob[pc->tc_b_off + ov] = bv(o);
+  }
+  pc->tc = true, pc->tc_N = N, pc->tc_unscale = 1.0f / scale;
+}
+
 // Reserve blob space and write a virtual conv: wv(o,c,j), bv(o) -> [Cin][K][CoutPad] + [CoutPad].
 template <class WF, class BF>
-PackedConv pack_virtual(svk_handle* h, int Cin, int Cout, int K, WF wv, BF bv) {
+PackedConv pack_virtual(svk_handle* h, int Cin, int Cout, int K, WF wv, BF bv, bool want_tc = true) {
   PackedConv pc;
   pc.Cin = Cin, pc.Cout = Cout, pc.K = K;
   const int ot = conv_ffma_channel_tile(Cout);
@@ -261,6 +311,7 @@ PackedConv pack_virtual(svk_handle* h, int Cin, int Cout, int K, WF wv, BF bv) {
   pc.b_off = align_up(h->h_blob.size(), 64);
   h->h_blob.resize(pc.b_off + pc.CoutPad, 0.f);
   for (int o = 0; o < Cout; ++o) h->h_blob[pc.b_off + o] = bv(o);
+  if (want_tc) pack_tc(h, &pc, wv, bv, 0);
   return pc;
 }
 
@@ -276,9 +327,13 @@ PackedConv pack_gate(svk_handle* h, const Folded& f, int H) {
     const int grp = o >> 3, e = o & 7;
     return e < 4 ? 4 * grp + e : H + 4 * grp + (e - 4);
   };
-  return pack_virtual(
+  PackedConv pc = pack_virtual(
       h, f.d1, f.d0, f.k, [&](int o, int c, int j) { return f.w[((size_t)real(o) * f.d1 + c) * f.k + j]; },
-      [&](int o) { return f.b.empty() ? 0.f : f.b[real(o)]; });
+      [&](int o) { return f.b.empty() ? 0.f : f.b[real(o)]; }, /*want_tc=*/false);
+  pack_tc(
+      h, &pc, [&](int o, int c, int j) { return f.w[((size_t)o * f.d1 + c) * f.k + j]; },
+      [&](int o) { return f.b.empty() ? 0.f : f.b[o]; }, H);
+  return pc;
 }
 
 // ConvTranspose1d as a K'=ceil(k/s)-tap conv over the input producing s*Cout virtual channels
@@ -328,7 +383,8 @@ extern "C" int svk_create(const svk_config* cfg, int device, svk_handle** out) {
   if (c.n_upsamples < 1 || c.n_upsamples > SVK_MAX_UPSAMPLES) return fail(SVK_ERR_INVALID, "n_upsamples out of range");
   if (c.n_resblock_kernels < 1 || c.n_resblock_kernels > SVK_MAX_RESBLOCK_KERNELS)
     return fail(SVK_ERR_INVALID, "n_resblock_kernels out of range");
-  if (c.precision != SVK_PRECISION_FP32) return fail(SVK_ERR_INVALID, "unsupported precision %d", c.precision);
+  if (c.precision != SVK_PRECISION_FP32 && c.precision != SVK_PRECISION_TC)
+    return fail(SVK_ERR_INVALID, "unsupported precision %d", c.precision);
   if (c.hidden_channels % 8 || c.inter_channels % 16 || c.n_mel % 8)
     return fail(SVK_ERR_INVALID, "n_mel, hidden_channels must be multiples of 8 and inter_channels of 16");
   if ((c.upsample_initial_channel >> c.n_upsamples) < 8 || (c.upsample_initial_channel >> c.n_upsamples) % 8)
@@ -365,6 +421,7 @@ extern "C" void svk_destroy(svk_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->d_blob) cudaFree(h->d_blob);
+  if (h->d_tcblob) cudaFree(h->d_tcblob);
   if (h->host_dev) cudaFree(h->host_dev);
   if (h->host_stream) cudaStreamDestroy(h->host_stream);
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
@@ -411,6 +468,7 @@ extern "C" int svk_finalize_weights(svk_handle* h) {
   const svk_config& c = h->cfg;
   const int half = c.inter_channels / 2;
   h->h_blob.clear();
+  h->h_tcblob.clear();
   h->enc_in.clear(), h->enc_rs.clear(), h->ups.clear(), h->flows.clear(), h->resblocks.clear();
 
   Folded f;
@@ -481,6 +539,14 @@ extern "C" int svk_finalize_weights(svk_handle* h) {
   CUDA_TRY(cudaMemcpy(h->d_blob, h->h_blob.data(), h->blob_floats * sizeof(float), cudaMemcpyHostToDevice));
   h->h_blob.clear();
   h->h_blob.shrink_to_fit();
+  if (h->d_tcblob) cudaFree(h->d_tcblob);
+  h->d_tcblob = nullptr;
+  if (!h->h_tcblob.empty()) {
+    CUDA_TRY(cudaMalloc(&h->d_tcblob, h->h_tcblob.size() * sizeof(uint16_t)));
+    CUDA_TRY(cudaMemcpy(h->d_tcblob, h->h_tcblob.data(), h->h_tcblob.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  }
+  h->h_tcblob.clear();
+  h->h_tcblob.shrink_to_fit();
   h->finalized = true;
   return SVK_OK;
 }
@@ -493,9 +559,11 @@ struct Runner {
   cudaStream_t stream;
   int B;
   cudaError_t err = cudaSuccess;
+  const PackedConv* cur = nullptr;  // layer of the ConvArgs most recently built by base()
 
   ConvArgs base(const PackedConv& pc, const float* x, int x_C, int x_ch_off, int x_stride, int Lin, int dil,
-                int pad, int Lout, int y_stride) const {
+                int pad, int Lout, int y_stride) {
+    cur = &pc;
     ConvArgs a;
     memset(&a, 0, sizeof(a));
     a.x = x, a.x_C = x_C, a.x_ch_off = x_ch_off, a.x_stride = x_stride, a.Lin = Lin;
@@ -542,7 +610,21 @@ struct Runner {
       macs = (double)B * a.Lin * (double)a.Cin * a.Cout * a.K;
     }
     const bool open = prof_open(layer, a, cout_logical, out_len, macs);
-    err = launch_conv_ffma(a, stream);
+    const PackedConv* pc = cur;
+    if (pc && pc->tc && a.wp == h->d_blob + pc->w_off) {
+      ConvTcArgs ta;
+      memset(&ta, 0, sizeof(ta));
+      ta.c = a;
+      ta.c.bias = h->d_blob + pc->tc_b_off;
+      ta.wtc = h->d_tcblob + pc->tc_off;
+      ta.unscale = pc->tc_unscale;
+      ta.N = pc->tc_N, ta.nsub = 1, ta.sep_cross = 1;
+      ta.nw = 4;
+      while (ta.nw > 2 && conv_tc_smem_bytes(ta.N, a.K, a.dil, 1, ta.nw, a.Cin / TC_KC > 1 ? 2 : 1) > 112 * 1024) ta.nw--;
+      err = launch_conv_tc(ta, stream);
+    } else {
+      err = launch_conv_ffma(a, stream);
+    }
     prof_close(open);
     h->launches++;
   }

@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/svk.h"
 #include "svk_kernels.cuh"
@@ -125,6 +126,110 @@ extern "C" int svk_conv_transpose1d(const float* x, int B, int Cin, int L, const
   cudaFreeAsync(wp, s);
   if (e != cudaSuccess) return cuda_fail(e, "svk_conv_transpose1d");
   return SVK_OK;
+}
+
+// ---- the same two operators on the tcgen05 engine (conv_tc.cu).  Weight images are built on the
+// host per call (device -> host copy, fp16 hi/lo split, upload): these entry points exist for
+// operator-level parity tests; the hot path packs once in svk_finalize_weights.
+namespace {
+
+int tc_tile(int Cout) {
+  const int ntiles = (Cout + 127) / 128;
+  const int per = (Cout + ntiles - 1) / ntiles;
+  return (per + 15) / 16 * 16;
+}
+
+// w_ock: logical [CoutV][Cin][K] on the host; bias_v: [CoutV] on the host.
+int run_tc(const float* x, int B, int Cin, int L, const std::vector<float>& w_ock, const std::vector<float>& bias_v,
+           int CoutV, int K, int dil, int pad, float pre_slope, ConvArgs a, cudaStream_t s, const char* who) {
+  const int N = tc_tile(CoutV);
+  const int ntiles = (CoutV + N - 1) / N;
+  const int CoutP = ntiles * N;
+  std::vector<float> wpad((size_t)CoutP * Cin * K, 0.f), bpad(CoutP, 0.f);
+  memcpy(wpad.data(), w_ock.data(), w_ock.size() * sizeof(float));
+  memcpy(bpad.data(), bias_v.data(), bias_v.size() * sizeof(float));
+  const float scale = conv_tc_weight_scale(wpad.data(), wpad.size());
+  std::vector<uint16_t> img(conv_tc_packed_halves(Cin, CoutP, K, N));
+  conv_tc_pack(wpad.data(), CoutP, Cin, K, N, scale, img.data());
+  uint16_t* dimg = nullptr;
+  float* dbias = nullptr;
+  cudaError_t e = cudaMalloc((void**)&dimg, img.size() * 2);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dbias, bpad.size() * 4);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dimg, img.data(), img.size() * 2, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dbias, bpad.data(), bpad.size() * 4, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) {
+    ConvTcArgs ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.c = a;
+    ta.c.x = x, ta.c.x_C = Cin, ta.c.x_stride = L, ta.c.Lin = L, ta.c.pre_slope = pre_slope;
+    ta.c.bias = dbias, ta.c.Cin = Cin, ta.c.Cout = CoutV, ta.c.CoutPad = CoutP, ta.c.K = K, ta.c.dil = dil, ta.c.pad = pad;
+    ta.c.split = 1 << 30, ta.c.post_div = 1.0f, ta.c.B = B;
+    ta.wtc = dimg, ta.unscale = 1.0f / scale, ta.N = N, ta.nsub = 1, ta.sep_cross = 1, ta.nw = 3;
+    e = launch_conv_tc(ta, s);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // the staging buffers are freed below
+  cudaFree(dimg);
+  cudaFree(dbias);
+  if (e != cudaSuccess) return cuda_fail(e, who);
+  return SVK_OK;
+}
+
+}  // namespace
+
+extern "C" int svk_conv1d_tc(const float* x, int B, int Cin, int L, const float* w, const float* bias, int Cout, int k,
+                             int dilation, int padding, float pre_slope, float* y, void* stream) {
+  if (!x || !w || !y || B <= 0 || Cin <= 0 || L <= 0 || Cout <= 0 || k < 1) return op_fail(SVK_ERR_INVALID, "svk_conv1d_tc: bad argument");
+  if (Cin % TC_KC) return op_fail(SVK_ERR_INVALID, "svk_conv1d_tc: Cin must be a multiple of 32");
+  if (dilation < 1) return op_fail(SVK_ERR_INVALID, "svk_conv1d_tc: dilation must be >= 1");
+  const int Lout = L + 2 * padding - dilation * (k - 1);
+  if (Lout <= 0) return op_fail(SVK_ERR_INVALID, "svk_conv1d_tc: empty output");
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<float> hw((size_t)Cout * Cin * k), hb(Cout, 0.f);
+  cudaError_t e = cudaMemcpyAsync(hw.data(), w, hw.size() * 4, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && bias) e = cudaMemcpyAsync(hb.data(), bias, hb.size() * 4, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return cuda_fail(e, "svk_conv1d_tc: weight staging");
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.Lout = Lout, a.y_stride = Lout, a.mode = MODE_STORE;
+  a.e[0].y = y, a.e[0].C = Cout, a.e[0].ch_sign = 1, a.e[1].ch_sign = 1;
+  return run_tc(x, B, Cin, L, hw, hb, Cout, k, dilation, padding, pre_slope, a, s, "svk_conv1d_tc");
+}
+
+extern "C" int svk_conv_transpose1d_tc(const float* x, int B, int Cin, int L, const float* w, const float* bias,
+                                       int Cout, int k, int stride, int padding, float pre_slope, float* y,
+                                       void* stream) {
+  if (!x || !w || !y || B <= 0 || Cin <= 0 || L <= 0 || Cout <= 0 || stride < 1 || k < 1)
+    return op_fail(SVK_ERR_INVALID, "svk_conv_transpose1d_tc: bad argument");
+  if (Cin % TC_KC) return op_fail(SVK_ERR_INVALID, "svk_conv_transpose1d_tc: Cin must be a multiple of 32");
+  const int Kv = (k + stride - 1) / stride;
+  const int Lout = (L - 1) * stride - 2 * padding + k;
+  if (Lout <= 0 || padding < 0) return op_fail(SVK_ERR_INVALID, "svk_conv_transpose1d_tc: empty output");
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<float> hw((size_t)Cin * Cout * k), hb(Cout, 0.f);
+  cudaError_t e = cudaMemcpyAsync(hw.data(), w, hw.size() * 4, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && bias) e = cudaMemcpyAsync(hb.data(), bias, hb.size() * 4, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return cuda_fail(e, "svk_conv_transpose1d_tc: weight staging");
+  // polyphase virtual conv: o' = co*s + r, tap jj <-> original tap r + (Kv-1-jj)*s
+  const int CoutV = Cout * stride;
+  std::vector<float> wv((size_t)CoutV * Cin * Kv, 0.f), bv(CoutV, 0.f);
+  for (int o = 0; o < CoutV; ++o) {
+    const int co = o / stride, r = o % stride;
+    bv[o] = hb[co];
+    for (int c = 0; c < Cin; ++c)
+      for (int jj = 0; jj < Kv; ++jj) {
+        const int j = r + (Kv - 1 - jj) * stride;
+        if (j < k) wv[((size_t)o * Cin + c) * Kv + jj] = hw[((size_t)c * Cout + co) * k + j];
+      }
+  }
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.Lout = (Lout - 1 + padding) / stride + 1;
+  a.y_stride = Lout, a.mode = MODE_SHUFFLE;
+  a.shuf_s = stride, a.shuf_p = padding, a.shuf_Lout = Lout;
+  a.e[0].y = y, a.e[0].C = Cout, a.e[0].ch_sign = 1, a.e[1].ch_sign = 1;
+  return run_tc(x, B, Cin, L, wv, bv, CoutV, Kv, 1, Kv - 1, pre_slope, a, s, "svk_conv_transpose1d_tc");
 }
 
 extern "C" int svk_sequence_mask(const int64_t* lengths, int B, int T, float* mask, void* stream) {

@@ -17,6 +17,8 @@ device buffers, the RNG draw and the stream.  Training-time methods are out of s
 """
 from __future__ import annotations
 
+import os
+
 from collections import OrderedDict, namedtuple
 from typing import Optional
 
@@ -114,6 +116,12 @@ class SynthesizerTrn(nn.Module):
         # (flow.*.post zero like modules.py:321-322).  Real use loads a checkpoint over them.
         init = W.make_state_dict(self.dims, seed=int(kwargs.get("init_seed", 0)), alive=False)
         self._sd = OrderedDict((k, torch.from_numpy(v)) for k, v in init.items())
+        # engine: "tc" (tcgen05 fp16x3 split, default) or "fp32" (FFMA); kwarg `engine=` or $SVK_ENGINE.
+        # Not a reference hyper-parameter: the reference swallows unknown kwargs (models.py:284).
+        eng = str(kwargs.get("engine", os.environ.get("SVK_ENGINE", "tc"))).lower()
+        if eng not in rt.PRECISIONS:
+            raise ValueError(f"engine must be one of {sorted(rt.PRECISIONS)}, got {eng!r}")
+        self.engine = eng
         self._handle: Optional[rt.Handle] = None
         self._device: Optional[torch.device] = None
         self._ws = _Workspace()
@@ -144,7 +152,7 @@ class SynthesizerTrn(nn.Module):
         if self._handle is not None and self._device == device:
             return
         self._release()
-        self._handle = rt.Handle(self.dims, idx)
+        self._handle = rt.Handle(self.dims, idx, rt.PRECISIONS[self.engine])
         self._device = device
         self._upload()
 

@@ -25,7 +25,9 @@ SVK_MAX_UPSAMPLES = 8
 SVK_MAX_RESBLOCK_KERNELS = 8
 SVK_RESBLOCK_PAIRS = 3
 
-PRECISION_FP32 = 0
+PRECISION_FP32 = 0   # fp32 FFMA everywhere
+PRECISION_TC = 1     # tcgen05 3-product fp16 split (fp32-class results), the default engine
+PRECISIONS = {"fp32": PRECISION_FP32, "ffma": PRECISION_FP32, "tc": PRECISION_TC}
 
 
 class SvkError(RuntimeError):
@@ -91,6 +93,8 @@ SIGNATURES = {
     "svk_resblock1": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "svk_conv1d": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
     "svk_conv_transpose1d": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
+    "svk_conv1d_tc": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
+    "svk_conv_transpose1d_tc": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
     "svk_sequence_mask": (_i, [_vp, _i, _i, _vp, _vp]),
     "svk_flip": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "svk_weight_norm": (_i, [_vp, _vp, _i64, _i64, _vp, _vp]),
@@ -121,7 +125,7 @@ def check(status: int) -> int:
     return status
 
 
-def make_config(dims, precision: int = PRECISION_FP32) -> SvkConfig:
+def make_config(dims, precision: int = PRECISION_TC) -> SvkConfig:
     """ModelDims (svk_weights.py) -> svk_config."""
     c = SvkConfig()
     c.n_mel = dims.n_mel
@@ -154,7 +158,7 @@ def make_config(dims, precision: int = PRECISION_FP32) -> SvkConfig:
 class Handle:
     """Owns one svk_handle (one device)."""
 
-    def __init__(self, dims, device: int, precision: int = PRECISION_FP32):
+    def __init__(self, dims, device: int, precision: int = PRECISION_TC):
         self._h = _vp()
         self.cfg = make_config(dims, precision)
         check(lib().svk_create(ctypes.byref(self.cfg), int(device), ctypes.byref(self._h)))

@@ -15,20 +15,22 @@ def dev(a, dtype=torch.float32):
     return torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dtype)
 
 
-def conv1d(x, w, b, dilation=1, padding=0, pre_slope=1.0):
+def conv1d(x, w, b, dilation=1, padding=0, pre_slope=1.0, engine="fp32"):
     B, Cin, L = x.shape
     Cout, _, k = w.shape
     y = torch.empty(B, Cout, L + 2 * padding - dilation * (k - 1), device="cuda")
-    rt.check(rt.lib().svk_conv1d(x.data_ptr(), B, Cin, L, w.data_ptr(), None if b is None else b.data_ptr(), Cout, k,
+    fn = rt.lib().svk_conv1d_tc if engine == "tc" else rt.lib().svk_conv1d
+    rt.check(fn(x.data_ptr(), B, Cin, L, w.data_ptr(), None if b is None else b.data_ptr(), Cout, k,
                                  dilation, padding, pre_slope, y.data_ptr(), _s()))
     return y
 
 
-def conv_transpose1d(x, w, b, stride, padding, pre_slope=1.0):
+def conv_transpose1d(x, w, b, stride, padding, pre_slope=1.0, engine="fp32"):
     B, Cin, L = x.shape
     _, Cout, k = w.shape
     y = torch.empty(B, Cout, (L - 1) * stride - 2 * padding + k, device="cuda")
-    rt.check(rt.lib().svk_conv_transpose1d(x.data_ptr(), B, Cin, L, w.data_ptr(), None if b is None else b.data_ptr(),
+    fn = rt.lib().svk_conv_transpose1d_tc if engine == "tc" else rt.lib().svk_conv_transpose1d
+    rt.check(fn(x.data_ptr(), B, Cin, L, w.data_ptr(), None if b is None else b.data_ptr(),
                                            Cout, k, stride, padding, pre_slope, y.data_ptr(), _s()))
     return y
 
