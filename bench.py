@@ -171,29 +171,24 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------------- our arm
 def aggregate_profile(records, steps):
-    """Group per-launch records by kernel configuration; pick the group with the largest device time."""
-    groups = {}
+    """Group per-launch records into kernel families (engine, layer kind, Cin, taps); pick the one with most time."""
+    fam, by_layer, by_engine = {}, {}, {}
     for r in records:
-        key = (r["layer"], r["cin"], r["cout"], r["k"], r["dilation"])
-        g = groups.setdefault(key, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
-        g["ms"] += r["ms"]
-        g["n"] += 1
-        g["flops"] += r["flops"]
-        g["bytes"] += r["bytes"]
-    total_ms = sum(g["ms"] for g in groups.values())
-    # the "dominant kernel" is one template (conv_ffma_kernel); report the instantiation family with most time:
-    fam = {}
-    for (layer, cin, cout, k, dil), g in groups.items():
-        f = fam.setdefault((layer.startswith("resblock"), cin, k), {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0,
-                                                                    "layers": set()})
-        for q in ("ms", "n", "flops", "bytes"):
-            f[q] += g[q]
-        f["layers"].add(layer)
+        key = (r["engine"], r["layer"].startswith("resblock"), r["cin"], r["k"])
+        f = fam.setdefault(key, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0, "layers": set()})
+        for q in ("ms", "flops", "bytes"):
+            f[q] += r[q]
+        f["n"] += 1
+        f["layers"].add(r["layer"])
+        by_layer[r["layer"]] = by_layer.get(r["layer"], 0.0) + r["ms"]
+        e = by_engine.setdefault(r["engine"], {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
+        e["ms"] += r["ms"]
+        e["flops"] += r["flops"]
+        e["bytes"] += r["bytes"]
+        e["n"] += 1
+    total_ms = sum(f["ms"] for f in fam.values())
     top_key, top = max(fam.items(), key=lambda kv: kv[1]["ms"])
-    by_layer = {}
-    for (layer, *_), g in groups.items():
-        by_layer[layer] = by_layer.get(layer, 0.0) + g["ms"]
-    return total_ms, top_key, top, by_layer
+    return total_ms, top_key, top, by_layer, by_engine
 
 
 def run_b200_arm(args):
@@ -320,32 +315,63 @@ def run_b200_arm(args):
     value = total_samples / (elapsed_ms / 1e3)
     ms_per_step = elapsed_ms / K
 
-    prof_total_ms, top_key, top, by_layer = aggregate_profile(records, K)
+    prof_total_ms, top_key, top, by_layer, by_engine = aggregate_profile(records, K)
+    eng, _, top_cin, top_k = top_key
     avg_ms = top["ms"] / top["n"]
     achieved_tf = (top["flops"] / top["n"]) / (avg_ms / 1e3) / 1e12
     hbm_gbs = (top["bytes"] / top["n"]) / (avg_ms / 1e3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            ent = tj.get("families", {}).get(f"{eng}:cin{top_cin}:k{top_k}")
+            if ent:
+                traffic, traffic_src = ent.get("dram_bytes_per_launch"), tj.get("source")
         except Exception:
             traffic = None
+    tc_peak = peaks["bf16_tflops_sustained"]
+    if eng == "tc":
+        bound, peak_tf = "tensor", tc_peak
+        kname = f"conv_tc_kernel (tcgen05 kind::f16, 3-product fp16 split) Cin={top_cin} k={top_k}"
+        peak_src = (f"{peaks['_source']}: cuBLAS bf16 sustained (kernel timed inside a long step); achieved counts USEFUL "
+                    f"fp32-equivalent FLOPs, the tensor pipe executes 3x that (tensor_raw), so the scheme's ceiling is frac=1/3")
+    else:
+        bound, peak_tf = "tensor", tc_peak
+        kname = f"conv_ffma_kernel Cin={top_cin} k={top_k}"
+        peak_src = f"{peaks['_source']}; FFMA-pipe kernel, fp32 peak {ffma_peak_tf:.1f} TFLOP/s"
+    step_tf = FLOP_PER_FRAME * B * T / (ms_per_step / 1e3) / 1e12
     roofline = {
-        "bound": "fp32_ffma", "kernel": f"conv_ffma_kernel<K={top_key[2]}> Cin={top_key[1]} ({'+'.join(sorted(top['layers']))})",
-        "achieved": achieved_tf, "peak": ffma_peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / ffma_peak_tf,
-        "peak_source": f"{n_sm} SMs x 128 FFMA lanes x 2 x {sm_max_mhz:.0f} MHz (clocks.max.sm); the path is compute-bound "
-                       f"on the fp32 pipe (SURVEY F13), tensor pipe not used in this precision",
-        "traffic": traffic,
+        "bound": bound, "kernel": kname + f" ({'+'.join(sorted(top['layers']))})",
+        "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+        "tensor_raw": {"achieved": 3 * achieved_tf, "frac": 3 * achieved_tf / peak_tf} if eng == "tc" else None,
+        "peak_source": peak_src,
+        "traffic": traffic, "traffic_source": traffic_src,
         "launches_in_group": top["n"], "avg_launch_ms": avg_ms, "share_of_step": top["ms"] / prof_total_ms,
         "algorithmic_flops_per_launch": top["flops"] / top["n"], "algorithmic_bytes_per_launch": top["bytes"] / top["n"],
         "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": peaks["hbm_gbs"], "frac": hbm_gbs / peaks["hbm_gbs"],
                 "peak_source": peaks["_source"]},
-        "whole_step": {"tflops": FLOP_PER_FRAME * B * T / (ms_per_step / 1e3) / 1e12,
-                       "frac_of_ffma_peak": FLOP_PER_FRAME * B * T / (ms_per_step / 1e3) / 1e12 / ffma_peak_tf,
+        "whole_step": {"tflops": step_tf, "frac_of_tensor_peak": step_tf / tc_peak,
+                       "frac_of_ffma_peak": step_tf / ffma_peak_tf,
                        "hbm_compulsory_frac": (BYTES_MIN_PER_FRAME * B * T + WEIGHT_BYTES_FP32) / (ms_per_step / 1e3) / 1e9 / peaks["hbm_gbs"],
-                       "kernel_time_share_by_layer": {k: v / prof_total_ms for k, v in sorted(by_layer.items(), key=lambda kv: -kv[1])}},
+                       "unfused_layer_traffic_gbs": sum(e["bytes"] for e in by_engine.values()) / K / (ms_per_step / 1e3) / 1e9,
+                       "kernel_time_share_by_layer": {k: v / prof_total_ms for k, v in sorted(by_layer.items(), key=lambda kv: -kv[1])},
+                       "kernel_time_share_by_engine": {k: v["ms"] / prof_total_ms for k, v in by_engine.items()},
+                       "profiled_kernel_ms_per_step": prof_total_ms / K},
     }
+
+    if args.dump_profile:
+        groups = {}
+        for r in records:
+            g = groups.setdefault((r["engine"], r["layer"], r["cin"], r["cout"], r["k"], r["dilation"], r["length"]),
+                                  {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
+            g["ms"], g["n"], g["flops"], g["bytes"] = g["ms"] + r["ms"], g["n"] + 1, g["flops"] + r["flops"], g["bytes"] + r["bytes"]
+        with open(args.dump_profile, "w") as f:
+            f.write("engine,layer,cin,cout,k,dil,length,launches_per_step,avg_ms,ms_per_step,useful_tflops,alg_gbs\n")
+            for key, g in sorted(groups.items(), key=lambda kv: -kv[1]["ms"]):
+                avg = g["ms"] / g["n"]
+                f.write(",".join(str(x) for x in key) + f",{g['n'] / K:.1f},{avg:.4f},{g['ms'] / K:.3f},"
+                        f"{g['flops'] / g['n'] / avg / 1e9:.1f},{g['bytes'] / g['n'] / avg / 1e6:.0f}\n")
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -398,6 +424,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-profile", default=None, help="write the per-layer launch table (CUDA-event times) to this file")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

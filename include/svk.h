@@ -152,7 +152,7 @@ typedef struct svk_launch_record {
   double flops;       /* algorithmic */
   double bytes;       /* algorithmic (compulsory) */
   float ms;           /* device time between the bracketing events */
-  int32_t reserved;
+  int32_t engine;     /* 0 = fp32 FFMA kernel, 1 = tcgen05 kernel */
 } svk_launch_record;
 int svk_profile_begin(svk_handle *h, int max_records);
 int svk_profile_end(svk_handle *h, svk_launch_record *out, int max_records, int *n_records);

@@ -609,9 +609,11 @@ struct Runner {
       cout_logical = a.Cout / a.shuf_s, out_len = a.shuf_Lout;
       macs = (double)B * a.Lin * (double)a.Cin * a.Cout * a.K;
     }
-    const bool open = prof_open(layer, a, cout_logical, out_len, macs);
     const PackedConv* pc = cur;
-    if (pc && pc->tc && a.wp == h->d_blob + pc->w_off) {
+    const bool use_tc = pc && pc->tc && a.wp == h->d_blob + pc->w_off;
+    const bool open = prof_open(layer, a, cout_logical, out_len, macs);
+    if (open) h->prof_records.back().engine = use_tc ? 1 : 0;
+    if (use_tc) {
       ConvTcArgs ta;
       memset(&ta, 0, sizeof(ta));
       ta.c = a;
