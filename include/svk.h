@@ -153,6 +153,8 @@ typedef struct svk_launch_record {
   double bytes;       /* algorithmic (compulsory) */
   float ms;           /* device time between the bracketing events */
   int32_t engine;     /* 0 = fp32 FFMA kernel, 1 = tcgen05 kernel */
+  float gap_ms;       /* device time between the previous record's end event and this one's start */
+  int32_t reserved;
 } svk_launch_record;
 int svk_profile_begin(svk_handle *h, int max_records);
 int svk_profile_end(svk_handle *h, svk_launch_record *out, int max_records, int *n_records);

@@ -5,24 +5,31 @@
 //     y = (xh.wh + xh.wl + xl.wh) / s          products exact in the fp32 accumulator; the dropped
 //                                               xl.wl term is <= 2^-22 relative
 //
-// GEMM mapping (one CTA = one [128*NSUB time] x [N output channels] tile of one utterance):
+// PERSISTENT, warp-specialised kernel: one CTA per SM walks a static round-robin list of work items
+// (item = one [128 time steps] x [N output channels] tile of one utterance).
 //     M = time (128 rows per MMA), N = output channels, K = input channels x taps
-//     A = activations, K-major, NO swizzle:  A_s[kgroup(8 ch)][row = time][16 B]
+//     A = activations, K-major, NO swizzle:  A_s[hi|lo][kgroup(8 ch)][row = time][16 B]
 //         -> a conv tap is a ROW shift, i.e. a 16 B-granular change of the descriptor start
 //            address (SBO = 128 B makes 8-row groups contiguous, so any row offset is legal);
 //            one staged tile with a (K-1)*dil halo serves every tap -- no im2col, no re-staging.
-//     B = weights per (chunk, tap), K-major, no swizzle: B_s[kgroup][n][16 B], pre-split/pre-packed
-//         at load time in exactly this image, so one cp.async.bulk per pipeline stage fills it.
-//     D = fp32 in TMEM: per time sub-tile a main accumulator (xh.wh) and (optionally separate) a
-//         cross accumulator (xh.wl + xl.wh), summed in the epilogue.
+//     B = weights per (32-channel chunk, tap), K-major, no swizzle: B_s[kgroup][hi n | lo n][16 B],
+//         pre-split/pre-packed at load time in exactly this image (one cp.async.bulk per stage).
+//         Because hi and lo rows are adjacent, ONE MMA with N' = 2N computes xh.wh into the main
+//         accumulator and xh.wl into the cross accumulator (columns [N, 2N)); a second MMA with
+//         N' = N adds xl.wh to the cross accumulator: 2 instructions and 20 KB of operand reads
+//         per K=16 step instead of 3 and 24 KB.  The small cross terms never touch the main
+//         accumulator (3x lower truncation error than one accumulator).
+//     D = fp32 in TMEM, double buffered: 2 stages x (main + cross) x N columns <= 512.
 //
-// Warp roles (192 threads): warp 0 = TMEM allocator + weight bulk-copy producer (1 lane),
-// warp 1 = barrier init + MMA issuer (1 lane), warps 2..5 = activation producers (global fp32 ->
-// leaky_relu/mask -> fp16 hi/lo -> smem) and, once the accumulators are committed, the epilogue
-// (tcgen05.ld -> bias / residual / running sum / mask / tanh -> coalesced global stores).
-// Pipelines: A ring (2 stages, mbarrier full/empty), weight ring (NW stages, expect_tx / commit),
-// accumulator-full barrier.  Overlap of epilogue and mainloop comes from 2 co-resident CTAs per SM
-// when the tile's smem/TMEM footprint allows it.
+// Warp roles (576 threads): warp 0 = TMEM allocator + weight bulk-copy producer (1 lane),
+// warp 1 = barrier init + MMA issuer (1 lane), warps 2..9 = activation producers in two groups
+// that alternate 32-channel chunks (global fp32 -> leaky_relu/mask -> fp16 hi/lo -> smem), running
+// ahead of the MMAs by the depth of the A ring (across tile boundaries), warps 10..17 = epilogue
+// (tcgen05.ld -> bias / residual / running sum / mask / tanh / gate / polyphase store) of tile i while
+// the MMAs of tile i+1 fill the other accumulator stage.
+// Pipelines: A ring (mbarrier full/empty), weight ring (expect_tx / tcgen05.commit) -- or, when the
+// layer's whole weight image fits the ring, weights are loaded once and stay resident for every tile
+// of the CTA -- and the accumulator full/empty pair.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -33,21 +40,34 @@ namespace svk {
 
 namespace {
 
-constexpr int KC = TC_KC;  // input channels per A chunk
+constexpr int KC = TC_KC;   // input channels per A chunk
 constexpr int KG = KC / 8;  // 16-byte k-groups per chunk
-constexpr int NA = 2;       // A ring depth (max)
-constexpr int MAXNW = 6;    // weight ring depth limit
-constexpr int THREADS = 192;
-constexpr int PRODUCERS = 128;
+constexpr int NA_MAX = 4;   // A ring depth limit (depth is 2 or 4: the two producer groups own alternate slots)
+constexpr int MAXNW = 16;   // weight ring depth limit
+#ifndef SVK_TC_PROD_WARPS
+#define SVK_TC_PROD_WARPS 8
+#endif
+#ifndef SVK_TC_EPI_WARPS
+#define SVK_TC_EPI_WARPS 8
+#endif
+constexpr int PROD_WARPS = SVK_TC_PROD_WARPS, EPI_WARPS = SVK_TC_EPI_WARPS;
+constexpr int THREADS = 64 + 32 * (PROD_WARPS + EPI_WARPS);  // 576
+constexpr int PROD_GROUP = 128;                              // threads per producer group (one time row each)
+constexpr int PROD_GROUPS = PROD_WARPS / 4;                  // groups take alternate chunks
+constexpr int EPI_SPLIT = EPI_WARPS / 4;                     // warps sharing one TMEM lane quarter split the columns
+constexpr int EPI_THREADS = 32 * EPI_WARPS;
+constexpr int FIRST_EPI_WARP = 2 + PROD_WARPS;
+static_assert(PROD_WARPS % 4 == 0 && (PROD_GROUPS == 1 || PROD_GROUPS == 2), "producer groups");
+static_assert(EPI_WARPS % 4 == 0 && EPI_SPLIT >= 1, "a warp may only read TMEM lane quarter (warp id & 3)");
 
 struct __align__(8) SmemHeader {
-  uint64_t a_full[NA], a_empty[NA];
+  uint64_t a_full[NA_MAX], a_empty[NA_MAX];
   uint64_t w_full[MAXNW], w_empty[MAXNW];
-  uint64_t acc_full;
+  uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
 };
-constexpr int HEADER_BYTES = 256;
+constexpr int HEADER_BYTES = 512;
 static_assert(sizeof(SmemHeader) <= HEADER_BYTES, "header");
 
 // ---------------------------------------------------------------------------------- PTX wrappers
@@ -149,32 +169,42 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 }
 
 // ------------------------------------------------------------------------------------- kernel
-__global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcArgs ta) {
+// item -> (output-channel tile, utterance, time tile); consecutive items are adjacent time tiles of
+// one utterance and one channel tile, so a wave of CTAs shares weights and halos in L2.
+__device__ __forceinline__ void decode_item(int item, int ntiles_t, int B, int& nt, int& b, int& tt) {
+  tt = item % ntiles_t;
+  const int r = item / ntiles_t;
+  b = r % B;
+  nt = r / B;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta) {
   extern __shared__ __align__(128) uint8_t smem[];
   const ConvArgs& a = ta.c;
   SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int N = ta.N, nsub = ta.nsub, nw = ta.nw, na = ta.na;
-  const int nacc = ta.sep_cross ? 2 : 1;
+  const int N = ta.N, nw = ta.nw, na = ta.na;
   const int K = a.K, dil = a.dil;
-  const int rows = ta.rows;                      // staged time rows per chunk (multiple of 8)
+  const int rows = ta.rows;                       // staged time rows per chunk (multiple of 8)
   const uint32_t a_plane = (uint32_t)rows * 16u;  // one k-group plane of A
   const uint32_t a_stage = a_plane * KG * 2u;     // hi + lo
-  const uint32_t w_plane = (uint32_t)N * 16u;
-  const uint32_t w_stage = w_plane * KG * 2u;
+  const uint32_t w_plane2 = (uint32_t)N * 32u;    // one k-group plane of B: N hi rows then N lo rows
+  const uint32_t w_stage = w_plane2 * KG;
   uint8_t* a_smem = smem + HEADER_BYTES;
-  uint8_t* w_smem = a_smem + na * a_stage;
-  const int t0 = blockIdx.x * (128 * nsub), ntile = blockIdx.y, b = blockIdx.z;
+  uint8_t* w_smem = a_smem + (size_t)na * a_stage;
   const int nchunks = a.Cin / KC;
-  const uint32_t tmem_cols = ta.tmem_cols;
+  const int per_tile = nchunks * K;  // weight stages per item
+  const int items = ta.items, ntiles_t = ta.ntiles_t;
+  const int resident = ta.resident;
+  const int n_my = (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < na; ++i) mbar_init(&hdr->a_full[i], PRODUCERS), mbar_init(&hdr->a_empty[i], 1);
-    for (int i = 0; i < nw; ++i) mbar_init(&hdr->w_full[i], 1), mbar_init(&hdr->w_empty[i], 1);
-    mbar_init(&hdr->acc_full, 1);
+    for (int i = 0; i < na; ++i) mbar_init(&hdr->a_full[i], PROD_GROUP), mbar_init(&hdr->a_empty[i], 1);
+    for (int i = 0; i < MAXNW; ++i) mbar_init(&hdr->w_full[i], 1), mbar_init(&hdr->w_empty[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&hdr->acc_full[i], 1), mbar_init(&hdr->acc_empty[i], EPI_THREADS);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(&hdr->tmem_base, tmem_cols);
+  if (warp == 0) tmem_alloc(&hdr->tmem_base, ta.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -183,73 +213,89 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcArgs ta
   if (warp == 0) {
     // ------------------------------------------------ weight producer: one bulk copy per (chunk, tap)
     if (lane == 0) {
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(ta.wtc) + (size_t)ntile * nchunks * K * w_stage;
-      const int total = nchunks * K;
       int st = 0;
       uint32_t ph = 0;
-      for (int it = 0; it < total; ++it) {
-        mbar_wait(&hdr->w_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&hdr->w_full[st], w_stage);
-        bulk_g2s(w_smem + (size_t)st * w_stage, src + (size_t)it * w_stage, w_stage, &hdr->w_full[st]);
-        if (++st == nw) st = 0, ph ^= 1;
+      for (int i = 0; i < n_my; ++i) {
+        if (resident && i > 0) break;  // the whole image already sits in the ring
+        int nt, b, tt;
+        decode_item((int)blockIdx.x + i * (int)gridDim.x, ntiles_t, a.B, nt, b, tt);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(ta.wtc) + (size_t)nt * per_tile * w_stage;
+        for (int it = 0; it < per_tile; ++it) {
+          if (!resident) mbar_wait(&hdr->w_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&hdr->w_full[st], w_stage);
+          bulk_g2s(w_smem + (size_t)st * w_stage, src + (size_t)it * w_stage, w_stage, &hdr->w_full[st]);
+          if (++st == nw) st = 0, ph ^= 1;
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, K-major
-      uint32_t started = 0;  // bit (sub * nacc + acc): accumulator already holds a partial sum
-      int wst = 0;
-      uint32_t wph = 0;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        const int as = ch % na;
-        mbar_wait(&hdr->a_full[as], (ch / na) & 1);
+      // f16 x f16 -> f32, both operands K-major, M = 128
+      const uint32_t idesc1 = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * N) >> 3) << 17) | ((128u >> 4) << 24);
+      const int wlim = resident ? per_tile : nw;
+      int ast = 0, wst = 0;
+      uint32_t aph = 0, wph = 0;
+      for (int i = 0; i < n_my; ++i) {
+        const int s = i & 1;
+        mbar_wait(&hdr->acc_empty[s], ((uint32_t)(i >> 1) & 1u) ^ 1u);  // epilogue drained this stage
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(a_smem + (size_t)as * a_stage), a_lo = a_hi + a_plane * KG;
-        for (int j = 0; j < K; ++j) {
-          mbar_wait(&hdr->w_full[wst], wph);
+        const uint32_t dmain = tmem + (uint32_t)(s * 2 * N), dcross = dmain + (uint32_t)N;
+        uint32_t acc = 0;
+        for (int ch = 0; ch < nchunks; ++ch) {
+          mbar_wait(&hdr->a_full[ast], aph);
           tc_fence_after();
-          const uint32_t b_hi = smem_u32(w_smem + (size_t)wst * w_stage), b_lo = b_hi + w_plane * KG;
+          const uint32_t a_hi = smem_u32(a_smem + (size_t)ast * a_stage), a_lo = a_hi + a_plane * KG;
+          for (int j = 0; j < K; ++j) {
+            if (!resident || i == 0) {
+              mbar_wait(&hdr->w_full[wst], wph);
+              tc_fence_after();
+            }
+            const uint32_t b0 = smem_u32(w_smem + (size_t)wst * w_stage);
 #pragma unroll
-          for (int ks = 0; ks < KC / 16; ++ks) {
-            const uint64_t dbh = make_desc(b_hi + 2 * ks * w_plane, w_plane, 128);
-            const uint64_t dbl = make_desc(b_lo + 2 * ks * w_plane, w_plane, 128);
-            for (int sub = 0; sub < nsub; ++sub) {
-              const uint32_t roff = (uint32_t)(sub * 128 + j * dil) * 16u + 2 * ks * a_plane;
+            for (int ks = 0; ks < KC / 16; ++ks) {
+              const uint32_t roff = (uint32_t)(j * dil) * 16u + 2 * ks * a_plane;
               const uint64_t dah = make_desc(a_hi + roff, a_plane, 128);
               const uint64_t dal = make_desc(a_lo + roff, a_plane, 128);
-              const int im = sub * nacc, ic = sub * nacc + nacc - 1;
-              const uint32_t dm = tmem + (uint32_t)(im * N), dc = tmem + (uint32_t)(ic * N);
-              umma_f16(dc, dal, dbh, idesc, (started >> ic) & 1u);
-              started |= 1u << ic;
-              umma_f16(dc, dah, dbl, idesc, 1u);
-              umma_f16(dm, dah, dbh, idesc, (started >> im) & 1u);
-              started |= 1u << im;
+              const uint64_t db = make_desc(b0 + 2 * ks * w_plane2, w_plane2, 128);
+              umma_f16(dmain, dah, db, idesc2, acc);  // [main | cross] (+)= xh . [wh | wl]
+              acc = 1u;
+              umma_f16(dcross, dal, db, idesc1, 1u);  // cross += xl . wh
             }
+            if (!resident) umma_commit(&hdr->w_empty[wst]);
+            if (++wst == wlim) wst = 0, wph ^= 1;
           }
-          umma_commit(&hdr->w_empty[wst]);
-          if (++wst == nw) wst = 0, wph ^= 1;
+          umma_commit(&hdr->a_empty[ast]);
+          if (++ast == na) ast = 0, aph ^= 1;
         }
-        umma_commit(&hdr->a_empty[as]);
+        umma_commit(&hdr->acc_full[s]);
       }
-      umma_commit(&hdr->acc_full);
     }
     __syncwarp();
-  } else {
-    // ------------------------------------------------ activation producers (128 threads)
+  } else if (warp < FIRST_EPI_WARP) {
+    // ------------------------------------------------ activation producers (2 groups x 128 threads)
+    // Group g stages chunks q = g, g+2, ... of this CTA's chunk sequence (q = tile * nchunks + chunk).
     // One task = one time row x all KC channels of the chunk: 32 independent coalesced loads in
     // flight per thread, then leaky_relu / mask / fp16 hi-lo split and 2 x 4 conflict-free 16 B stores.
-    const int rp = tid - 64;
+    const int g = (warp - 2) >> 2;
+    const int rp = tid - 64 - PROD_GROUP * g;
     const float slope = a.pre_slope;
-    const float* mrow = a.in_mask ? a.in_mask + (size_t)b * a.mask_stride : nullptr;
-    for (int ch = 0; ch < nchunks; ++ch) {
-      const int as = ch % na;
-      mbar_wait(&hdr->a_empty[as], ((ch / na) & 1) ^ 1);
+    const int na_shift = na == 4 ? 2 : 1;
+    const int total_q = n_my * nchunks;
+    for (int q = g; q < total_q; q += PROD_GROUPS) {
+      const int i = q / nchunks, ch = q - i * nchunks;
+      int nt, b, tt;
+      decode_item((int)blockIdx.x + i * (int)gridDim.x, ntiles_t, a.B, nt, b, tt);
+      const int t0 = tt * 128;
+      const int as = q & (na - 1);
+      mbar_wait(&hdr->a_empty[as], ((uint32_t)(q >> na_shift) & 1u) ^ 1u);
       uint4* Ahi = reinterpret_cast<uint4*>(a_smem + (size_t)as * a_stage);
       uint4* Alo = Ahi + KG * rows;
+      const float* mrow = a.in_mask ? a.in_mask + (size_t)b * a.mask_stride : nullptr;
       const float* xb = a.x + ((size_t)b * a.x_C + a.x_ch_off + ch * KC) * a.x_stride;
-      for (int r = rp; r < rows; r += PRODUCERS) {
+      for (int r = rp; r < rows; r += PROD_GROUP) {
         const int t = t0 - a.pad + r;
         const bool ok = t >= 0 && t < a.Lin;
         float v[KC];
@@ -258,9 +304,9 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcArgs ta
         const float mk = (ok && mrow) ? __ldg(mrow + t) : 1.0f;
 #pragma unroll
         for (int c = 0; c < KC; ++c) {
-          float q = v[c];
-          q = q > 0.f ? q : q * slope;
-          v[c] = mrow ? q * mk : q;
+          float qv = v[c];
+          qv = qv > 0.f ? qv : qv * slope;
+          v[c] = mrow ? qv * mk : qv;
         }
 #pragma unroll
         for (int kg = 0; kg < KG; ++kg) {
@@ -276,159 +322,225 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcArgs ta
       fence_proxy_async_smem();
       mbar_arrive(&hdr->a_full[as]);
     }
-
+  } else {
     // ------------------------------------------------ epilogue: TMEM -> registers -> global
-    mbar_wait(&hdr->acc_full, 0);
-    tc_fence_after();
-    const int q4 = warp & 3;  // TMEM lane quarter this warp may read
+    // warp w owns TMEM lane quarter w & 3 (= 32 time rows); the warps of a quarter split the tile's
+    // 16-column chunks between them.  Everything that varies per element is branch-free: operand loads
+    // use clamped (always valid) addresses so 16-32 of them are in flight per thread, the operands of
+    // the NEXT chunk -- and of the next tile's first chunk -- are requested before the current chunk
+    // is finished, and only the final store is predicated.
+    const int q4 = warp & 3;
+    const int part = (warp - FIRST_EPI_WARP) >> 2;
     const int row = q4 * 32 + lane;
-    const uint32_t tlane = tmem + ((uint32_t)(q4 * 32) << 16);
     const float unscale = ta.unscale;
-    const float* omask = a.out_mask ? a.out_mask + (size_t)b * a.mask_stride : nullptr;
-    const int o_tile = ntile * N;
-    for (int sub = 0; sub < nsub; ++sub) {
-      const int t = t0 + sub * 128 + row;
-      const uint32_t tsub = tlane + (uint32_t)(sub * nacc * N);
+    const int mode = a.mode;
 
-      if (a.mode == MODE_STORE) {
-        // y = ((acc/s + bias) + (res + acc_in)) / post_div * mask, tanh; res / acc_in of the NEXT 16
-        // channels are in flight while the current 16 are finished (same element is read then
-        // written by the same thread only, so in-place operation is safe).
-        const bool tin = t < a.Lout;
-        const float mv = (omask && tin) ? omask[t] : 1.0f;
-        const float* res_c = nullptr;
-        const float* acc_c = nullptr;
-        float* y_c = nullptr;
-        ptrdiff_t step_c = 0;
-        int um_c = 0, nv_c = 0;
-        float r1[16];
-        auto chunk_params = [&](int n0, const float*& res, const float*& accin, float*& y, ptrdiff_t& step, int& um,
-                                int& nvalid) {
-          const int o0 = o_tile + n0;
-          const bool s1 = o0 >= a.split;
-          const int rel0 = s1 ? o0 - a.split : o0;
-          const int dC = s1 ? a.e[1].C : a.e[0].C, dch = s1 ? a.e[1].ch_off : a.e[0].ch_off;
-          const int dsg = s1 ? a.e[1].ch_sign : a.e[0].ch_sign;
-          const size_t off = ((size_t)b * dC + dch + dsg * rel0) * a.y_stride + t;
-          const float* rs = s1 ? a.e[1].res : a.e[0].res;
-          const float* ai = s1 ? a.e[1].acc_in : a.e[0].acc_in;
-          res = rs ? rs + off : nullptr;
-          accin = ai ? ai + off : nullptr;
-          y = (s1 ? a.e[1].y : a.e[0].y) + off;
-          step = (ptrdiff_t)dsg * a.y_stride;
-          um = s1 ? a.e[1].use_mask : a.e[0].use_mask;
-          nvalid = tin ? min(16, a.Cout - o0) : 0;
-        };
-        auto load16 = [&](const float* res, const float* accin, ptrdiff_t step, int nvalid, float (&q1)[16]) {
+    // STORE-mode addressing of the 16-channel chunk starting at virtual channel o0 (never straddles a.split)
+    struct ChunkIO {
+      const float* res;
+      const float* acc;
+      float* y;
+      ptrdiff_t step;
+      int um, nvalid;
+    };
+    auto chunk_io = [&](int b, int o0, int t, int tl) {
+      ChunkIO io;
+      const int s1 = o0 >= a.split ? 1 : 0;
+      const EpiDesc& d = a.e[s1];
+      const int rel0 = s1 ? o0 - a.split : o0;
+      const size_t off = ((size_t)b * d.C + d.ch_off + d.ch_sign * rel0) * a.y_stride;
+      io.res = d.res ? d.res + off + tl : nullptr;
+      io.acc = d.acc_in ? d.acc_in + off + tl : nullptr;
+      io.y = d.y + off + t;
+      io.step = (ptrdiff_t)d.ch_sign * a.y_stride;
+      io.um = d.use_mask;
+      io.nvalid = max(0, min(16, a.Cout - o0));
+      return io;
+    };
+    auto load16 = [&](const ChunkIO& io, float (&q)[16]) {
+      if (io.nvalid == 16) {
+        if (io.res) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float u1 = (res && e < nvalid) ? res[e * step] : 0.f;
-            const float u2 = (accin && e < nvalid) ? accin[e * step] : 0.f;
-            q1[e] = u1 + u2;
-          }
-        };
-        chunk_params(0, res_c, acc_c, y_c, step_c, um_c, nv_c);
-        load16(res_c, acc_c, step_c, nv_c, r1);
-        for (int n0 = 0; n0 < N; n0 += 16) {
-          const float* res_n = nullptr;
-          const float* acc_n = nullptr;
-          float* y_n = nullptr;
-          ptrdiff_t step_n = 0;
-          int um_n = 0, nv_n = 0;
+          for (int e = 0; e < 16; ++e) q[e] = io.res[e * io.step];
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) q[e] = 0.f;
+        }
+        if (io.acc) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) q[e] += io.acc[e * io.step];
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float u1 = (io.res && e < io.nvalid) ? io.res[e * io.step] : 0.f;
+          const float u2 = (io.acc && e < io.nvalid) ? io.acc[e * io.step] : 0.f;
+          q[e] = u1 + u2;
+        }
+      }
+    };
+
+    const int nch = N >> 4, hc = (nch + EPI_SPLIT - 1) / EPI_SPLIT;
+    const int n_lo = part * hc * 16, n_hi = min(nch, (part + 1) * hc) * 16;  // STORE / SHUFFLE column range
+    const bool have_cols = n_lo < n_hi;
+
+    float r1[16];
+    if (mode == MODE_STORE && have_cols && n_my > 0) {
+      int nt0, b0, tt0;
+      decode_item((int)blockIdx.x, ntiles_t, a.B, nt0, b0, tt0);
+      const int t = tt0 * 128 + row;
+      load16(chunk_io(b0, nt0 * N + n_lo, t, min(t, a.Lout - 1)), r1);
+    }
+
+    for (int i = 0; i < n_my; ++i) {
+      const int s = i & 1;
+      int ntile, b, tt;
+      decode_item((int)blockIdx.x + i * (int)gridDim.x, ntiles_t, a.B, ntile, b, tt);
+      const int t = tt * 128 + row;
+      const bool tin = t < a.Lout;
+      const int tl = min(t, a.Lout - 1);
+      const float* omask = a.out_mask ? a.out_mask + (size_t)b * a.mask_stride : nullptr;
+      const float mv = omask ? omask[tl] : 1.0f;
+      const int o_tile = ntile * N;
+      mbar_wait(&hdr->acc_full[s], (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t tsub = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(s * 2 * N);
+
+      if (mode == MODE_STORE) {
+        // y = ((acc/s + bias) + (res + acc_in)) / post_div * mask, tanh  (same element is read then
+        // written by the same thread only, so in-place operation is safe)
+        for (int n0 = n_lo; n0 < n_hi; n0 += 16) {
+          // request the operands of the next chunk (or of the next tile's first chunk)
           float p1[16];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) p1[e] = 0.f;
-          if (n0 + 16 < N) {
-            chunk_params(n0 + 16, res_n, acc_n, y_n, step_n, um_n, nv_n);
-            load16(res_n, acc_n, step_n, nv_n, p1);
+          bool have_next = true;
+          if (n0 + 16 < n_hi) {
+            load16(chunk_io(b, o_tile + n0 + 16, t, tl), p1);
+          } else if (i + 1 < n_my) {
+            int nt2, b2, tt2;
+            decode_item((int)blockIdx.x + (i + 1) * (int)gridDim.x, ntiles_t, a.B, nt2, b2, tt2);
+            const int t2 = tt2 * 128 + row;
+            load16(chunk_io(b2, nt2 * N + n_lo, t2, min(t2, a.Lout - 1)), p1);
+          } else {
+            have_next = false;
           }
+
           uint32_t m[16], c[16];
           tmem_ld16(tsub + (uint32_t)n0, m);
-          if (nacc == 2) tmem_ld16(tsub + (uint32_t)(N + n0), c);
+          tmem_ld16(tsub + (uint32_t)(N + n0), c);
+          const float4* b4 = reinterpret_cast<const float4*>(a.bias + o_tile + n0);
+          const ChunkIO io_c = chunk_io(b, o_tile + n0, t, tl);
           tmem_wait_ld();
-          const float* bptr = a.bias + o_tile + n0;
+          float v[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            if (e < nv_c) {
-              float v = __uint_as_float(m[e]);
-              if (nacc == 2) v += __uint_as_float(c[e]);
-              v = fmaf(v, unscale, __ldg(bptr + e));
-              v += r1[e];
-              if (a.post_div != 1.0f) v = v / a.post_div;
-              if (um_c && omask) v *= mv;
-              if (a.act_tanh) v = tanhf(v);
-              y_c[e * step_c] = v;
-            }
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const float4 q = __ldg(b4 + e4);
+            v[4 * e4 + 0] = fmaf(__uint_as_float(m[4 * e4 + 0]) + __uint_as_float(c[4 * e4 + 0]), unscale, q.x) + r1[4 * e4 + 0];
+            v[4 * e4 + 1] = fmaf(__uint_as_float(m[4 * e4 + 1]) + __uint_as_float(c[4 * e4 + 1]), unscale, q.y) + r1[4 * e4 + 1];
+            v[4 * e4 + 2] = fmaf(__uint_as_float(m[4 * e4 + 2]) + __uint_as_float(c[4 * e4 + 2]), unscale, q.z) + r1[4 * e4 + 2];
+            v[4 * e4 + 3] = fmaf(__uint_as_float(m[4 * e4 + 3]) + __uint_as_float(c[4 * e4 + 3]), unscale, q.w) + r1[4 * e4 + 3];
           }
+          if (a.post_div != 1.0f) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) r1[e] = p1[e];
-          res_c = res_n, acc_c = acc_n, y_c = y_n, step_c = step_n, um_c = um_n, nv_c = nv_n;
+            for (int e = 0; e < 16; ++e) v[e] = v[e] / a.post_div;
+          }
+          if (io_c.um && omask) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] *= mv;
+          }
+          if (a.act_tanh) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = tanhf(v[e]);
+          }
+          if (io_c.nvalid == 16) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (tin) io_c.y[e * io_c.step] = v[e];
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (tin && e < io_c.nvalid) io_c.y[e * io_c.step] = v[e];
+          }
+          if (have_next) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) r1[e] = p1[e];
+          }
         }
-      } else if (a.mode == MODE_GATE) {
+      } else if (mode == MODE_GATE) {
         // columns [0, N/2) hold the tanh half, [N/2, N) the sigmoid half of channels
         // ntile*N/2 + [0, N/2) (commons.py:100-107); bias is in the same virtual order.
-        const bool tin = t < a.Lout;
-        const int half = N >> 1;
+        const int hN = N >> 1;
+        const int npair = hN >> 4, hp = (npair + EPI_SPLIT - 1) / EPI_SPLIT;
+        const int g_lo = part * hp * 16, g_hi = min(npair, (part + 1) * hp) * 16;
         const float* bptr = a.bias + o_tile;
-        float* ybase = a.e[0].y + ((size_t)b * a.e[0].C + a.e[0].ch_off + ntile * half) * a.y_stride + t;
-        for (int n0 = 0; n0 < half; n0 += 16) {
-          uint32_t mt[16], ms[16], ct[16], cs[16];
-          tmem_ld16(tsub + (uint32_t)n0, mt);
-          tmem_ld16(tsub + (uint32_t)(half + n0), ms);
-          if (nacc == 2) {
-            tmem_ld16(tsub + (uint32_t)(N + n0), ct);
-            tmem_ld16(tsub + (uint32_t)(N + half + n0), cs);
-          }
+        float* ybase = a.e[0].y + ((size_t)b * a.e[0].C + a.e[0].ch_off + ntile * hN) * a.y_stride + t;
+        for (int n0 = g_lo; n0 < g_hi; n0 += 16) {
+          uint32_t m[16], c[16];
+          float g[16];
+          tmem_ld16(tsub + (uint32_t)n0, m);
+          tmem_ld16(tsub + (uint32_t)(N + n0), c);
           tmem_wait_ld();
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int cidx = ntile * half + n0 + e;
-            if (tin && cidx < (a.Cout >> 1)) {
-              float vt = __uint_as_float(mt[e]), vs = __uint_as_float(ms[e]);
-              if (nacc == 2) vt += __uint_as_float(ct[e]), vs += __uint_as_float(cs[e]);
-              vt = fmaf(vt, unscale, __ldg(bptr + n0 + e));
-              vs = fmaf(vs, unscale, __ldg(bptr + half + n0 + e));
-              ybase[(size_t)(n0 + e) * a.y_stride] = tanhf(vt) * sigmoidf_(vs);
-            }
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(bptr + n0) + e4);
+            g[4 * e4 + 0] = tanhf(fmaf(__uint_as_float(m[4 * e4 + 0]) + __uint_as_float(c[4 * e4 + 0]), unscale, q.x));
+            g[4 * e4 + 1] = tanhf(fmaf(__uint_as_float(m[4 * e4 + 1]) + __uint_as_float(c[4 * e4 + 1]), unscale, q.y));
+            g[4 * e4 + 2] = tanhf(fmaf(__uint_as_float(m[4 * e4 + 2]) + __uint_as_float(c[4 * e4 + 2]), unscale, q.z));
+            g[4 * e4 + 3] = tanhf(fmaf(__uint_as_float(m[4 * e4 + 3]) + __uint_as_float(c[4 * e4 + 3]), unscale, q.w));
           }
+          tmem_ld16(tsub + (uint32_t)(hN + n0), m);
+          tmem_ld16(tsub + (uint32_t)(N + hN + n0), c);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(bptr + hN + n0) + e4);
+            g[4 * e4 + 0] *= sigmoidf_(fmaf(__uint_as_float(m[4 * e4 + 0]) + __uint_as_float(c[4 * e4 + 0]), unscale, q.x));
+            g[4 * e4 + 1] *= sigmoidf_(fmaf(__uint_as_float(m[4 * e4 + 1]) + __uint_as_float(c[4 * e4 + 1]), unscale, q.y));
+            g[4 * e4 + 2] *= sigmoidf_(fmaf(__uint_as_float(m[4 * e4 + 2]) + __uint_as_float(c[4 * e4 + 2]), unscale, q.z));
+            g[4 * e4 + 3] *= sigmoidf_(fmaf(__uint_as_float(m[4 * e4 + 3]) + __uint_as_float(c[4 * e4 + 3]), unscale, q.w));
+          }
+          const int nval = max(0, min(16, (a.Cout >> 1) - (ntile * hN + n0)));
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (tin && e < nval) ybase[(size_t)(n0 + e) * a.y_stride] = g[e];
         }
       } else {
         // MODE_SHUFFLE: virtual channel o' = co*s + r of time row q lands at y[co, s*q + r - p]
         // (ConvTranspose1d polyphase form).
-        const int s = a.shuf_s;
-        const bool qin = t < a.Lout;
+        const int sh = a.shuf_s;
         float* ybase = a.e[0].y + ((size_t)b * a.e[0].C + a.e[0].ch_off) * a.y_stride;
-        for (int n0 = 0; n0 < N; n0 += 16) {
+        for (int n0 = n_lo; n0 < n_hi; n0 += 16) {
           uint32_t m[16], c[16];
           tmem_ld16(tsub + (uint32_t)n0, m);
-          if (nacc == 2) tmem_ld16(tsub + (uint32_t)(N + n0), c);
-          tmem_wait_ld();
+          tmem_ld16(tsub + (uint32_t)(N + n0), c);
           const int o0 = o_tile + n0;
+          float bv[16];
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(a.bias + o0) + e4);
+            bv[4 * e4] = q.x, bv[4 * e4 + 1] = q.y, bv[4 * e4 + 2] = q.z, bv[4 * e4 + 3] = q.w;
+          }
+          tmem_wait_ld();
           float v[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            float q = __uint_as_float(m[e]);
-            if (nacc == 2) q += __uint_as_float(c[e]);
-            v[e] = fmaf(q, unscale, (o0 + e < a.Cout) ? __ldg(a.bias + o0 + e) : 0.f);
-          }
-          if (!qin) continue;
-          if (s == 8 && (a.shuf_p & 3) == 0) {
+          for (int e = 0; e < 16; ++e) v[e] = fmaf(__uint_as_float(m[e]) + __uint_as_float(c[e]), unscale, bv[e]);
+          if (!tin) continue;
+          if (sh == 8 && (a.shuf_p & 3) == 0) {
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              const int co = (o0 >> 3) + g;
-              if (o0 + 8 * g >= a.Cout) break;
+            for (int gq = 0; gq < 2; ++gq) {
+              const int co = (o0 >> 3) + gq;
+              if (o0 + 8 * gq >= a.Cout) break;
               float* yrow = ybase + (size_t)co * a.y_stride;
-              const int tt = 8 * t - a.shuf_p;
+              const int tq = 8 * t - a.shuf_p;
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
-                const int th = tt + 4 * h;
+                const int th = tq + 4 * h;
                 if (th >= 0 && th + 3 < a.shuf_Lout) {
                   *reinterpret_cast<float4*>(yrow + th) =
-                      make_float4(v[8 * g + 4 * h], v[8 * g + 4 * h + 1], v[8 * g + 4 * h + 2], v[8 * g + 4 * h + 3]);
+                      make_float4(v[8 * gq + 4 * h], v[8 * gq + 4 * h + 1], v[8 * gq + 4 * h + 2], v[8 * gq + 4 * h + 3]);
                 } else {
 #pragma unroll
-                  for (int i = 0; i < 4; ++i)
-                    if (th + i >= 0 && th + i < a.shuf_Lout) yrow[th + i] = v[8 * g + 4 * h + i];
+                  for (int k2 = 0; k2 < 4; ++k2)
+                    if (th + k2 >= 0 && th + k2 < a.shuf_Lout) yrow[th + k2] = v[8 * gq + 4 * h + k2];
                 }
               }
             }
@@ -436,29 +548,28 @@ __global__ void __launch_bounds__(THREADS, 2) conv_tc_kernel(const ConvTcArgs ta
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               const int o = o0 + e;
-              const int co = o / s, r = o - co * s;
-              const int tt = s * t + r - a.shuf_p;
-              if (o < a.Cout && tt >= 0 && tt < a.shuf_Lout) ybase[(size_t)co * a.y_stride + tt] = v[e];
+              const int co = o / sh, r = o - co * sh;
+              const int tq = sh * t + r - a.shuf_p;
+              if (o < a.Cout && tq >= 0 && tq < a.shuf_Lout) ybase[(size_t)co * a.y_stride + tq] = v[e];
             }
           }
         }
       }
+      // every tcgen05.ld of this stage has completed (wait::ld above): hand the stage back
+      tc_fence_before();
+      mbar_arrive(&hdr->acc_empty[s]);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+  if (warp == 0) tmem_dealloc(tmem, ta.tmem_cols);
 }
 
 }  // namespace
 
 // ------------------------------------------------------------------------------- host helpers
-int conv_tc_rows(int K, int dil, int nsub) { return (128 * nsub + (K - 1) * dil + 7) & ~7; }
-
-size_t conv_tc_smem_bytes(int N, int K, int dil, int nsub, int nw, int na) {
-  return HEADER_BYTES + (size_t)na * conv_tc_rows(K, dil, nsub) * 16 * KG * 2 + (size_t)nw * N * 16 * KG * 2;
-}
+int conv_tc_rows(int K, int dil) { return (128 + (K - 1) * dil + 7) & ~7; }
 
 size_t conv_tc_packed_halves(int Cin, int Cout, int K, int N) {
   const int ntiles = (Cout + N - 1) / N, nchunks = Cin / KC;
@@ -478,15 +589,15 @@ float conv_tc_weight_scale(const float* w, size_t n) {
   return ldexpf(1.0f, 10 - e);
 }
 
-// wv(o, c, j) is the logical fp32 weight; image = [ntile][chunk][tap][hi|lo][kgroup][n][8].
+// wv(o, c, j) is the logical fp32 weight; image = [ntile][chunk][tap][kgroup][hi n | lo n][8].
 void conv_tc_pack(const float* w_ock, int Cout, int Cin, int K, int N, float scale, uint16_t* out) {
   const int ntiles = (Cout + N - 1) / N, nchunks = Cin / KC;
   size_t idx = 0;
   for (int nt = 0; nt < ntiles; ++nt)
     for (int ch = 0; ch < nchunks; ++ch)
       for (int j = 0; j < K; ++j)
-        for (int part = 0; part < 2; ++part)
-          for (int kg = 0; kg < KG; ++kg)
+        for (int kg = 0; kg < KG; ++kg)
+          for (int part = 0; part < 2; ++part)
             for (int n = 0; n < N; ++n)
               for (int e = 0; e < 8; ++e) {
                 const int o = nt * N + n, c = ch * KC + kg * 8 + e;
@@ -499,33 +610,54 @@ void conv_tc_pack(const float* w_ock, int Cout, int Cin, int K, int N, float sca
               }
 }
 
+// Ring depths for one layer shape: A ring of 4 (2 when the halo makes stages large), the rest of the
+// 227 KB goes to the weight ring; `resident` when every (chunk, tap) stage of the layer fits at once.
+void conv_tc_plan(int Cin, int Cout, int K, int dil, int N, int* na, int* nw, int* resident, size_t* smem_bytes) {
+  const size_t budget = 227 * 1024 - HEADER_BYTES;
+  const size_t a_stage = (size_t)conv_tc_rows(K, dil) * 16 * KG * 2, w_stage = (size_t)N * 32 * KG;
+  const int per_tile = (Cin / KC) * K, ntiles_n = (Cout + N - 1) / N;
+  int A = 4;
+  if (A * a_stage + 2 * w_stage > budget) A = 2;
+  int W = (int)((budget - A * a_stage) / w_stage);
+  if (W > MAXNW) W = MAXNW;
+  int res = 0;
+  if (ntiles_n == 1 && per_tile <= W) res = 1, W = per_tile;
+  *na = A, *nw = W, *resident = res;
+  *smem_bytes = HEADER_BYTES + A * a_stage + (size_t)W * w_stage;
+}
+
 cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
   ConvTcArgs ta = ta_in;
   const ConvArgs& a = ta.c;
-  if (a.Cin % KC != 0 || ta.N % 16 != 0 || ta.N < 16 || ta.N > 256) return cudaErrorInvalidValue;
-  if (ta.nsub < 1 || ta.nsub > 2 || ta.nw < 2 || ta.nw > MAXNW) return cudaErrorInvalidValue;
+  if (a.Cin % KC != 0 || ta.N % 16 != 0 || ta.N < 16 || ta.N > 128) return cudaErrorInvalidValue;
   if (a.split != (1 << 30) && (a.split % 16 != 0 || a.mode != MODE_STORE)) return cudaErrorInvalidValue;
   if (a.mode == MODE_GATE && (ta.N % 32 != 0 || a.Cout % 2)) return cudaErrorInvalidValue;
-  ta.na = (a.Cin / KC) > 1 ? NA : 1;
-  const int nacc = ta.sep_cross ? 2 : 1;
-  const int need = ta.nsub * nacc * ta.N;
-  if (need > 512) return cudaErrorInvalidValue;
+  if (a.B <= 0 || a.Lout <= 0 || a.Cout <= 0) return cudaSuccess;
+  size_t smem = 0;
+  conv_tc_plan(a.Cin, a.Cout, a.K, a.dil, ta.N, &ta.na, &ta.nw, &ta.resident, &smem);
+  if (ta.nw < 2 && !ta.resident) return cudaErrorInvalidValue;
   int cols = 32;
-  while (cols < need) cols <<= 1;
+  while (cols < 4 * ta.N) cols <<= 1;
   ta.tmem_cols = cols;
-  ta.rows = conv_tc_rows(a.K, a.dil, ta.nsub);
-  const size_t smem = conv_tc_smem_bytes(ta.N, a.K, a.dil, ta.nsub, ta.nw, ta.na);
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  static size_t configured[64] = {0};
+  ta.rows = conv_tc_rows(a.K, a.dil);
+  ta.ntiles_t = (a.Lout + 127) / 128;
+  const int ntiles_n = (a.Cout + ta.N - 1) / ta.N;
+  const long long items = (long long)ntiles_n * a.B * ta.ntiles_t;
+  if (items > 0x7FFFFFFFLL / 8) return cudaErrorInvalidValue;
+  ta.items = (int)items;
+  static int sm_count[64] = {0};
+  static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (smem > configured[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dev &= 63;
+  if (!configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    configured[dev & 63] = smem;
+    e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    configured[dev] = true;
   }
-  dim3 grid((a.Lout + 128 * ta.nsub - 1) / (128 * ta.nsub), (a.Cout + ta.N - 1) / ta.N, a.B);
-  if (grid.x == 0 || grid.y == 0 || grid.z == 0) return cudaSuccess;
+  const int grid = ta.items < sm_count[dev] ? ta.items : sm_count[dev];
   conv_tc_kernel<<<grid, THREADS, smem, stream>>>(ta);
   return cudaGetLastError();
 }

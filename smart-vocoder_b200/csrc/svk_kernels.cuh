@@ -68,17 +68,15 @@ struct ConvTcArgs {
   ConvArgs c;           // c.wp unused; c.bias = fp32 bias [Cout] (unscaled)
   const uint16_t* wtc;  // packed image, see conv_tc_pack
   float unscale;        // 1 / weight scale (power of two)
-  int N;                // output channels per CTA (multiple of 16, <= 256)
-  int nsub;             // 128-row time sub-tiles per CTA (1 or 2)
-  int sep_cross;        // keep the hi*lo cross terms in their own TMEM accumulator
-  int nw;               // weight pipeline stages
-  int rows, tmem_cols, na;  // filled by launch_conv_tc
+  int N;                // output channels per tile (multiple of 16, <= 128)
+  // filled by launch_conv_tc:
+  int rows, tmem_cols, na, nw, resident, items, ntiles_t;
 };
-int conv_tc_rows(int K, int dil, int nsub);
-size_t conv_tc_smem_bytes(int N, int K, int dil, int nsub, int nw, int na);
+int conv_tc_rows(int K, int dil);
 size_t conv_tc_packed_halves(int Cin, int Cout, int K, int N);
 float conv_tc_weight_scale(const float* w, size_t n);
 void conv_tc_pack(const float* w_ock, int Cout, int Cin, int K, int N, float scale, uint16_t* out);
+void conv_tc_plan(int Cin, int Cout, int K, int dil, int N, int* na, int* nw, int* resident, size_t* smem_bytes);
 cudaError_t launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream);
 
 // elementwise / small kernels

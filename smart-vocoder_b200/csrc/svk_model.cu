@@ -620,9 +620,7 @@ struct Runner {
       ta.c.bias = h->d_blob + pc->tc_b_off;
       ta.wtc = h->d_tcblob + pc->tc_off;
       ta.unscale = pc->tc_unscale;
-      ta.N = pc->tc_N, ta.nsub = 1, ta.sep_cross = 1;
-      ta.nw = 4;
-      while (ta.nw > 2 && conv_tc_smem_bytes(ta.N, a.K, a.dil, 1, ta.nw, a.Cin / TC_KC > 1 ? 2 : 1) > 112 * 1024) ta.nw--;
+      ta.N = pc->tc_N;
       err = launch_conv_tc(ta, stream);
     } else {
       err = launch_conv_ffma(a, stream);
@@ -861,6 +859,9 @@ extern "C" int svk_profile_end(svk_handle* h, svk_launch_record* out, int max_re
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, h->prof_events[2 * i], h->prof_events[2 * i + 1]));
     h->prof_records[i].ms = ms;
+    float gap = 0.f;
+    if (i > 0) CUDA_TRY(cudaEventElapsedTime(&gap, h->prof_events[2 * i - 1], h->prof_events[2 * i]));
+    h->prof_records[i].gap_ms = gap;
   }
   int m = 0;
   for (size_t i = 0; i < n && out && m < max_records; ++i) out[m++] = h->prof_records[i];

@@ -164,7 +164,7 @@ int run_tc(const float* x, int B, int Cin, int L, const std::vector<float>& w_oc
     ta.c.x = x, ta.c.x_C = Cin, ta.c.x_stride = L, ta.c.Lin = L, ta.c.pre_slope = pre_slope;
     ta.c.bias = dbias, ta.c.Cin = Cin, ta.c.Cout = CoutV, ta.c.CoutPad = CoutP, ta.c.K = K, ta.c.dil = dil, ta.c.pad = pad;
     ta.c.split = 1 << 30, ta.c.post_div = 1.0f, ta.c.B = B;
-    ta.wtc = dimg, ta.unscale = 1.0f / scale, ta.N = N, ta.nsub = 1, ta.sep_cross = 1, ta.nw = 3;
+    ta.wtc = dimg, ta.unscale = 1.0f / scale, ta.N = N;
     e = launch_conv_tc(ta, s);
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // the staging buffers are freed below

@@ -1,6 +1,6 @@
 // Developer probe for the tcgen05 conv kernel (conv_tc.cu): runs one shape, compares against a CPU
 // fp64 reference (small shapes) or the FFMA kernel (large shapes), prints error statistics and time.
-//   tc_probe B Cin Cout K dil L N nsub sep nw [ref=cpu|ffma] [res=0|1] [reps]
+//   tc_probe B Cin Cout K dil L N [ref=cpu|ffma] [res=0|1] [reps]
 // Built by tools/build_probe.sh; not part of the product.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -35,15 +35,15 @@ static float gauss() {
 }
 
 int main(int argc, char** argv) {
-  if (argc < 11) {
-    printf("usage: tc_probe B Cin Cout K dil L N nsub sep nw [cpu|ffma] [res] [reps]\n");
+  if (argc < 8) {
+    printf("usage: tc_probe B Cin Cout K dil L N [cpu|ffma] [res] [reps]\n");
     return 2;
   }
   const int B = atoi(argv[1]), Cin = atoi(argv[2]), Cout = atoi(argv[3]), K = atoi(argv[4]), dil = atoi(argv[5]),
-            L = atoi(argv[6]), N = atoi(argv[7]), nsub = atoi(argv[8]), sep = atoi(argv[9]), nw = atoi(argv[10]);
-  const bool cpu_ref = argc > 11 ? !strcmp(argv[11], "cpu") : true;
-  const int use_res = argc > 12 ? atoi(argv[12]) : 0;
-  const int reps = argc > 13 ? atoi(argv[13]) : 3;
+            L = atoi(argv[6]), N = atoi(argv[7]);
+  const bool cpu_ref = argc > 8 ? !strcmp(argv[8], "cpu") : true;
+  const int use_res = argc > 9 ? atoi(argv[9]) : 0;
+  const int reps = argc > 10 ? atoi(argv[10]) : 3;
   const int pad = (K - 1) * dil / 2;
   const float slope = 0.1f;
 
@@ -84,7 +84,7 @@ int main(int argc, char** argv) {
   a.Lout = L, a.y_stride = L, a.mode = MODE_STORE, a.split = 1 << 30, a.post_div = 1.0f, a.B = B;
   a.e[0].y = dy, a.e[0].C = Cout, a.e[0].ch_sign = 1, a.e[1].ch_sign = 1;
   a.e[0].res = dres;
-  ta.wtc = dimg, ta.unscale = 1.0f / scale, ta.N = N, ta.nsub = nsub, ta.sep_cross = sep, ta.nw = nw;
+  ta.wtc = dimg, ta.unscale = 1.0f / scale, ta.N = N;
 
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
@@ -173,9 +173,12 @@ int main(int argc, char** argv) {
     }
   }
   const double flops = 2.0 * B * (double)L * Cout * Cin * K;
-  printf("B=%d Cin=%d Cout=%d K=%d dil=%d L=%d N=%d nsub=%d sep=%d nw=%d res=%d ref=%s | maxabs %.3e rms %.3e (ref rms %.3e) "
+  int pna = 0, pnw = 0, pres = 0;
+  size_t psmem = 0;
+  conv_tc_plan(Cin, Cout, K, dil, N, &pna, &pnw, &pres, &psmem);
+  printf("B=%d Cin=%d Cout=%d K=%d dil=%d L=%d N=%d na=%d nw=%d resident=%d smem=%zu res=%d ref=%s | maxabs %.3e rms %.3e (ref rms %.3e) "
          "signed-rel-bias %.3e nan %zu bad %zu",
-         B, Cin, Cout, K, dil, L, N, nsub, sep, nw, use_res, cpu_ref ? "cpu64" : "ffma", maxabs, sqrt(sumsq / ny),
+         B, Cin, Cout, K, dil, L, N, pna, pnw, pres, psmem, use_res, cpu_ref ? "cpu64" : "ffma", maxabs, sqrt(sumsq / ny),
          sqrt(sumref2 / ny), bias_num / (bias_den + 1e-30), nnan, nbad);
   printf(" | %.3f ms %.1f TFLOP/s(useful)", best, flops / best / 1e9);
   if (!cpu_ref) printf(" ffma %.3f ms", ffma_ms);
