@@ -138,6 +138,37 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// Same MMA with descriptors given as (low word, shared high word): no 64-bit arithmetic per issue.
+__device__ __forceinline__ void umma_f16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_u32(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// Lean wait for the MMA warp: one try_wait on the fast path; bounded spin, then trap.
+__device__ __forceinline__ void mbar_wait_u32(uint32_t addr, uint32_t parity) {
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spin > (1u << 28)) __trap();
+  }
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
@@ -231,46 +262,60 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the loop (uniform control flow, barrier waits by all lanes); one elected
+    // lane issues.  The tensor pipe only stays busy if issuing an MMA costs far less than the MMA
+    // itself (64-128 cycles), so descriptors are never rebuilt: their high words are constants and
+    // their low words (start address >> 4 | LBO) advance by 32-bit adds.
+    {
       // f16 x f16 -> f32, both operands K-major, M = 128
       const uint32_t idesc1 = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * N) >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t desc_hi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
+      const uint32_t a_lo0 = ((smem_u32(a_smem) & 0x3FFFFu) >> 4) | ((a_plane >> 4) << 16);
+      const uint32_t w_lo0 = ((smem_u32(w_smem) & 0x3FFFFu) >> 4) | ((w_plane2 >> 4) << 16);
+      const uint32_t a_stage16 = a_stage >> 4, w_stage16 = w_stage >> 4;
+      const uint32_t lo_plane16 = (a_plane * KG) >> 4;  // hi planes -> lo planes of one A stage
+      const uint32_t ks_a16 = (2 * a_plane) >> 4, ks_b16 = (2 * w_plane2) >> 4;
+      const uint32_t dil16 = (uint32_t)dil;             // one tap = dil rows = dil * 16 B
+      const uint32_t bar_a_full = smem_u32(&hdr->a_full[0]), bar_a_empty = smem_u32(&hdr->a_empty[0]);
+      const uint32_t bar_w_full = smem_u32(&hdr->w_full[0]), bar_w_empty = smem_u32(&hdr->w_empty[0]);
+      const uint32_t bar_acc_full = smem_u32(&hdr->acc_full[0]), bar_acc_empty = smem_u32(&hdr->acc_empty[0]);
       const int wlim = resident ? per_tile : nw;
+      const bool leader = elect_one();
       int ast = 0, wst = 0;
       uint32_t aph = 0, wph = 0;
       for (int i = 0; i < n_my; ++i) {
         const int s = i & 1;
-        mbar_wait(&hdr->acc_empty[s], ((uint32_t)(i >> 1) & 1u) ^ 1u);  // epilogue drained this stage
+        mbar_wait_u32(bar_acc_empty + 8u * s, ((uint32_t)(i >> 1) & 1u) ^ 1u);  // epilogue drained this stage
         tc_fence_after();
         const uint32_t dmain = tmem + (uint32_t)(s * 2 * N), dcross = dmain + (uint32_t)N;
+        const bool wait_w = !resident || i == 0;
         uint32_t acc = 0;
         for (int ch = 0; ch < nchunks; ++ch) {
-          mbar_wait(&hdr->a_full[ast], aph);
+          mbar_wait_u32(bar_a_full + 8u * ast, aph);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(a_smem + (size_t)ast * a_stage), a_lo = a_hi + a_plane * KG;
+          uint32_t ah = a_lo0 + (uint32_t)ast * a_stage16;  // tap 0, ks 0, hi planes
           for (int j = 0; j < K; ++j) {
-            if (!resident || i == 0) {
-              mbar_wait(&hdr->w_full[wst], wph);
+            if (wait_w) {
+              mbar_wait_u32(bar_w_full + 8u * wst, wph);
               tc_fence_after();
             }
-            const uint32_t b0 = smem_u32(w_smem + (size_t)wst * w_stage);
-#pragma unroll
-            for (int ks = 0; ks < KC / 16; ++ks) {
-              const uint32_t roff = (uint32_t)(j * dil) * 16u + 2 * ks * a_plane;
-              const uint64_t dah = make_desc(a_hi + roff, a_plane, 128);
-              const uint64_t dal = make_desc(a_lo + roff, a_plane, 128);
-              const uint64_t db = make_desc(b0 + 2 * ks * w_plane2, w_plane2, 128);
-              umma_f16(dmain, dah, db, idesc2, acc);  // [main | cross] (+)= xh . [wh | wl]
-              acc = 1u;
-              umma_f16(dcross, dal, db, idesc1, 1u);  // cross += xl . wh
+            if (leader) {
+              const uint32_t bw = w_lo0 + (uint32_t)wst * w_stage16;
+              umma_f16_lo(dmain, ah, bw, desc_hi, idesc2, acc);  // [main | cross] (+)= xh . [wh | wl]
+              umma_f16_lo(dcross, ah + lo_plane16, bw, desc_hi, idesc1, 1u);  // cross += xl . wh
+              umma_f16_lo(dmain, ah + ks_a16, bw + ks_b16, desc_hi, idesc2, 1u);
+              umma_f16_lo(dcross, ah + ks_a16 + lo_plane16, bw + ks_b16, desc_hi, idesc1, 1u);
+              if (!resident) umma_commit_u32(bar_w_empty + 8u * wst);
             }
-            if (!resident) umma_commit(&hdr->w_empty[wst]);
+            acc = 1u;
+            ah += dil16;
             if (++wst == wlim) wst = 0, wph ^= 1;
           }
-          umma_commit(&hdr->a_empty[ast]);
+          if (leader) umma_commit_u32(bar_a_empty + 8u * ast);
           if (++ast == na) ast = 0, aph ^= 1;
         }
-        umma_commit(&hdr->acc_full[s]);
+        if (leader) umma_commit_u32(bar_acc_full + 8u * s);
       }
     }
     __syncwarp();
