@@ -276,7 +276,82 @@ bool conv_ffma_supports_k(int k) {
   return k == 1 || k == 2 || k == 3 || k == 5 || k == 7 || k == 9 || k == 11;
 }
 
+// ---- Cout == 1 (dec.conv_post, models.py:156-158): a pure HBM stream -- every input element is
+// read once, 2*Cin*K flops per output.  One CTA = 1024 outputs of one utterance, 4 per thread;
+// input channels are staged 8 at a time through shared memory (prologue applied while staging),
+// read back as conflict-free LDS.128.
+constexpr int C1_TILE = 1024, C1_THREADS = 256, C1_CC = 8, C1_MAXK = 11;
+constexpr int C1_PITCH = C1_TILE + 16;  // >= C1_TILE + C1_MAXK - 1, multiple of 4
+
+static __global__ void __launch_bounds__(C1_THREADS) conv_cout1_kernel(const ConvArgs a) {
+  __shared__ __align__(16) float xs[C1_CC][C1_PITCH];
+  __shared__ float ws[C1_CC * C1_MAXK];
+  const int tid = threadIdx.x, b = blockIdx.y;
+  const int t0 = blockIdx.x * C1_TILE;
+  const int K = a.K, span = C1_TILE + K - 1;
+  const float slope = a.pre_slope;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c0 = 0; c0 < a.Cin; c0 += C1_CC) {
+    __syncthreads();
+    const float* xb = a.x + ((size_t)b * a.x_C + a.x_ch_off + c0) * a.x_stride;
+    for (int idx = tid; idx < C1_CC * span; idx += C1_THREADS) {
+      const int c = idx / span, r = idx - c * span;
+      const int t = t0 - a.pad + r;
+      float v = (t >= 0 && t < a.Lin) ? __ldg(xb + (size_t)c * a.x_stride + t) : 0.f;
+      xs[c][r] = v > 0.f ? v : v * slope;
+    }
+    if (tid < C1_CC * K) ws[tid] = a.wp[(size_t)(c0 * K + tid) * a.CoutPad];
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < C1_CC; ++c) {
+      float v[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 f = *reinterpret_cast<const float4*>(&xs[c][4 * tid + 4 * q]);
+        v[4 * q] = f.x, v[4 * q + 1] = f.y, v[4 * q + 2] = f.z, v[4 * q + 3] = f.w;
+      }
+#pragma unroll
+      for (int j = 0; j < C1_MAXK; ++j) {
+        if (j < K) {
+          const float w = ws[c * K + j];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[i] = fmaf(w, v[i + j], acc[i]);
+        }
+      }
+    }
+  }
+  const float bias = a.bias[0];
+  float* y = a.e[0].y + ((size_t)b * a.e[0].C + a.e[0].ch_off) * a.y_stride;
+  const float* om = a.out_mask ? a.out_mask + (size_t)b * a.mask_stride : nullptr;
+  const int t = t0 + 4 * tid;
+  float o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float v = acc[i] + bias;
+    if (a.post_div != 1.0f) v = v / a.post_div;
+    if (om && a.e[0].use_mask && t + i < a.Lout) v *= om[t + i];
+    o[i] = a.act_tanh ? tanhf(v) : v;
+  }
+  if (t + 3 < a.Lout && (a.y_stride & 3) == 0) {
+    *reinterpret_cast<float4*>(y + t) = make_float4(o[0], o[1], o[2], o[3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (t + i < a.Lout) y[t + i] = o[i];
+  }
+}
+
+static bool conv_cout1_applicable(const ConvArgs& a) {
+  return a.Cout == 1 && a.mode == MODE_STORE && a.dil == 1 && a.K <= C1_MAXK && a.Cin % C1_CC == 0 && !a.in_mask &&
+         !a.e[0].res && !a.e[0].acc_in && a.e[0].ch_sign == 1 && a.split > 0;
+}
+
 cudaError_t launch_conv_ffma(const ConvArgs& a, cudaStream_t stream) {
+  if (conv_cout1_applicable(a)) {
+    if (a.B <= 0 || a.Lout <= 0) return cudaSuccess;
+    conv_cout1_kernel<<<dim3((a.Lout + C1_TILE - 1) / C1_TILE, a.B), C1_THREADS, 0, stream>>>(a);
+    return cudaGetLastError();
+  }
   switch (a.K) {
     case 1: return launch_k<1>(a, stream);
     case 2: return launch_k<2>(a, stream);

@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta
   const uint32_t a_stage = a_plane * KG * 2u;     // hi + lo
   const uint32_t w_plane2 = (uint32_t)N * 32u;    // one k-group plane of B: N hi rows then N lo rows
   const uint32_t w_stage = w_plane2 * KG;
-  uint8_t* a_smem = smem + HEADER_BYTES;
+  float* bias_s = reinterpret_cast<float*>(smem + HEADER_BYTES);  // [ntiles_n * N], staged once per CTA
+  uint8_t* a_smem = smem + HEADER_BYTES + ta.bias_bytes;
   uint8_t* w_smem = a_smem + (size_t)na * a_stage;
   const int nchunks = a.Cin / KC;
   const int per_tile = nchunks * K;  // weight stages per item
@@ -236,6 +237,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(&hdr->tmem_base, ta.tmem_cols);
+  for (int i = tid; i < ta.bias_count; i += THREADS) bias_s[i] = __ldg(a.bias + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -472,13 +474,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta
           uint32_t m[16], c[16];
           tmem_ld16(tsub + (uint32_t)n0, m);
           tmem_ld16(tsub + (uint32_t)(N + n0), c);
-          const float4* b4 = reinterpret_cast<const float4*>(a.bias + o_tile + n0);
+          const float4* b4 = reinterpret_cast<const float4*>(bias_s + o_tile + n0);
           const ChunkIO io_c = chunk_io(b, o_tile + n0, t, tl);
           tmem_wait_ld();
           float v[16];
 #pragma unroll
           for (int e4 = 0; e4 < 4; ++e4) {
-            const float4 q = __ldg(b4 + e4);
+            const float4 q = b4[e4];
             v[4 * e4 + 0] = fmaf(__uint_as_float(m[4 * e4 + 0]) + __uint_as_float(c[4 * e4 + 0]), unscale, q.x) + r1[4 * e4 + 0];
             v[4 * e4 + 1] = fmaf(__uint_as_float(m[4 * e4 + 1]) + __uint_as_float(c[4 * e4 + 1]), unscale, q.y) + r1[4 * e4 + 1];
             v[4 * e4 + 2] = fmaf(__uint_as_float(m[4 * e4 + 2]) + __uint_as_float(c[4 * e4 + 2]), unscale, q.z) + r1[4 * e4 + 2];
@@ -516,7 +518,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta
         const int hN = N >> 1;
         const int npair = hN >> 4, hp = (npair + EPI_SPLIT - 1) / EPI_SPLIT;
         const int g_lo = part * hp * 16, g_hi = min(npair, (part + 1) * hp) * 16;
-        const float* bptr = a.bias + o_tile;
+        const float* bptr = bias_s + o_tile;
         float* ybase = a.e[0].y + ((size_t)b * a.e[0].C + a.e[0].ch_off + ntile * hN) * a.y_stride + t;
         for (int n0 = g_lo; n0 < g_hi; n0 += 16) {
           uint32_t m[16], c[16];
@@ -526,7 +528,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta
           tmem_wait_ld();
 #pragma unroll
           for (int e4 = 0; e4 < 4; ++e4) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(bptr + n0) + e4);
+            const float4 q = reinterpret_cast<const float4*>(bptr + n0)[e4];
             g[4 * e4 + 0] = tanhf(fmaf(__uint_as_float(m[4 * e4 + 0]) + __uint_as_float(c[4 * e4 + 0]), unscale, q.x));
             g[4 * e4 + 1] = tanhf(fmaf(__uint_as_float(m[4 * e4 + 1]) + __uint_as_float(c[4 * e4 + 1]), unscale, q.y));
             g[4 * e4 + 2] = tanhf(fmaf(__uint_as_float(m[4 * e4 + 2]) + __uint_as_float(c[4 * e4 + 2]), unscale, q.z));
@@ -537,7 +539,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta
           tmem_wait_ld();
 #pragma unroll
           for (int e4 = 0; e4 < 4; ++e4) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(bptr + hN + n0) + e4);
+            const float4 q = reinterpret_cast<const float4*>(bptr + hN + n0)[e4];
             g[4 * e4 + 0] *= sigmoidf_(fmaf(__uint_as_float(m[4 * e4 + 0]) + __uint_as_float(c[4 * e4 + 0]), unscale, q.x));
             g[4 * e4 + 1] *= sigmoidf_(fmaf(__uint_as_float(m[4 * e4 + 1]) + __uint_as_float(c[4 * e4 + 1]), unscale, q.y));
             g[4 * e4 + 2] *= sigmoidf_(fmaf(__uint_as_float(m[4 * e4 + 2]) + __uint_as_float(c[4 * e4 + 2]), unscale, q.z));
@@ -561,7 +563,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta
           float bv[16];
 #pragma unroll
           for (int e4 = 0; e4 < 4; ++e4) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(a.bias + o0) + e4);
+            const float4 q = reinterpret_cast<const float4*>(bias_s + o0)[e4];
             bv[4 * e4] = q.x, bv[4 * e4 + 1] = q.y, bv[4 * e4 + 2] = q.z, bv[4 * e4 + 3] = q.w;
           }
           tmem_wait_ld();
@@ -657,8 +659,11 @@ void conv_tc_pack(const float* w_ock, int Cout, int Cin, int K, int N, float sca
 
 // Ring depths for one layer shape: A ring of 4 (2 when the halo makes stages large), the rest of the
 // 227 KB goes to the weight ring; `resident` when every (chunk, tap) stage of the layer fits at once.
+size_t conv_tc_bias_bytes(int Cout, int N) { return (((size_t)((Cout + N - 1) / N) * N * 4) + 127) & ~(size_t)127; }
+
 void conv_tc_plan(int Cin, int Cout, int K, int dil, int N, int* na, int* nw, int* resident, size_t* smem_bytes) {
-  const size_t budget = 227 * 1024 - HEADER_BYTES;
+  const size_t fixed = HEADER_BYTES + conv_tc_bias_bytes(Cout, N);
+  const size_t budget = 227 * 1024 - fixed;
   const size_t a_stage = (size_t)conv_tc_rows(K, dil) * 16 * KG * 2, w_stage = (size_t)N * 32 * KG;
   const int per_tile = (Cin / KC) * K, ntiles_n = (Cout + N - 1) / N;
   int A = 4;
@@ -668,7 +673,7 @@ void conv_tc_plan(int Cin, int Cout, int K, int dil, int N, int* na, int* nw, in
   int res = 0;
   if (ntiles_n == 1 && per_tile <= W) res = 1, W = per_tile;
   *na = A, *nw = W, *resident = res;
-  *smem_bytes = HEADER_BYTES + A * a_stage + (size_t)W * w_stage;
+  *smem_bytes = fixed + A * a_stage + (size_t)W * w_stage;
 }
 
 cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
@@ -685,6 +690,8 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
   while (cols < 4 * ta.N) cols <<= 1;
   ta.tmem_cols = cols;
   ta.rows = conv_tc_rows(a.K, a.dil);
+  ta.bias_bytes = (int)conv_tc_bias_bytes(a.Cout, ta.N);
+  ta.bias_count = ((a.Cout + ta.N - 1) / ta.N) * ta.N;
   ta.ntiles_t = (a.Lout + 127) / 128;
   const int ntiles_n = (a.Cout + ta.N - 1) / ta.N;
   const long long items = (long long)ntiles_n * a.B * ta.ntiles_t;

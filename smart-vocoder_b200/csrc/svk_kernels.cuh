@@ -70,7 +70,7 @@ struct ConvTcArgs {
   float unscale;        // 1 / weight scale (power of two)
   int N;                // output channels per tile (multiple of 16, <= 128)
   // filled by launch_conv_tc:
-  int rows, tmem_cols, na, nw, resident, items, ntiles_t;
+  int rows, tmem_cols, na, nw, resident, items, ntiles_t, bias_bytes, bias_count;
 };
 int conv_tc_rows(int K, int dil);
 size_t conv_tc_packed_halves(int Cin, int Cout, int K, int N);
