@@ -171,6 +171,7 @@ int svk_flow_reverse(svk_handle *h, float *z_dev, const float *mask_dev, int B, 
 int svk_generator(svk_handle *h, const float *z_dev, int B, int L, float *o_dev, void *workspace_dev,
                   size_t workspace_bytes, void *stream);
 /* ResBlock1.forward(x) (modules.py:210-223) of dec.resblocks[index]: [B,C,L] -> [B,C,L]. */
+size_t svk_resblock1_workspace_bytes(const svk_handle *h, int index, int B, int L);
 int svk_resblock1(svk_handle *h, int index, const float *x_dev, int B, int L, float *y_dev,
                   void *workspace_dev, size_t workspace_bytes, void *stream);
 

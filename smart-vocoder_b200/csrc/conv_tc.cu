@@ -30,9 +30,11 @@
 // Pipelines: A ring (mbarrier full/empty), weight ring (expect_tx / tcgen05.commit) -- or, when the
 // layer's whole weight image fits the ring, weights are loaded once and stay resident for every tile
 // of the CTA -- and the accumulator full/empty pair.
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "svk_kernels.cuh"
 
@@ -57,6 +59,14 @@ constexpr int PROD_GROUPS = PROD_WARPS / 4;                  // groups take alte
 constexpr int EPI_SPLIT = EPI_WARPS / 4;                     // warps sharing one TMEM lane quarter split the columns
 constexpr int EPI_THREADS = 32 * EPI_WARPS;
 constexpr int FIRST_EPI_WARP = 2 + PROD_WARPS;
+// TMA-input variant (activations already in HBM as fp16 hi/lo operand images): warps 0..3 are the
+// weight producer, the MMA issuer, the activation TMA issuer and a spare; the rest is epilogue.
+#ifndef SVK_TC_EPI_WARPS_TMA
+#define SVK_TC_EPI_WARPS_TMA 8
+#endif
+constexpr int EPI_WARPS_TMA = SVK_TC_EPI_WARPS_TMA;
+constexpr int THREADS_TMA = 128 + 32 * EPI_WARPS_TMA;
+static_assert(EPI_WARPS_TMA % 4 == 0, "a warp may only read TMEM lane quarter (warp id & 3)");
 static_assert(PROD_WARPS % 4 == 0 && (PROD_GROUPS == 1 || PROD_GROUPS == 2), "producer groups");
 static_assert(EPI_WARPS % 4 == 0 && EPI_SPLIT >= 1, "a warp may only read TMEM lane quarter (warp id & 3)");
 
@@ -113,6 +123,16 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                    smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+
+// 4-D tiled TMA load (cp.async.bulk.tensor): box -> smem, completion counted on the mbarrier.
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -209,7 +229,13 @@ __device__ __forceinline__ void decode_item(int item, int ntiles_t, int B, int& 
   nt = r / B;
 }
 
-__global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta) {
+template <bool kTma>
+__global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
+    conv_tc_kernel(const ConvTcArgs ta, const __grid_constant__ CUtensorMap tmap) {
+  constexpr int kThreads = kTma ? THREADS_TMA : THREADS;
+  constexpr int kFirstEpi = kTma ? 4 : FIRST_EPI_WARP;
+  constexpr int kEpiSplit = (kTma ? EPI_WARPS_TMA : EPI_WARPS) / 4;
+  constexpr int kEpiThreads = 32 * (kTma ? EPI_WARPS_TMA : EPI_WARPS);
   extern __shared__ __align__(128) uint8_t smem[];
   const ConvArgs& a = ta.c;
   SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
@@ -231,13 +257,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta
   const int n_my = (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < na; ++i) mbar_init(&hdr->a_full[i], PROD_GROUP), mbar_init(&hdr->a_empty[i], 1);
+    for (int i = 0; i < na; ++i) mbar_init(&hdr->a_full[i], kTma ? 1 : PROD_GROUP), mbar_init(&hdr->a_empty[i], 1);
     for (int i = 0; i < MAXNW; ++i) mbar_init(&hdr->w_full[i], 1), mbar_init(&hdr->w_empty[i], 1);
-    for (int i = 0; i < 2; ++i) mbar_init(&hdr->acc_full[i], 1), mbar_init(&hdr->acc_empty[i], EPI_THREADS);
+    for (int i = 0; i < 2; ++i) mbar_init(&hdr->acc_full[i], 1), mbar_init(&hdr->acc_empty[i], kEpiThreads);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(&hdr->tmem_base, ta.tmem_cols);
-  for (int i = tid; i < ta.bias_count; i += THREADS) bias_s[i] = __ldg(a.bias + i);
+  for (int i = tid; i < ta.bias_count; i += kThreads) bias_s[i] = __ldg(a.bias + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -321,53 +347,80 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta
       }
     }
     __syncwarp();
-  } else if (warp < FIRST_EPI_WARP) {
-    // ------------------------------------------------ activation producers (2 groups x 128 threads)
-    // Group g stages chunks q = g, g+2, ... of this CTA's chunk sequence (q = tile * nchunks + chunk).
-    // One task = one time row x all KC channels of the chunk: 32 independent coalesced loads in
-    // flight per thread, then leaky_relu / mask / fp16 hi-lo split and 2 x 4 conflict-free 16 B stores.
-    const int g = (warp - 2) >> 2;
-    const int rp = tid - 64 - PROD_GROUP * g;
-    const float slope = a.pre_slope;
-    const int na_shift = na == 4 ? 2 : 1;
-    const int total_q = n_my * nchunks;
-    for (int q = g; q < total_q; q += PROD_GROUPS) {
-      const int i = q / nchunks, ch = q - i * nchunks;
-      int nt, b, tt;
-      decode_item((int)blockIdx.x + i * (int)gridDim.x, ntiles_t, a.B, nt, b, tt);
-      const int t0 = tt * 128;
-      const int as = q & (na - 1);
-      mbar_wait(&hdr->a_empty[as], ((uint32_t)(q >> na_shift) & 1u) ^ 1u);
-      uint4* Ahi = reinterpret_cast<uint4*>(a_smem + (size_t)as * a_stage);
-      uint4* Alo = Ahi + KG * rows;
-      const float* mrow = a.in_mask ? a.in_mask + (size_t)b * a.mask_stride : nullptr;
-      const float* xb = a.x + ((size_t)b * a.x_C + a.x_ch_off + ch * KC) * a.x_stride;
-      for (int r = rp; r < rows; r += PROD_GROUP) {
-        const int t = t0 - a.pad + r;
-        const bool ok = t >= 0 && t < a.Lin;
-        float v[KC];
-#pragma unroll
-        for (int c = 0; c < KC; ++c) v[c] = ok ? __ldg(xb + (size_t)c * a.x_stride + t) : 0.f;
-        const float mk = (ok && mrow) ? __ldg(mrow + t) : 1.0f;
-#pragma unroll
-        for (int c = 0; c < KC; ++c) {
-          float qv = v[c];
-          qv = qv > 0.f ? qv : qv * slope;
-          v[c] = mrow ? qv * mk : qv;
-        }
-#pragma unroll
-        for (int kg = 0; kg < KG; ++kg) {
-          uint4 h, l;
-          split2(v[kg * 8 + 0], v[kg * 8 + 1], h.x, l.x);
-          split2(v[kg * 8 + 2], v[kg * 8 + 3], h.y, l.y);
-          split2(v[kg * 8 + 4], v[kg * 8 + 5], h.z, l.z);
-          split2(v[kg * 8 + 6], v[kg * 8 + 7], h.w, l.w);
-          Ahi[kg * rows + r] = h;
-          Alo[kg * rows + r] = l;
+  } else if (warp < kFirstEpi) {
+    if constexpr (kTma) {
+      // ---------------------------------------------- activation loader: one TMA box per 32-channel chunk
+      // The source tensor is the fp16 operand image [hi|lo][B*C/8][L][8] written by the producing
+      // layer's epilogue (or split_image_kernel); box (8, rows, 4 k-groups, 2) lands exactly in the
+      // A stage layout.  Rows outside [0, L) are zero-filled by the TMA unit = the conv's zero padding
+      // (leaky_relu and mask were applied when the image was written).
+      if (warp == 2 && lane == 0) {
+        const int total_q = n_my * nchunks;
+        const int cg0 = a.x_ch_off >> 3, cgs = a.x_C >> 3;
+        int as = 0;
+        uint32_t ph = 0;
+        int q = 0;
+        for (int i = 0; i < n_my && q < total_q; ++i) {
+          int nt, b, tt;
+          decode_item((int)blockIdx.x + i * (int)gridDim.x, ntiles_t, a.B, nt, b, tt);
+          const int t0 = tt * 128 - a.pad;
+          for (int ch = 0; ch < nchunks; ++ch, ++q) {
+            mbar_wait(&hdr->a_empty[as], ph ^ 1);
+            mbar_arrive_expect_tx(&hdr->a_full[as], a_stage);
+            tma_load_4d(a_smem + (size_t)as * a_stage, &tmap, 0, t0, b * cgs + cg0 + ch * KG, 0, &hdr->a_full[as]);
+            if (++as == na) as = 0, ph ^= 1;
+          }
         }
       }
-      fence_proxy_async_smem();
-      mbar_arrive(&hdr->a_full[as]);
+      __syncwarp();
+    } else {
+      // ------------------------------------------------ activation producers (2 groups x 128 threads)
+      // Group g stages chunks q = g, g+2, ... of this CTA's chunk sequence (q = tile * nchunks + chunk).
+      // One task = one time row x all KC channels of the chunk: 32 independent coalesced loads in
+      // flight per thread, then leaky_relu / mask / fp16 hi-lo split and 2 x 4 conflict-free 16 B stores.
+      const int g = (warp - 2) >> 2;
+      const int rp = tid - 64 - PROD_GROUP * g;
+      const float slope = a.pre_slope;
+      const int na_shift = na == 4 ? 2 : 1;
+      const int total_q = n_my * nchunks;
+      for (int q = g; q < total_q; q += PROD_GROUPS) {
+        const int i = q / nchunks, ch = q - i * nchunks;
+        int nt, b, tt;
+        decode_item((int)blockIdx.x + i * (int)gridDim.x, ntiles_t, a.B, nt, b, tt);
+        const int t0 = tt * 128;
+        const int as = q & (na - 1);
+        mbar_wait(&hdr->a_empty[as], ((uint32_t)(q >> na_shift) & 1u) ^ 1u);
+        uint4* Ahi = reinterpret_cast<uint4*>(a_smem + (size_t)as * a_stage);
+        uint4* Alo = Ahi + KG * rows;
+        const float* mrow = a.in_mask ? a.in_mask + (size_t)b * a.mask_stride : nullptr;
+        const float* xb = a.x + ((size_t)b * a.x_C + a.x_ch_off + ch * KC) * a.x_stride;
+        for (int r = rp; r < rows; r += PROD_GROUP) {
+          const int t = t0 - a.pad + r;
+          const bool ok = t >= 0 && t < a.Lin;
+          float v[KC];
+  #pragma unroll
+          for (int c = 0; c < KC; ++c) v[c] = ok ? __ldg(xb + (size_t)c * a.x_stride + t) : 0.f;
+          const float mk = (ok && mrow) ? __ldg(mrow + t) : 1.0f;
+  #pragma unroll
+          for (int c = 0; c < KC; ++c) {
+            float qv = v[c];
+            qv = qv > 0.f ? qv : qv * slope;
+            v[c] = mrow ? qv * mk : qv;
+          }
+  #pragma unroll
+          for (int kg = 0; kg < KG; ++kg) {
+            uint4 h, l;
+            split2(v[kg * 8 + 0], v[kg * 8 + 1], h.x, l.x);
+            split2(v[kg * 8 + 2], v[kg * 8 + 3], h.y, l.y);
+            split2(v[kg * 8 + 4], v[kg * 8 + 5], h.z, l.z);
+            split2(v[kg * 8 + 6], v[kg * 8 + 7], h.w, l.w);
+            Ahi[kg * rows + r] = h;
+            Alo[kg * rows + r] = l;
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&hdr->a_full[as]);
+      }
     }
   } else {
     // ------------------------------------------------ epilogue: TMEM -> registers -> global
@@ -377,7 +430,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta
     // the NEXT chunk -- and of the next tile's first chunk -- are requested before the current chunk
     // is finished, and only the final store is predicated.
     const int q4 = warp & 3;
-    const int part = (warp - FIRST_EPI_WARP) >> 2;
+    const int part = (warp - kFirstEpi) >> 2;
     const int row = q4 * 32 + lane;
     const float unscale = ta.unscale;
     const int mode = a.mode;
@@ -387,9 +440,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta
       const float* res;
       const float* acc;
       float* y;
+      uint16_t* sp;  // operand-image position of (hi plane, first channel group of the chunk, row t), or null
+      float sp_slope;
       ptrdiff_t step;
       int um, nvalid;
     };
+    const size_t sp_plane = (size_t)a.B * a.y_stride;  // x channels: halves between the hi and lo planes
     auto chunk_io = [&](int b, int o0, int t, int tl) {
       ChunkIO io;
       const int s1 = o0 >= a.split ? 1 : 0;
@@ -398,7 +454,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta
       const size_t off = ((size_t)b * d.C + d.ch_off + d.ch_sign * rel0) * a.y_stride;
       io.res = d.res ? d.res + off + tl : nullptr;
       io.acc = d.acc_in ? d.acc_in + off + tl : nullptr;
-      io.y = d.y + off + t;
+      io.y = d.y ? d.y + off + t : nullptr;
+      io.sp = d.split ? d.split + (((size_t)b * (d.C >> 3) + ((d.ch_off + rel0) >> 3)) * a.y_stride + t) * 8 : nullptr;
+      io.sp_slope = d.split_slope;
       io.step = (ptrdiff_t)d.ch_sign * a.y_stride;
       io.um = d.use_mask;
       io.nvalid = max(0, min(16, a.Cout - o0));
@@ -427,7 +485,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta
       }
     };
 
-    const int nch = N >> 4, hc = (nch + EPI_SPLIT - 1) / EPI_SPLIT;
+    const int nch = N >> 4, hc = (nch + kEpiSplit - 1) / kEpiSplit;
     const int n_lo = part * hc * 16, n_hi = min(nch, (part + 1) * hc) * 16;  // STORE / SHUFFLE column range
     const bool have_cols = n_lo < n_hi;
 
@@ -498,7 +556,27 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta
 #pragma unroll
             for (int e = 0; e < 16; ++e) v[e] = tanhf(v[e]);
           }
-          if (io_c.nvalid == 16) {
+          if (io_c.sp && tin) {
+            // second output: leaky_relu(y) as fp16 hi/lo, 8 channels = one 16 B row of the operand image
+            uint16_t* sp = io_c.sp;
+#pragma unroll
+            for (int g8 = 0; g8 < 2; ++g8) {
+              float w8[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) w8[e] = v[8 * g8 + e] > 0.f ? v[8 * g8 + e] : v[8 * g8 + e] * io_c.sp_slope;
+              uint4 h, l;
+              split2(w8[0], w8[1], h.x, l.x);
+              split2(w8[2], w8[3], h.y, l.y);
+              split2(w8[4], w8[5], h.z, l.z);
+              split2(w8[6], w8[7], h.w, l.w);
+              *reinterpret_cast<uint4*>(sp) = h;
+              *reinterpret_cast<uint4*>(sp + sp_plane * (size_t)a.e[o_tile + n0 >= a.split ? 1 : 0].C) = l;
+              sp += (size_t)a.y_stride * 8;
+            }
+          }
+          if (!io_c.y) {
+            // operand image only
+          } else if (io_c.nvalid == 16) {
 #pragma unroll
             for (int e = 0; e < 16; ++e)
               if (tin) io_c.y[e * io_c.step] = v[e];
@@ -516,7 +594,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta
         // columns [0, N/2) hold the tanh half, [N/2, N) the sigmoid half of channels
         // ntile*N/2 + [0, N/2) (commons.py:100-107); bias is in the same virtual order.
         const int hN = N >> 1;
-        const int npair = hN >> 4, hp = (npair + EPI_SPLIT - 1) / EPI_SPLIT;
+        const int npair = hN >> 4, hp = (npair + kEpiSplit - 1) / kEpiSplit;
         const int g_lo = part * hp * 16, g_hi = min(npair, (part + 1) * hp) * 16;
         const float* bptr = bias_s + o_tile;
         float* ybase = a.e[0].y + ((size_t)b * a.e[0].C + a.e[0].ch_off + ntile * hN) * a.y_stride + t;
@@ -613,6 +691,30 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const ConvTcArgs ta
   if (warp == 0) tmem_dealloc(tmem, ta.tmem_cols);
 }
 
+// fp32 [B, C, L] -> operand image [hi|lo][B][C/8][L][8] of leaky_relu(x, slope): one thread = one
+// (channel group, time) cell: 8 coalesced channel-row reads, two 16 B stores.
+__global__ void __launch_bounds__(256) split_image_kernel(const float* __restrict__ x, int B, int C, int L, float slope,
+                                                          uint16_t* __restrict__ img) {
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int cg = blockIdx.y, b = blockIdx.z;
+  if (t >= L) return;
+  const float* xr = x + ((size_t)b * C + cg * 8) * L + t;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float q = __ldg(xr + (size_t)e * L);
+    v[e] = q > 0.f ? q : q * slope;
+  }
+  uint4 h, l;
+  split2(v[0], v[1], h.x, l.x);
+  split2(v[2], v[3], h.y, l.y);
+  split2(v[4], v[5], h.z, l.z);
+  split2(v[6], v[7], h.w, l.w);
+  const size_t cell = (((size_t)b * (C >> 3) + cg) * L + t) * 8;
+  *reinterpret_cast<uint4*>(img + cell) = h;
+  *reinterpret_cast<uint4*>(img + (size_t)B * C * L + cell) = l;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------- host helpers
@@ -676,6 +778,50 @@ void conv_tc_plan(int Cin, int Cout, int K, int dil, int N, int* na, int* nw, in
   *smem_bytes = fixed + A * a_stage + (size_t)W * w_stage;
 }
 
+cudaError_t launch_split_image(const float* x, int B, int C, int L, float slope, uint16_t* img, cudaStream_t stream) {
+  if (C % 8 != 0) return cudaErrorInvalidValue;
+  if (B <= 0 || C <= 0 || L <= 0) return cudaSuccess;
+  split_image_kernel<<<dim3((L + 255) / 256, C / 8, B), 256, 0, stream>>>(x, B, C, L, slope, img);
+  return cudaGetLastError();
+}
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libsvk does not link libcuda).
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// Operand image [hi|lo][B*C/8][L][8] fp16 as a 4-D tensor; box = (8, rows, 4 k-groups, hi+lo) = one A stage.
+cudaError_t make_image_map(const uint16_t* img, int B, int C, int L, int rows, CUtensorMap* map) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return cudaErrorNotSupported;
+  const cuuint64_t dims[4] = {8, (cuuint64_t)L, (cuuint64_t)B * (C / 8), 2};
+  const cuuint64_t strides[3] = {16, (cuuint64_t)L * 16, (cuuint64_t)B * (C / 8) * L * 16};
+  const cuuint32_t box[4] = {8, (cuuint32_t)rows, (cuuint32_t)KG, 2};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<uint16_t*>(img), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+}  // namespace
+
 cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
   ConvTcArgs ta = ta_in;
   const ConvArgs& a = ta.c;
@@ -703,14 +849,28 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
   cudaGetDevice(&dev);
   dev &= 63;
   if (!configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
     configured[dev] = true;
   }
   const int grid = ta.items < sm_count[dev] ? ta.items : sm_count[dev];
-  conv_tc_kernel<<<grid, THREADS, smem, stream>>>(ta);
+  for (int sd = 0; sd < 2; ++sd)
+    if (a.e[sd].split && (a.mode != MODE_STORE || a.e[sd].ch_sign != 1 || a.e[sd].ch_off % 8 || a.e[sd].C % 8 || a.Cout % 16))
+      return cudaErrorInvalidValue;
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  if (ta.x_split) {
+    if (a.x_C % 8 || a.x_ch_off % 8 || a.x_stride != a.Lin) return cudaErrorInvalidValue;
+    cudaError_t e = make_image_map(ta.x_split, a.B, a.x_C, a.Lin, ta.rows, &map);
+    if (e != cudaSuccess) return e;
+    conv_tc_kernel<true><<<grid, THREADS_TMA, smem, stream>>>(ta, map);
+  } else {
+    conv_tc_kernel<false><<<grid, THREADS, smem, stream>>>(ta, map);
+  }
   return cudaGetLastError();
 }
 

@@ -16,6 +16,11 @@ struct EpiDesc {
   int ch_off;           // destination channel = ch_off + ch_sign * (o - first o of this side)
   int ch_sign;          // +1, or -1 to write channels in reversed order (folded Flip)
   int use_mask;         // multiply by out_mask[b, t]
+  // Optional second output for the tcgen05 engine: leaky_relu(y, split_slope) as the fp16 hi/lo operand
+  // image [hi|lo][B][C/8][L = y_stride][8] that the consuming conv loads by TMA (conv_tc.cu).  `y` may
+  // then be null when nothing reads the fp32 tensor.  Needs ch_sign == +1 and ch_off % 8 == 0.
+  uint16_t* split;
+  float split_slope;
 };
 
 enum ConvMode : int {
@@ -69,6 +74,8 @@ struct ConvTcArgs {
   const uint16_t* wtc;  // packed image, see conv_tc_pack
   float unscale;        // 1 / weight scale (power of two)
   int N;                // output channels per tile (multiple of 16, <= 128)
+  const uint16_t* x_split;  // non-null: input comes from this operand image (geometry [B, c.x_C, c.Lin]) by TMA;
+                            // leaky_relu / mask were applied when it was written, c.x / pre_slope / in_mask unused
   // filled by launch_conv_tc:
   int rows, tmem_cols, na, nw, resident, items, ntiles_t, bias_bytes, bias_count;
 };
@@ -78,6 +85,9 @@ float conv_tc_weight_scale(const float* w, size_t n);
 void conv_tc_pack(const float* w_ock, int Cout, int Cin, int K, int N, float scale, uint16_t* out);
 void conv_tc_plan(int Cin, int Cout, int K, int dil, int N, int* na, int* nw, int* resident, size_t* smem_bytes);
 cudaError_t launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream);
+// fp32 [B, C, L] -> operand image of leaky_relu(x, slope) (C % 8 == 0); bytes = 4 * B * C * L
+cudaError_t launch_split_image(const float* x, int B, int C, int L, float slope, uint16_t* img, cudaStream_t stream);
+inline size_t split_image_halves(int B, int C, int L) { return (size_t)2 * B * C * L; }
 
 // elementwise / small kernels
 cudaError_t launch_sequence_mask(const int64_t* lengths, int B, int T, float* mask, cudaStream_t s);

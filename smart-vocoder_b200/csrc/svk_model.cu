@@ -586,10 +586,17 @@ struct Runner {
     r.layer = layer, r.cin = a.Cin, r.cout = cout_logical, r.k = a.K, r.dilation = a.dil, r.batch = B;
     r.length = out_len;
     r.flops = 2.0 * macs;
-    double bytes = 4.0 * ((double)B * a.Cin * a.Lin + (double)B * cout_logical * out_len + (double)a.Cin * a.K * a.Cout);
-    for (int s = 0; s < 2; ++s) {
-      if (a.e[s].res) bytes += 4.0 * B * (double)out_len * (s == 0 ? (a.split < a.Cout ? a.split : a.Cout) : a.Cout - a.split);
-      if (a.e[s].acc_in) bytes += 4.0 * B * (double)out_len * (s == 0 ? (a.split < a.Cout ? a.split : a.Cout) : a.Cout - a.split);
+    // compulsory traffic of this launch: input (fp32 tensor or operand image, 4 B/element either way),
+    // weights, and per destination side the fp32 tensor and/or operand image written plus res / acc_in read
+    double bytes = 4.0 * ((double)B * a.Cin * a.Lin + (double)a.Cin * a.K * a.Cout);
+    if (a.mode != MODE_STORE) {
+      bytes += 4.0 * B * (double)cout_logical * out_len;
+    } else {
+      for (int s = 0; s < 2; ++s) {
+        const double n_s = s == 0 ? (a.split < a.Cout ? a.split : a.Cout) : (a.split < a.Cout ? a.Cout - a.split : 0);
+        const double per = 4.0 * B * (double)out_len * n_s;
+        bytes += per * ((a.e[s].y ? 1 : 0) + (a.e[s].split ? 1 : 0) + (a.e[s].res ? 1 : 0) + (a.e[s].acc_in ? 1 : 0));
+      }
     }
     r.bytes = bytes;
     h->prof_records.push_back(r);
@@ -599,7 +606,7 @@ struct Runner {
   void prof_close(bool open) {
     if (open) cudaEventRecord(h->prof_events[2 * (h->prof_records.size() - 1) + 1], stream);
   }
-  void run(const ConvArgs& a, int layer = SVK_LAYER_OTHER) {
+  void run(const ConvArgs& a, int layer = SVK_LAYER_OTHER, const uint16_t* x_split = nullptr) {
     if (err != cudaSuccess) return;
     int cout_logical = a.Cout;
     int64_t out_len = a.Lout;
@@ -621,7 +628,10 @@ struct Runner {
       ta.wtc = h->d_tcblob + pc->tc_off;
       ta.unscale = pc->tc_unscale;
       ta.N = pc->tc_N;
+      ta.x_split = x_split;
       err = launch_conv_tc(ta, stream);
+    } else if (x_split) {
+      err = cudaErrorInvalidValue;  // operand images are a tcgen05-engine format
     } else {
       err = launch_conv_ffma(a, stream);
     }
@@ -655,6 +665,42 @@ struct Runner {
     }
   }
 
+  // True when every conv of the block runs on the tcgen05 engine with operand-image I/O.
+  bool resblock_uses_images(const ResBlock& rb) const {
+    if (h->cfg.precision != SVK_PRECISION_TC || rb.C % 16) return false;
+    for (int l = 0; l < SVK_RESBLOCK_PAIRS; ++l)
+      if (!rb.c1[l].tc || !rb.c2[l].tc) return false;
+    return true;
+  }
+
+  // ResBlock1.forward on the tcgen05 engine.  Activations that feed a conv live in HBM as fp16 hi/lo
+  // operand images of leaky_relu(x, 0.1) (written by the producing epilogue, loaded by TMA); the fp32
+  // tensors are kept only where the residual adds need them (modules.py:220).  x_img = image of x.
+  void resblock_images(const ResBlock& rb, const float* x, const uint16_t* x_img, uint16_t* xt_img, float* cur,
+                       uint16_t* cur_img, float* dst, const float* acc_in, float post_div, int L) {
+    const int C = rb.C;
+    for (int l = 0; l < SVK_RESBLOCK_PAIRS; ++l) {
+      const float* src = l == 0 ? x : cur;
+      const uint16_t* src_img = l == 0 ? x_img : cur_img;
+      const int d = rb.dil[l];
+      ConvArgs a = base(rb.c1[l], src, C, 0, L, L, d, (rb.k * d - d) / 2, L, L);
+      a.pre_slope = 0.1f;
+      a.e[0].y = nullptr, a.e[0].C = C;
+      a.e[0].split = xt_img, a.e[0].split_slope = 0.1f;  // xt is only ever read through leaky_relu by c2
+      run(a, SVK_LAYER_RESBLOCK_CONV1, src_img);
+      ConvArgs b = base(rb.c2[l], nullptr, C, 0, L, L, 1, (rb.k - 1) / 2, L, L);
+      b.pre_slope = 0.1f;
+      b.e[0].res = src, b.e[0].C = C;
+      if (l < SVK_RESBLOCK_PAIRS - 1) {
+        b.e[0].y = cur;
+        b.e[0].split = cur_img, b.e[0].split_slope = 0.1f;
+      } else {
+        b.e[0].y = dst, b.e[0].acc_in = acc_in, b.post_div = post_div;
+      }
+      run(b, SVK_LAYER_RESBLOCK_CONV2, xt_img);
+    }
+  }
+
   // ResBlock1.forward (modules.py:210-223).  `dst` receives x_out (+ acc_in) / post_div.
   void resblock(const ResBlock& rb, const float* x, float* xt, float* cur, float* dst, const float* acc_in,
                 float post_div, int L) {
@@ -680,7 +726,8 @@ struct Runner {
 };
 
 struct DecoderPlan {
-  size_t buf_floats;  // each of the 4 rotating stage buffers
+  size_t buf_floats;  // each of the rotating stage buffers (an operand image has the same byte size)
+  int n_bufs;         // 4 fp32 tensors + 3 operand images on the tcgen05 engine
 };
 
 DecoderPlan plan_decoder(const svk_handle* h, int B, int L) {
@@ -691,7 +738,7 @@ DecoderPlan plan_decoder(const svk_handle* h, int B, int L) {
     const size_t v = (size_t)h->stage_channels(i) * len;
     if (v > mx) mx = v;
   }
-  return DecoderPlan{align_up(mx * (size_t)B, 64)};
+  return DecoderPlan{align_up(mx * (size_t)B, 64), h->cfg.precision == SVK_PRECISION_TC ? 7 : 4};
 }
 
 // Generator.forward (models.py:141-160).  z rows have stride z_stride; in_mask (optional) fuses
@@ -701,6 +748,9 @@ void run_decoder(Runner& R, const float* z, int z_stride, const float* in_mask, 
   const svk_config& c = h->cfg;
   const DecoderPlan plan = plan_decoder(h, R.B, L);
   float* buf[4] = {ws, ws + plan.buf_floats, ws + 2 * plan.buf_floats, ws + 3 * plan.buf_floats};
+  uint16_t* img[3] = {nullptr, nullptr, nullptr};
+  if (plan.n_bufs == 7)
+    for (int i = 0; i < 3; ++i) img[i] = reinterpret_cast<uint16_t*>(ws + (4 + i) * plan.buf_floats);
   const int U = c.upsample_initial_channel;
   {
     ConvArgs a = R.base(h->conv_pre, z, c.inter_channels, 0, z_stride, L, 1, 3, L, L);
@@ -733,9 +783,15 @@ void run_decoder(Runner& R, const float* z, int z_stride, const float* in_mask, 
     }
     // xs = sum_j resblock_j(x); x = xs / num_kernels (models.py:150-155)
     const int nk = c.n_resblock_kernels;
+    bool images = img[0] != nullptr;
+    for (int j = 0; j < nk; ++j) images = images && R.resblock_uses_images(h->resblocks[i * nk + j]);
+    if (images) R.note(launch_split_image(X, R.B, C, Lout, 0.1f, img[0], R.stream));  // shared by the nk blocks
     for (int j = 0; j < nk; ++j) {
       const ResBlock& rb = h->resblocks[i * nk + j];
-      R.resblock(rb, X, XT, CUR, XS, j ? XS : nullptr, j == nk - 1 ? (float)nk : 1.0f, Lout);
+      const float* acc = j ? XS : nullptr;
+      const float div = j == nk - 1 ? (float)nk : 1.0f;
+      if (images) R.resblock_images(rb, X, img[0], img[1], CUR, img[2], XS, acc, div, Lout);
+      else R.resblock(rb, X, XT, CUR, XS, acc, div, Lout);
     }
     prev = XS, prevC = C, len = Lout;
   }
@@ -768,7 +824,10 @@ InferPlan plan_infer(const svk_handle* h, int B, int T, int max_len) {
   p.acts = take((size_t)B * c.hidden_channels * T);
   p.out = take((size_t)B * c.hidden_channels * T);
   for (int i = 0; i < 4; ++i) p.lat[i] = take((size_t)B * c.inter_channels * T);
-  p.dec = take(4 * plan_decoder(h, B, Tp).buf_floats);
+  {
+    const DecoderPlan dp = plan_decoder(h, B, Tp);
+    p.dec = take(dp.n_bufs * dp.buf_floats);
+  }
   p.total = off;
   return p;
 }
@@ -1001,7 +1060,8 @@ extern "C" int svk_generator(svk_handle* h, const float* z, int B, int L, float*
                              size_t workspace_bytes, void* stream) {
   SVK_TRY(check_ready(h, "svk_generator"));
   if (!z || !o || B <= 0 || L <= 0) return fail(SVK_ERR_INVALID, "svk_generator: bad argument");
-  const size_t need = 4 * plan_decoder(h, B, L).buf_floats * sizeof(float);
+  const DecoderPlan dplan = plan_decoder(h, B, L);
+  const size_t need = dplan.n_bufs * dplan.buf_floats * sizeof(float);
   if (!workspace || workspace_bytes < need) return fail(SVK_ERR_WORKSPACE, "svk_generator: workspace %zu < %zu", workspace_bytes, need);
   CUDA_TRY(cudaSetDevice(h->device));
   h->launches = 0;
@@ -1011,6 +1071,11 @@ extern "C" int svk_generator(svk_handle* h, const float* z, int B, int L, float*
   return SVK_OK;
 }
 
+extern "C" size_t svk_resblock1_workspace_bytes(const svk_handle* h, int index, int B, int L) {
+  if (!h || index < 0 || index >= (int)h->resblocks.size() || B <= 0 || L <= 0) return 0;
+  return 4 * align_up((size_t)B * h->resblocks[index].C * L, 64) * sizeof(float);
+}
+
 extern "C" int svk_resblock1(svk_handle* h, int index, const float* x, int B, int L, float* y, void* workspace,
                              size_t workspace_bytes, void* stream) {
   SVK_TRY(check_ready(h, "svk_resblock1"));
@@ -1018,12 +1083,21 @@ extern "C" int svk_resblock1(svk_handle* h, int index, const float* x, int B, in
   if (!x || !y || B <= 0 || L <= 0) return fail(SVK_ERR_INVALID, "svk_resblock1: bad argument");
   const ResBlock& rb = h->resblocks[index];
   const size_t n = align_up((size_t)B * rb.C * L, 64);
-  if (!workspace || workspace_bytes < 2 * n * sizeof(float)) return fail(SVK_ERR_WORKSPACE, "svk_resblock1: workspace too small");
+  if (!workspace || workspace_bytes < 4 * n * sizeof(float))
+    return fail(SVK_ERR_WORKSPACE, "svk_resblock1: workspace %zu < %zu (svk_resblock1_workspace_bytes)", workspace_bytes,
+                4 * n * sizeof(float));
   CUDA_TRY(cudaSetDevice(h->device));
   float* ws = (float*)workspace;
   h->launches = 0;
   Runner R{h, (cudaStream_t)stream, B};
-  R.resblock(rb, x, ws, ws + n, y, nullptr, 1.0f, L);
+  if (R.resblock_uses_images(rb)) {
+    uint16_t* x_img = reinterpret_cast<uint16_t*>(ws + n);
+    R.note(launch_split_image(x, B, rb.C, L, 0.1f, x_img, R.stream));
+    R.resblock_images(rb, x, x_img, reinterpret_cast<uint16_t*>(ws + 2 * n), ws, reinterpret_cast<uint16_t*>(ws + 3 * n), y,
+                      nullptr, 1.0f, L);
+  } else {
+    R.resblock(rb, x, ws, ws + n, y, nullptr, 1.0f, L);
+  }
   if (R.err != cudaSuccess) return fail(SVK_ERR_CUDA, "svk_resblock1: %s", cudaGetErrorString(R.err));
   return SVK_OK;
 }

@@ -90,6 +90,7 @@ SIGNATURES = {
     "svk_mel_encoder": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "svk_flow_reverse": (_i, [_vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "svk_generator": (_i, [_vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
+    "svk_resblock1_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "svk_resblock1": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "svk_conv1d": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
     "svk_conv_transpose1d": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),

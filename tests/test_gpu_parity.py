@@ -260,7 +260,7 @@ def test_resblock_and_generator_vs_oracle(net, base_sd, base_dims):
         k = base_dims.resblock_kernel_sizes[idx % 3]
         ref = orc.resblock1(base_sd, f"dec.resblocks.{idx}", x, k, (1, 3, 5))
         xd, y = dev(x), torch.empty(2, C, L, device="cuda")
-        ws = torch.empty(2 * 2 * C * L * 4 + 1024, dtype=torch.uint8, device="cuda")
+        ws = torch.empty(rt.lib().svk_resblock1_workspace_bytes(net._handle.ptr, idx, 2, L), dtype=torch.uint8, device="cuda")
         rt.check(rt.lib().svk_resblock1(net._handle.ptr, idx, xd.data_ptr(), 2, L, y.data_ptr(), ws.data_ptr(),
                                         ws.numel(), torch.cuda.current_stream().cuda_stream))
         assert np.abs(_np(y) - ref).max() <= TOL, idx

@@ -21,6 +21,13 @@ run 1 256 256 7 3 520 128 cpu 1 1
 run 1 192 512 7 1 300 128 cpu 0 1
 run 2 96 192 1 1 9000 96 cpu 0 1
 run 1 192 96 1 1 500 96 cpu 1 1
+echo "== operand-image input (TMA) / output"
+run 1 32 32 3 3 200 32 cpu 0 1 t
+run 2 32 32 11 1 30000 32 cpu 1 1 ts
+run 2 64 64 7 5 20000 64 cpu 1 1 tsn
+run 3 128 128 11 5 10000 128 cpu 1 1 ts
+run 1 256 256 7 3 520 128 cpu 1 1 tsn
+run 2 96 192 1 1 9001 96 cpu 0 1 t
 fi
 if [ "$1" != "check" ]; then
 echo "== timing (ffma reference), decoder stage shapes at 16x1024 frames"
@@ -39,4 +46,14 @@ run 16 32 32 7 1 262144 32 ffma 1 3
 run 16 32 32 11 1 262144 32 ffma 1 3
 run 16 192 384 5 1 1024 128 ffma 0 3
 run 16 192 384 1 1 1024 128 ffma 1 3
+echo "== timing, operand-image path (t = TMA input, s = + image output, n = image only)"
+for f in t ts tsn; do
+run 16 256 256 11 5 8192 128 ffma 1 3 $f
+run 16 128 128 3 1 65536 128 ffma 1 3 $f
+run 16 128 128 11 1 65536 128 ffma 1 3 $f
+run 16 64 64 3 1 131072 64 ffma 1 3 $f
+run 16 64 64 11 1 131072 64 ffma 1 3 $f
+run 16 32 32 3 1 262144 32 ffma 1 3 $f
+run 16 32 32 11 1 262144 32 ffma 1 3 $f
+done
 fi

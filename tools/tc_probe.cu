@@ -1,7 +1,9 @@
 // Developer probe for the tcgen05 conv kernel (conv_tc.cu): runs one shape, compares against a CPU
 // fp64 reference (small shapes) or the FFMA kernel (large shapes), prints error statistics and time.
-//   tc_probe B Cin Cout K dil L N [ref=cpu|ffma] [res=0|1] [reps]
+//   tc_probe B Cin Cout K dil L N [ref=cpu|ffma] [res=0|1] [reps] [flags: t = TMA input from an operand image,
+//            s = also write + check the output operand image, n = with s: no fp32 output]
 // Built by tools/build_probe.sh; not part of the product.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -44,6 +46,9 @@ int main(int argc, char** argv) {
   const bool cpu_ref = argc > 8 ? !strcmp(argv[8], "cpu") : true;
   const int use_res = argc > 9 ? atoi(argv[9]) : 0;
   const int reps = argc > 10 ? atoi(argv[10]) : 3;
+  const char* flags = argc > 11 ? argv[11] : "";
+  const bool f_tma = strchr(flags, 't') != nullptr, f_split = strchr(flags, 's') != nullptr, f_noraw = strchr(flags, 'n') != nullptr;
+  const float out_slope = 0.25f;
   const int pad = (K - 1) * dil / 2;
   const float slope = 0.1f;
 
@@ -85,6 +90,18 @@ int main(int argc, char** argv) {
   a.e[0].y = dy, a.e[0].C = Cout, a.e[0].ch_sign = 1, a.e[1].ch_sign = 1;
   a.e[0].res = dres;
   ta.wtc = dimg, ta.unscale = 1.0f / scale, ta.N = N;
+  uint16_t *dximg = nullptr, *dyimg = nullptr;
+  if (f_tma) {
+    CK(cudaMalloc(&dximg, split_image_halves(B, Cin, L) * 2));
+    CK(launch_split_image(dx, B, Cin, L, slope, dximg, 0));
+    ta.x_split = dximg;
+  }
+  if (f_split) {
+    CK(cudaMalloc(&dyimg, split_image_halves(B, Cout, L) * 2));
+    CK(cudaMemset(dyimg, 0xFF, split_image_halves(B, Cout, L) * 2));
+    a.e[0].split = dyimg, a.e[0].split_slope = out_slope;
+    if (f_noraw) a.e[0].y = nullptr;
+  }
 
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
@@ -103,6 +120,21 @@ int main(int argc, char** argv) {
   }
   std::vector<float> hy(ny);
   CK(cudaMemcpy(hy.data(), dy, ny * 4, cudaMemcpyDeviceToHost));
+  std::vector<uint16_t> himgy;
+  if (f_split) {
+    himgy.resize(split_image_halves(B, Cout, L));
+    CK(cudaMemcpy(himgy.data(), dyimg, himgy.size() * 2, cudaMemcpyDeviceToHost));
+    if (f_noraw) {  // reconstruct y from the image for the comparison below (slope inverted)
+      for (int b = 0; b < B; ++b)
+        for (int o = 0; o < Cout; ++o)
+          for (int t = 0; t < L; ++t) {
+            const size_t cell = (((size_t)b * (Cout / 8) + o / 8) * L + t) * 8 + o % 8;
+            const float v = __half2float(*reinterpret_cast<const __half*>(&himgy[cell])) +
+                            __half2float(*reinterpret_cast<const __half*>(&himgy[(size_t)B * Cout * L + cell]));
+            hy[((size_t)b * Cout + o) * L + t] = v >= 0.f ? v : v / out_slope;
+          }
+    }
+  }
 
   // ---- reference
   std::vector<double> ref;
@@ -172,14 +204,30 @@ int main(int argc, char** argv) {
       if (first_bad == (size_t)-1) first_bad = i;
     }
   }
+  if (f_split && !f_noraw) {  // image must equal leaky_relu(y) to fp16x2 precision
+    double worst = 0;
+    for (int b = 0; b < B; ++b)
+      for (int o = 0; o < Cout; ++o)
+        for (int t = 0; t < L; ++t) {
+          const size_t cell = (((size_t)b * (Cout / 8) + o / 8) * L + t) * 8 + o % 8;
+          const float v = __half2float(*reinterpret_cast<const __half*>(&himgy[cell])) +
+                          __half2float(*reinterpret_cast<const __half*>(&himgy[(size_t)B * Cout * L + cell]));
+          const float y = hy[((size_t)b * Cout + o) * L + t];
+          const float want = y > 0.f ? y : y * out_slope;
+          const double d = fabs((double)v - want) / (4e-8 + 1e-6 * fabs(want));  // fp16 subnormal floor + 2^-20 relative
+          if (!(d <= worst)) worst = d;
+        }
+    printf("  [split image vs leaky_relu(y): worst err / tolerance %.3f]\n", worst);
+    if (!(worst < 1.0)) nbad++;
+  }
   const double flops = 2.0 * B * (double)L * Cout * Cin * K;
   int pna = 0, pnw = 0, pres = 0;
   size_t psmem = 0;
   conv_tc_plan(Cin, Cout, K, dil, N, &pna, &pnw, &pres, &psmem);
   printf("B=%d Cin=%d Cout=%d K=%d dil=%d L=%d N=%d na=%d nw=%d resident=%d smem=%zu res=%d ref=%s | maxabs %.3e rms %.3e (ref rms %.3e) "
-         "signed-rel-bias %.3e nan %zu bad %zu",
+         "signed-rel-bias %.3e nan %zu bad %zu flags=%s",
          B, Cin, Cout, K, dil, L, N, pna, pnw, pres, psmem, use_res, cpu_ref ? "cpu64" : "ffma", maxabs, sqrt(sumsq / ny),
-         sqrt(sumref2 / ny), bias_num / (bias_den + 1e-30), nnan, nbad);
+         sqrt(sumref2 / ny), bias_num / (bias_den + 1e-30), nnan, nbad, flags);
   printf(" | %.3f ms %.1f TFLOP/s(useful)", best, flops / best / 1e9);
   if (!cpu_ref) printf(" ffma %.3f ms", ffma_ms);
   printf("\n");
