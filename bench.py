@@ -137,6 +137,21 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def wait_started(self, timeout=8.0):
+        """nvidia-smi's start-up (driver attach) stalls kernel launches for a few 100 ms: let it finish and
+        deliver its first sample before the timed region begins."""
+        if self.proc is None:
+            return
+        t0 = time.time()
+        while time.time() - t0 < timeout:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    break
+            except OSError:
+                pass
+            time.sleep(0.05)
+        time.sleep(0.3)
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
@@ -256,6 +271,8 @@ def run_b200_arm(args):
             return ev0.elapsed_time(ev1), recs, out
 
         sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            sampler.wait_started()
         elapsed_ms, _, o = timed_pass(False)
         # the same K steps again with a CUDA-event pair around every launch (roofline numbers); kept out of
         # `value` because event pairs serialise the stream at every launch boundary

@@ -46,6 +46,7 @@ constexpr int KC = TC_KC;   // input channels per A chunk
 constexpr int KG = KC / 8;  // 16-byte k-groups per chunk
 constexpr int NA_MAX = 4;   // A ring depth limit (depth is 2 or 4: the two producer groups own alternate slots)
 constexpr int MAXNW = 16;   // weight ring depth limit
+constexpr int MAXACC = 8;   // accumulator ring depth limit (512 TMEM columns / 2N, power of two)
 #ifndef SVK_TC_PROD_WARPS
 #define SVK_TC_PROD_WARPS 8
 #endif
@@ -73,7 +74,7 @@ static_assert(EPI_WARPS % 4 == 0 && EPI_SPLIT >= 1, "a warp may only read TMEM l
 struct __align__(8) SmemHeader {
   uint64_t a_full[NA_MAX], a_empty[NA_MAX];
   uint64_t w_full[MAXNW], w_empty[MAXNW];
-  uint64_t acc_full[2], acc_empty[2];
+  uint64_t acc_full[MAXACC], acc_empty[MAXACC];
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -255,11 +256,12 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
   const int items = ta.items, ntiles_t = ta.ntiles_t;
   const int resident = ta.resident;
   const int n_my = (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int nacc = ta.nacc, nacc_shift = 31 - __clz(nacc);  // accumulator stages (power of two)
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < na; ++i) mbar_init(&hdr->a_full[i], kTma ? 1 : PROD_GROUP), mbar_init(&hdr->a_empty[i], 1);
     for (int i = 0; i < MAXNW; ++i) mbar_init(&hdr->w_full[i], 1), mbar_init(&hdr->w_empty[i], 1);
-    for (int i = 0; i < 2; ++i) mbar_init(&hdr->acc_full[i], 1), mbar_init(&hdr->acc_empty[i], kEpiThreads);
+    for (int i = 0; i < MAXACC; ++i) mbar_init(&hdr->acc_full[i], 1), mbar_init(&hdr->acc_empty[i], kEpiThreads);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(&hdr->tmem_base, ta.tmem_cols);
@@ -313,8 +315,8 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
       int ast = 0, wst = 0;
       uint32_t aph = 0, wph = 0;
       for (int i = 0; i < n_my; ++i) {
-        const int s = i & 1;
-        mbar_wait_u32(bar_acc_empty + 8u * s, ((uint32_t)(i >> 1) & 1u) ^ 1u);  // epilogue drained this stage
+        const int s = i & (nacc - 1);
+        mbar_wait_u32(bar_acc_empty + 8u * s, ((uint32_t)(i >> nacc_shift) & 1u) ^ 1u);  // epilogue drained this stage
         tc_fence_after();
         const uint32_t dmain = tmem + (uint32_t)(s * 2 * N), dcross = dmain + (uint32_t)N;
         const bool wait_w = !resident || i == 0;
@@ -498,7 +500,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
     }
 
     for (int i = 0; i < n_my; ++i) {
-      const int s = i & 1;
+      const int s = i & (nacc - 1);
       int ntile, b, tt;
       decode_item((int)blockIdx.x + i * (int)gridDim.x, ntiles_t, a.B, ntile, b, tt);
       const int t = tt * 128 + row;
@@ -507,7 +509,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
       const float* omask = a.out_mask ? a.out_mask + (size_t)b * a.mask_stride : nullptr;
       const float mv = omask ? omask[tl] : 1.0f;
       const int o_tile = ntile * N;
-      mbar_wait(&hdr->acc_full[s], (uint32_t)(i >> 1) & 1u);
+      mbar_wait(&hdr->acc_full[s], (uint32_t)(i >> nacc_shift) & 1u);
       tc_fence_after();
       const uint32_t tsub = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(s * 2 * N);
 
@@ -832,8 +834,11 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
   size_t smem = 0;
   conv_tc_plan(a.Cin, a.Cout, a.K, a.dil, ta.N, &ta.na, &ta.nw, &ta.resident, &smem);
   if (ta.nw < 2 && !ta.resident) return cudaErrorInvalidValue;
+  // accumulator ring: as many (main + cross) stages as fit the 512 TMEM columns, at least 2, power of two
+  ta.nacc = 2;
+  while (ta.nacc < MAXACC && 2 * ta.nacc * 2 * ta.N <= 512) ta.nacc *= 2;
   int cols = 32;
-  while (cols < 4 * ta.N) cols <<= 1;
+  while (cols < ta.nacc * 2 * ta.N) cols <<= 1;
   ta.tmem_cols = cols;
   ta.rows = conv_tc_rows(a.K, a.dil);
   ta.bias_bytes = (int)conv_tc_bias_bytes(a.Cout, ta.N);

@@ -77,7 +77,7 @@ struct ConvTcArgs {
   const uint16_t* x_split;  // non-null: input comes from this operand image (geometry [B, c.x_C, c.Lin]) by TMA;
                             // leaky_relu / mask were applied when it was written, c.x / pre_slope / in_mask unused
   // filled by launch_conv_tc:
-  int rows, tmem_cols, na, nw, resident, items, ntiles_t, bias_bytes, bias_count;
+  int rows, tmem_cols, na, nw, resident, items, ntiles_t, bias_bytes, bias_count, nacc;
 };
 int conv_tc_rows(int K, int dil);
 size_t conv_tc_packed_halves(int Cin, int Cout, int K, int N);

@@ -677,7 +677,8 @@ struct Runner {
   // operand images of leaky_relu(x, 0.1) (written by the producing epilogue, loaded by TMA); the fp32
   // tensors are kept only where the residual adds need them (modules.py:220).  x_img = image of x.
   void resblock_images(const ResBlock& rb, const float* x, const uint16_t* x_img, uint16_t* xt_img, float* cur,
-                       uint16_t* cur_img, float* dst, const float* acc_in, float post_div, int L) {
+                       uint16_t* cur_img, float* dst, const float* acc_in, float post_div, int L,
+                       uint16_t* dst_img = nullptr) {
     const int C = rb.C;
     for (int l = 0; l < SVK_RESBLOCK_PAIRS; ++l) {
       const float* src = l == 0 ? x : cur;
@@ -696,6 +697,7 @@ struct Runner {
         b.e[0].split = cur_img, b.e[0].split_slope = 0.1f;
       } else {
         b.e[0].y = dst, b.e[0].acc_in = acc_in, b.post_div = post_div;
+        b.e[0].split = dst_img, b.e[0].split_slope = 0.1f;  // next upsampler reads leaky_relu(x, 0.1) (models.py:147)
       }
       run(b, SVK_LAYER_RESBLOCK_CONV2, xt_img);
     }
@@ -752,10 +754,12 @@ void run_decoder(Runner& R, const float* z, int z_stride, const float* in_mask, 
   if (plan.n_bufs == 7)
     for (int i = 0; i < 3; ++i) img[i] = reinterpret_cast<uint16_t*>(ws + (4 + i) * plan.buf_floats);
   const int U = c.upsample_initial_channel;
+  const uint16_t* prev_img = nullptr;  // operand image of leaky_relu(prev, 0.1) when the producer wrote one
   {
     ConvArgs a = R.base(h->conv_pre, z, c.inter_channels, 0, z_stride, L, 1, 3, L, L);
     a.in_mask = in_mask, a.mask_stride = z_stride;
     a.e[0].y = buf[1], a.e[0].C = U;
+    if (img[0] && h->conv_pre.tc && h->ups[0].tc) a.e[0].split = img[0], a.e[0].split_slope = 0.1f, prev_img = img[0];
     R.run(a, SVK_LAYER_CONV_PRE);
   }
   const float* prev = buf[1];
@@ -779,7 +783,8 @@ void run_decoder(Runner& R, const float* z, int z_stride, const float* in_mask, 
       a.mode = MODE_SHUFFLE;
       a.shuf_s = up.s, a.shuf_p = up.p, a.shuf_Lout = Lout;
       a.e[0].y = X, a.e[0].C = C;
-      R.run(a, SVK_LAYER_UPSAMPLE);
+      R.run(a, SVK_LAYER_UPSAMPLE, up.tc ? prev_img : nullptr);
+      prev_img = nullptr;
     }
     // xs = sum_j resblock_j(x); x = xs / num_kernels (models.py:150-155)
     const int nk = c.n_resblock_kernels;
@@ -790,9 +795,12 @@ void run_decoder(Runner& R, const float* z, int z_stride, const float* in_mask, 
       const ResBlock& rb = h->resblocks[i * nk + j];
       const float* acc = j ? XS : nullptr;
       const float div = j == nk - 1 ? (float)nk : 1.0f;
-      if (images) R.resblock_images(rb, X, img[0], img[1], CUR, img[2], XS, acc, div, Lout);
+      // the last block's final epilogue also writes the next upsampler's operand image
+      uint16_t* next_img = (images && j == nk - 1 && i + 1 < c.n_upsamples && h->ups[i + 1].tc && C % 16 == 0) ? img[0] : nullptr;
+      if (images) R.resblock_images(rb, X, img[0], img[1], CUR, img[2], XS, acc, div, Lout, next_img);
       else R.resblock(rb, X, XT, CUR, XS, acc, div, Lout);
     }
+    if (images && i + 1 < c.n_upsamples && h->ups[i + 1].tc && C % 16 == 0) prev_img = img[0];
     prev = XS, prevC = C, len = Lout;
   }
   // tanh(conv_post(leaky_relu(x)))  -- default slope 0.01 (models.py:156-158)
