@@ -44,7 +44,7 @@ namespace {
 
 constexpr int KC = TC_KC;   // input channels per A chunk
 constexpr int KG = KC / 8;  // 16-byte k-groups per chunk
-constexpr int NA_MAX = 4;   // A ring depth limit (depth is 2 or 4: the two producer groups own alternate slots)
+constexpr int NA_MAX = 8;   // A ring depth limit (producer warps: 2 or 4, the groups own alternate slots; TMA: up to 8)
 constexpr int MAXNW = 16;   // weight ring depth limit
 constexpr int MAXACC = 8;   // accumulator ring depth limit (512 TMEM columns / 2N, power of two)
 #ifndef SVK_TC_PROD_WARPS
@@ -78,7 +78,7 @@ struct __align__(8) SmemHeader {
   uint32_t tmem_base;
   uint32_t pad;
 };
-constexpr int HEADER_BYTES = 512;
+constexpr int HEADER_BYTES = 640;
 static_assert(sizeof(SmemHeader) <= HEADER_BYTES, "header");
 
 // ---------------------------------------------------------------------------------- PTX wrappers
@@ -223,11 +223,16 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 // ------------------------------------------------------------------------------------- kernel
 // item -> (output-channel tile, utterance, time tile); consecutive items are adjacent time tiles of
 // one utterance and one channel tile, so a wave of CTAs shares weights and halos in L2.
-__device__ __forceinline__ void decode_item(int item, int ntiles_t, int B, int& nt, int& b, int& tt) {
-  tt = item % ntiles_t;
-  const int r = item / ntiles_t;
-  b = r % B;
-  nt = r / B;
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv& f) {
+  const uint32_t t = __umulhi(f.m, n);
+  return (t + ((n - t) >> f.sh1)) >> f.sh2;
+}
+__device__ __forceinline__ void decode_item(int item, const FastDiv& dt, const FastDiv& db, int& nt, int& b, int& tt) {
+  const uint32_t r = fast_div((uint32_t)item, dt);
+  tt = item - (int)(r * dt.d);
+  const uint32_t q = fast_div(r, db);
+  b = (int)(r - q * db.d);
+  nt = (int)q;
 }
 
 template <bool kTma>
@@ -261,7 +266,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < na; ++i) mbar_init(&hdr->a_full[i], kTma ? 1 : PROD_GROUP), mbar_init(&hdr->a_empty[i], 1);
     for (int i = 0; i < MAXNW; ++i) mbar_init(&hdr->w_full[i], 1), mbar_init(&hdr->w_empty[i], 1);
-    for (int i = 0; i < MAXACC; ++i) mbar_init(&hdr->acc_full[i], 1), mbar_init(&hdr->acc_empty[i], kEpiThreads);
+    for (int i = 0; i < MAXACC; ++i) mbar_init(&hdr->acc_full[i], 1), mbar_init(&hdr->acc_empty[i], kEpiThreads / ta.epi_groups);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(&hdr->tmem_base, ta.tmem_cols);
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
       for (int i = 0; i < n_my; ++i) {
         if (resident && i > 0) break;  // the whole image already sits in the ring
         int nt, b, tt;
-        decode_item((int)blockIdx.x + i * (int)gridDim.x, ntiles_t, a.B, nt, b, tt);
+        decode_item((int)blockIdx.x + i * (int)gridDim.x, ta.div_t, ta.div_b, nt, b, tt);
         const uint8_t* src = reinterpret_cast<const uint8_t*>(ta.wtc) + (size_t)nt * per_tile * w_stage;
         for (int it = 0; it < per_tile; ++it) {
           if (!resident) mbar_wait(&hdr->w_empty[st], ph ^ 1);
@@ -364,7 +369,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
         int q = 0;
         for (int i = 0; i < n_my && q < total_q; ++i) {
           int nt, b, tt;
-          decode_item((int)blockIdx.x + i * (int)gridDim.x, ntiles_t, a.B, nt, b, tt);
+          decode_item((int)blockIdx.x + i * (int)gridDim.x, ta.div_t, ta.div_b, nt, b, tt);
           const int t0 = tt * 128 - a.pad;
           for (int ch = 0; ch < nchunks; ++ch, ++q) {
             mbar_wait(&hdr->a_empty[as], ph ^ 1);
@@ -388,7 +393,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
       for (int q = g; q < total_q; q += PROD_GROUPS) {
         const int i = q / nchunks, ch = q - i * nchunks;
         int nt, b, tt;
-        decode_item((int)blockIdx.x + i * (int)gridDim.x, ntiles_t, a.B, nt, b, tt);
+        decode_item((int)blockIdx.x + i * (int)gridDim.x, ta.div_t, ta.div_b, nt, b, tt);
         const int t0 = tt * 128;
         const int as = q & (na - 1);
         mbar_wait(&hdr->a_empty[as], ((uint32_t)(q >> na_shift) & 1u) ^ 1u);
@@ -431,8 +436,14 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
     // use clamped (always valid) addresses so 16-32 of them are in flight per thread, the operands of
     // the NEXT chunk -- and of the next tile's first chunk -- are requested before the current chunk
     // is finished, and only the final store is predicated.
+    // Narrow layers (several accumulator stages available) instead give whole tiles to alternating warp
+    // groups, so the per-tile fixed latency (barrier wait, TMEM load, address set-up) of one group
+    // overlaps the other group's tile.
     const int q4 = warp & 3;
-    const int part = (warp - kFirstEpi) >> 2;
+    const int egroups = ta.epi_groups;                 // warp groups that take alternate tiles
+    const int esplit = kEpiSplit / egroups;            // warps of one lane quarter sharing a tile's columns
+    const int eq = (warp - kFirstEpi) >> 2;            // 0 .. kEpiSplit-1
+    const int egroup = eq % egroups, part = eq / egroups;
     const int row = q4 * 32 + lane;
     const float unscale = ta.unscale;
     const int mode = a.mode;
@@ -487,22 +498,22 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
       }
     };
 
-    const int nch = N >> 4, hc = (nch + kEpiSplit - 1) / kEpiSplit;
+    const int nch = N >> 4, hc = (nch + esplit - 1) / esplit;
     const int n_lo = part * hc * 16, n_hi = min(nch, (part + 1) * hc) * 16;  // STORE / SHUFFLE column range
     const bool have_cols = n_lo < n_hi;
 
     float r1[16];
-    if (mode == MODE_STORE && have_cols && n_my > 0) {
+    if (mode == MODE_STORE && have_cols && egroup < n_my) {
       int nt0, b0, tt0;
-      decode_item((int)blockIdx.x, ntiles_t, a.B, nt0, b0, tt0);
+      decode_item((int)blockIdx.x + egroup * (int)gridDim.x, ta.div_t, ta.div_b, nt0, b0, tt0);
       const int t = tt0 * 128 + row;
       load16(chunk_io(b0, nt0 * N + n_lo, t, min(t, a.Lout - 1)), r1);
     }
 
-    for (int i = 0; i < n_my; ++i) {
+    for (int i = egroup; i < n_my; i += egroups) {
       const int s = i & (nacc - 1);
       int ntile, b, tt;
-      decode_item((int)blockIdx.x + i * (int)gridDim.x, ntiles_t, a.B, ntile, b, tt);
+      decode_item((int)blockIdx.x + i * (int)gridDim.x, ta.div_t, ta.div_b, ntile, b, tt);
       const int t = tt * 128 + row;
       const bool tin = t < a.Lout;
       const int tl = min(t, a.Lout - 1);
@@ -522,9 +533,9 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
           bool have_next = true;
           if (n0 + 16 < n_hi) {
             load16(chunk_io(b, o_tile + n0 + 16, t, tl), p1);
-          } else if (i + 1 < n_my) {
+          } else if (i + egroups < n_my) {
             int nt2, b2, tt2;
-            decode_item((int)blockIdx.x + (i + 1) * (int)gridDim.x, ntiles_t, a.B, nt2, b2, tt2);
+            decode_item((int)blockIdx.x + (i + egroups) * (int)gridDim.x, ta.div_t, ta.div_b, nt2, b2, tt2);
             const int t2 = tt2 * 128 + row;
             load16(chunk_io(b2, nt2 * N + n_lo, t2, min(t2, a.Lout - 1)), p1);
           } else {
@@ -596,7 +607,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
         // columns [0, N/2) hold the tanh half, [N/2, N) the sigmoid half of channels
         // ntile*N/2 + [0, N/2) (commons.py:100-107); bias is in the same virtual order.
         const int hN = N >> 1;
-        const int npair = hN >> 4, hp = (npair + kEpiSplit - 1) / kEpiSplit;
+        const int npair = hN >> 4, hp = (npair + esplit - 1) / esplit;
         const int g_lo = part * hp * 16, g_hi = min(npair, (part + 1) * hp) * 16;
         const float* bptr = bias_s + o_tile;
         float* ybase = a.e[0].y + ((size_t)b * a.e[0].C + a.e[0].ch_off + ntile * hN) * a.y_stride + t;
@@ -765,7 +776,7 @@ void conv_tc_pack(const float* w_ock, int Cout, int Cin, int K, int N, float sca
 // 227 KB goes to the weight ring; `resident` when every (chunk, tap) stage of the layer fits at once.
 size_t conv_tc_bias_bytes(int Cout, int N) { return (((size_t)((Cout + N - 1) / N) * N * 4) + 127) & ~(size_t)127; }
 
-void conv_tc_plan(int Cin, int Cout, int K, int dil, int N, int* na, int* nw, int* resident, size_t* smem_bytes) {
+void conv_tc_plan(int Cin, int Cout, int K, int dil, int N, bool tma, int* na, int* nw, int* resident, size_t* smem_bytes) {
   const size_t fixed = HEADER_BYTES + conv_tc_bias_bytes(Cout, N);
   const size_t budget = 227 * 1024 - fixed;
   const size_t a_stage = (size_t)conv_tc_rows(K, dil) * 16 * KG * 2, w_stage = (size_t)N * 32 * KG;
@@ -776,6 +787,20 @@ void conv_tc_plan(int Cin, int Cout, int K, int dil, int N, int* na, int* nw, in
   if (W > MAXNW) W = MAXNW;
   int res = 0;
   if (ntiles_n == 1 && per_tile <= W) res = 1, W = per_tile;
+  if (tma) {
+    // TMA-fed A ring: the ring depth is the prefetch distance that hides HBM latency (no registers
+    // involved), so it takes whatever the weights leave: all stages when resident, else >= 6 weight stages
+    const int minW = res ? per_tile : (W < 6 ? W : 6);
+    int A2 = (int)((budget - (size_t)minW * w_stage) / a_stage);
+    if (A2 > NA_MAX) A2 = NA_MAX;
+    if (A2 > A) {
+      A = A2;
+      if (!res) {
+        W = (int)((budget - A * a_stage) / w_stage);
+        if (W > MAXNW) W = MAXNW;
+      }
+    }
+  }
   *na = A, *nw = W, *resident = res;
   *smem_bytes = fixed + A * a_stage + (size_t)W * w_stage;
 }
@@ -824,6 +849,17 @@ cudaError_t make_image_map(const uint16_t* img, int B, int C, int L, int rows, C
 
 }  // namespace
 
+static FastDiv make_fast_div(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  f.m = (uint32_t)((((1ull << l) - d) << 32) / d + 1);
+  f.sh1 = l < 1 ? l : 1;
+  f.sh2 = l > 0 ? l - 1 : 0;
+  return f;
+}
+
 cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
   ConvTcArgs ta = ta_in;
   const ConvArgs& a = ta.c;
@@ -832,11 +868,17 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
   if (a.mode == MODE_GATE && (ta.N % 32 != 0 || a.Cout % 2)) return cudaErrorInvalidValue;
   if (a.B <= 0 || a.Lout <= 0 || a.Cout <= 0) return cudaSuccess;
   size_t smem = 0;
-  conv_tc_plan(a.Cin, a.Cout, a.K, a.dil, ta.N, &ta.na, &ta.nw, &ta.resident, &smem);
+  conv_tc_plan(a.Cin, a.Cout, a.K, a.dil, ta.N, ta.x_split != nullptr, &ta.na, &ta.nw, &ta.resident, &smem);
   if (ta.nw < 2 && !ta.resident) return cudaErrorInvalidValue;
   // accumulator ring: as many (main + cross) stages as fit the 512 TMEM columns, at least 2, power of two
   ta.nacc = 2;
   while (ta.nacc < MAXACC && 2 * ta.nacc * 2 * ta.N <= 512) ta.nacc *= 2;
+  // epilogue warp groups that alternate tiles: only when each group can own >= 2 accumulator stages
+  {
+    const int quarters = (ta.x_split ? EPI_WARPS_TMA : EPI_WARPS) / 4;
+    ta.epi_groups = 1;
+    while (ta.epi_groups * 2 <= quarters && quarters % (ta.epi_groups * 2) == 0 && ta.nacc >= 4 * ta.epi_groups) ta.epi_groups *= 2;
+  }
   int cols = 32;
   while (cols < ta.nacc * 2 * ta.N) cols <<= 1;
   ta.tmem_cols = cols;
@@ -848,6 +890,7 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
   const long long items = (long long)ntiles_n * a.B * ta.ntiles_t;
   if (items > 0x7FFFFFFFLL / 8) return cudaErrorInvalidValue;
   ta.items = (int)items;
+  ta.div_t = make_fast_div((uint32_t)ta.ntiles_t), ta.div_b = make_fast_div((uint32_t)a.B);
   static int sm_count[64] = {0};
   static bool configured[64] = {false};
   int dev = 0;

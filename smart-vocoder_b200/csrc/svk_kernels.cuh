@@ -69,6 +69,11 @@ cudaError_t launch_conv_ffma(const ConvArgs& a, cudaStream_t stream);
 
 // ---- tcgen05 path (conv_tc.cu): same ConvArgs semantics, weights pre-split into fp16 hi/lo images.
 constexpr int TC_KC = 32;  // input channels per staged chunk (Cin must be a multiple)
+// Division by a launch-invariant divisor as multiply-high + shifts (Granlund-Montgomery, exact for all uint32).
+struct FastDiv {
+  uint32_t d, m, sh1, sh2;
+};
+
 struct ConvTcArgs {
   ConvArgs c;           // c.wp unused; c.bias = fp32 bias [Cout] (unscaled)
   const uint16_t* wtc;  // packed image, see conv_tc_pack
@@ -77,13 +82,14 @@ struct ConvTcArgs {
   const uint16_t* x_split;  // non-null: input comes from this operand image (geometry [B, c.x_C, c.Lin]) by TMA;
                             // leaky_relu / mask were applied when it was written, c.x / pre_slope / in_mask unused
   // filled by launch_conv_tc:
-  int rows, tmem_cols, na, nw, resident, items, ntiles_t, bias_bytes, bias_count, nacc;
+  int rows, tmem_cols, na, nw, resident, items, ntiles_t, bias_bytes, bias_count, nacc, epi_groups;
+  FastDiv div_t, div_b;  // by ntiles_t and by B (work-item decoding)
 };
 int conv_tc_rows(int K, int dil);
 size_t conv_tc_packed_halves(int Cin, int Cout, int K, int N);
 float conv_tc_weight_scale(const float* w, size_t n);
 void conv_tc_pack(const float* w_ock, int Cout, int Cin, int K, int N, float scale, uint16_t* out);
-void conv_tc_plan(int Cin, int Cout, int K, int dil, int N, int* na, int* nw, int* resident, size_t* smem_bytes);
+void conv_tc_plan(int Cin, int Cout, int K, int dil, int N, bool tma, int* na, int* nw, int* resident, size_t* smem_bytes);
 cudaError_t launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream);
 // fp32 [B, C, L] -> operand image of leaky_relu(x, slope) (C % 8 == 0); bytes = 4 * B * C * L
 cudaError_t launch_split_image(const float* x, int B, int C, int L, float slope, uint16_t* img, cudaStream_t stream);
