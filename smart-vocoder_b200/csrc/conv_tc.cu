@@ -502,12 +502,27 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
     const int n_lo = part * hc * 16, n_hi = min(nch, (part + 1) * hc) * 16;  // STORE / SHUFFLE column range
     const bool have_cols = n_lo < n_hi;
 
-    float r1[16];
-    if (mode == MODE_STORE && have_cols && egroup < n_my) {
-      int nt0, b0, tt0;
-      decode_item((int)blockIdx.x + egroup * (int)gridDim.x, ta.div_t, ta.div_b, nt0, b0, tt0);
-      const int t = tt0 * 128 + row;
-      load16(chunk_io(b0, nt0 * N + n_lo, t, min(t, a.Lout - 1)), r1);
+    // Residual / running-sum operands are requested TWO chunk-jobs ahead of their use (a job = one
+    // 16-column chunk of one tile of this warp): on narrow layers one job is much shorter than the
+    // HBM latency.  (la_i, la_n0) is the look-ahead cursor over this warp's job sequence.
+    float r1[16], r2[16];
+    int la_i = egroup, la_n0 = n_lo;
+    auto la_load = [&](float (&q)[16]) {
+      if (la_i < n_my) {
+        int nt2, b2, tt2;
+        decode_item((int)blockIdx.x + la_i * (int)gridDim.x, ta.div_t, ta.div_b, nt2, b2, tt2);
+        const int t2 = tt2 * 128 + row;
+        load16(chunk_io(b2, nt2 * N + la_n0, t2, min(t2, a.Lout - 1)), q);
+        la_n0 += 16;
+        if (la_n0 >= n_hi) la_n0 = n_lo, la_i += egroups;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) q[e] = 0.f;
+      }
+    };
+    if (mode == MODE_STORE && have_cols) {
+      la_load(r1);
+      la_load(r2);
     }
 
     for (int i = egroup; i < n_my; i += egroups) {
@@ -528,19 +543,9 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
         // y = ((acc/s + bias) + (res + acc_in)) / post_div * mask, tanh  (same element is read then
         // written by the same thread only, so in-place operation is safe)
         for (int n0 = n_lo; n0 < n_hi; n0 += 16) {
-          // request the operands of the next chunk (or of the next tile's first chunk)
+          // request the operands of the job after next
           float p1[16];
-          bool have_next = true;
-          if (n0 + 16 < n_hi) {
-            load16(chunk_io(b, o_tile + n0 + 16, t, tl), p1);
-          } else if (i + egroups < n_my) {
-            int nt2, b2, tt2;
-            decode_item((int)blockIdx.x + (i + egroups) * (int)gridDim.x, ta.div_t, ta.div_b, nt2, b2, tt2);
-            const int t2 = tt2 * 128 + row;
-            load16(chunk_io(b2, nt2 * N + n_lo, t2, min(t2, a.Lout - 1)), p1);
-          } else {
-            have_next = false;
-          }
+          la_load(p1);
 
           uint32_t m[16], c[16];
           tmem_ld16(tsub + (uint32_t)n0, m);
@@ -598,10 +603,8 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
             for (int e = 0; e < 16; ++e)
               if (tin && e < io_c.nvalid) io_c.y[e * io_c.step] = v[e];
           }
-          if (have_next) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) r1[e] = p1[e];
-          }
+          for (int e = 0; e < 16; ++e) r1[e] = r2[e], r2[e] = p1[e];
         }
       } else if (mode == MODE_GATE) {
         // columns [0, N/2) hold the tanh half, [N/2, N) the sigmoid half of channels

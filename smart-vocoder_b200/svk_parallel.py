@@ -31,32 +31,34 @@ def shard_bounds(n_utterances: int, world_size: int) -> List[Tuple[int, int]]:
 def _scatter(buf_local: torch.Tensor, chunks: Optional[Sequence[torch.Tensor]], src: int, group=None):
     """dist.scatter with uneven chunks emulated by point-to-point sends (NCCL grouped send/recv)."""
     rank = dist.get_rank(group)
+    ops = []
     if rank == src:
-        reqs = []
         for r, c in enumerate(chunks):
             if r == src:
                 buf_local.copy_(c)
             elif c.numel():
-                reqs.append(dist.isend(c.contiguous(), dst=r, group=group))
-        for q in reqs:
-            q.wait()
+                ops.append(dist.P2POp(dist.isend, c.contiguous(), r, group))
     elif buf_local.numel():
-        dist.recv(buf_local, src=src, group=group)
+        ops.append(dist.P2POp(dist.irecv, buf_local, src, group))
+    if ops:  # one batch = one NCCL group call (ncclGroupStart/End around the sends / the recv)
+        for q in dist.batch_isend_irecv(ops):
+            q.wait()
 
 
 def _gather(local: torch.Tensor, outs: Optional[Sequence[torch.Tensor]], dst: int, group=None):
     rank = dist.get_rank(group)
+    ops = []
     if rank == dst:
-        reqs = []
         for r, o in enumerate(outs):
             if r == dst:
                 o.copy_(local)
             elif o.numel():
-                reqs.append(dist.irecv(o, src=r, group=group))
-        for q in reqs:
-            q.wait()
+                ops.append(dist.P2POp(dist.irecv, o, r, group))
     elif local.numel():
-        dist.send(local.contiguous(), dst=dst, group=group)
+        ops.append(dist.P2POp(dist.isend, local.contiguous(), dst, group))
+    if ops:
+        for q in dist.batch_isend_irecv(ops):
+            q.wait()
 
 
 def sharded_infer(infer_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tensor], mel: Optional[torch.Tensor],
