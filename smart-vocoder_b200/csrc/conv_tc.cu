@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
         const int npair = hN >> 4, hp = (npair + esplit - 1) / esplit;
         const int g_lo = part * hp * 16, g_hi = min(npair, (part + 1) * hp) * 16;
         const float* bptr = bias_s + o_tile;
-        float* ybase = a.e[0].y + ((size_t)b * a.e[0].C + a.e[0].ch_off + ntile * hN) * a.y_stride + t;
+        float* ybase = a.e[0].y ? a.e[0].y + ((size_t)b * a.e[0].C + a.e[0].ch_off + ntile * hN) * a.y_stride + t : nullptr;
         for (int n0 = g_lo; n0 < g_hi; n0 += 16) {
           uint32_t m[16], c[16];
           float g[16];
@@ -640,9 +640,26 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
             g[4 * e4 + 3] *= sigmoidf_(fmaf(__uint_as_float(m[4 * e4 + 3]) + __uint_as_float(c[4 * e4 + 3]), unscale, q.w));
           }
           const int nval = max(0, min(16, (a.Cout >> 1) - (ntile * hN + n0)));
+          if (a.e[0].split && tin && nval == 16) {
+            // acts as the operand image of the res_skip conv (modules.py:169): no fp32 copy needed
+            uint16_t* sp = a.e[0].split + (((size_t)b * (a.e[0].C >> 3) + ((a.e[0].ch_off + ntile * hN + n0) >> 3)) * a.y_stride + t) * 8;
 #pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if (tin && e < nval) ybase[(size_t)(n0 + e) * a.y_stride] = g[e];
+            for (int g8 = 0; g8 < 2; ++g8) {
+              uint4 h, l;
+              split2(g[8 * g8 + 0], g[8 * g8 + 1], h.x, l.x);
+              split2(g[8 * g8 + 2], g[8 * g8 + 3], h.y, l.y);
+              split2(g[8 * g8 + 4], g[8 * g8 + 5], h.z, l.z);
+              split2(g[8 * g8 + 6], g[8 * g8 + 7], h.w, l.w);
+              *reinterpret_cast<uint4*>(sp) = h;
+              *reinterpret_cast<uint4*>(sp + sp_plane * (size_t)a.e[0].C) = l;
+              sp += (size_t)a.y_stride * 8;
+            }
+          }
+          if (ybase) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (tin && e < nval) ybase[(size_t)(n0 + e) * a.y_stride] = g[e];
+          }
         }
       } else {
         // MODE_SHUFFLE: virtual channel o' = co*s + r of time row q lands at y[co, s*q + r - p]
@@ -910,7 +927,8 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
   }
   const int grid = ta.items < sm_count[dev] ? ta.items : sm_count[dev];
   for (int sd = 0; sd < 2; ++sd)
-    if (a.e[sd].split && (a.mode != MODE_STORE || a.e[sd].ch_sign != 1 || a.e[sd].ch_off % 8 || a.e[sd].C % 8 || a.Cout % 16))
+    if (a.e[sd].split && (a.mode == MODE_SHUFFLE || a.e[sd].ch_sign != 1 || a.e[sd].ch_off % 8 || a.e[sd].C % 8 ||
+                          (a.mode == MODE_STORE ? a.Cout % 16 : a.Cout % 32)))
       return cudaErrorInvalidValue;
   CUtensorMap map;
   memset(&map, 0, sizeof(map));

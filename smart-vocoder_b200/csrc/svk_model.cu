@@ -644,25 +644,39 @@ struct Runner {
   }
 
   // modules.WN.forward, g=None (modules.py:148-176).  x is updated in place, result in `out`.
+  // With x_img / acts_img (tcgen05 engine) the convs read operand images by TMA: x_img must hold the image of
+  // the incoming x; every res_skip epilogue rewrites it together with x, the gate epilogue writes acts only
+  // as an image (nothing else reads it).
   void wn(const std::vector<PackedConv>& in, const std::vector<PackedConv>& rs, float* x, float* acts,
-          float* out, const float* mask, int T) {
+          float* out, const float* mask, int T, uint16_t* x_img = nullptr, uint16_t* acts_img = nullptr) {
     const int H = h->cfg.hidden_channels, n = (int)in.size(), k = h->cfg.wn_kernel;
+    bool images = x_img && acts_img && h->cfg.precision == SVK_PRECISION_TC && H % 32 == 0;
+    for (int i = 0; i < n && images; ++i) images = in[i].tc && rs[i].tc;
     for (int i = 0; i < n; ++i) {
       ConvArgs a = base(in[i], x, H, 0, T, T, 1, (k - 1) / 2, T, T);
       a.mode = MODE_GATE;
-      a.e[0].y = acts, a.e[0].C = H;
-      run(a, SVK_LAYER_WN_IN);
+      a.e[0].C = H;
+      if (images) a.e[0].y = nullptr, a.e[0].split = acts_img, a.e[0].split_slope = 1.0f;
+      else a.e[0].y = acts;
+      run(a, SVK_LAYER_WN_IN, images ? x_img : nullptr);
       ConvArgs r = base(rs[i], acts, H, 0, T, T, 1, 0, T, T);
       r.out_mask = mask, r.mask_stride = T;
       if (i < n - 1) {
         r.split = H;
         r.e[0].res = x, r.e[0].y = x, r.e[0].C = H, r.e[0].use_mask = 1;       // x = (x + res) * mask
+        if (images) r.e[0].split = x_img, r.e[0].split_slope = 1.0f;            // ... and its image for layer i+1
         r.e[1].acc_in = i ? out : nullptr, r.e[1].y = out, r.e[1].C = H;      // out += skip
       } else {
         r.e[0].acc_in = i ? out : nullptr, r.e[0].y = out, r.e[0].C = H, r.e[0].use_mask = 1;  // (out + rs) * mask
       }
-      run(r, SVK_LAYER_WN_RES_SKIP);
+      run(r, SVK_LAYER_WN_RES_SKIP, images ? acts_img : nullptr);
     }
+  }
+  bool wn_uses_images(const std::vector<PackedConv>& in, const std::vector<PackedConv>& rs) const {
+    if (h->cfg.precision != SVK_PRECISION_TC || h->cfg.hidden_channels % 32) return false;
+    for (size_t i = 0; i < in.size(); ++i)
+      if (!in[i].tc || !rs[i].tc) return false;
+    return true;
   }
 
   // True when every conv of the block runs on the tcgen05 engine with operand-image I/O.
@@ -814,7 +828,7 @@ void run_decoder(Runner& R, const float* z, int z_stride, const float* in_mask, 
 }
 
 struct InferPlan {
-  size_t mask, hbuf, acts, out, lat[4], dec, total;  // float offsets
+  size_t mask, hbuf, acts, out, ximg, aimg, lat[4], dec, total;  // float offsets (operand images: same bytes as fp32)
 };
 
 InferPlan plan_infer(const svk_handle* h, int B, int T, int max_len) {
@@ -831,6 +845,8 @@ InferPlan plan_infer(const svk_handle* h, int B, int T, int max_len) {
   p.hbuf = take((size_t)B * c.hidden_channels * T);
   p.acts = take((size_t)B * c.hidden_channels * T);
   p.out = take((size_t)B * c.hidden_channels * T);
+  p.ximg = take((size_t)B * c.hidden_channels * T);
+  p.aimg = take((size_t)B * c.hidden_channels * T);
   for (int i = 0; i < 4; ++i) p.lat[i] = take((size_t)B * c.inter_channels * T);
   {
     const DecoderPlan dp = plan_decoder(h, B, Tp);
@@ -847,7 +863,7 @@ int check_ready(const svk_handle* h, const char* who) {
 }
 
 void run_mel_encoder(Runner& R, const float* mel, const float* mask, int T, float* hbuf, float* acts, float* out,
-                     float* m, float* logs) {
+                     float* m, float* logs, uint16_t* x_img = nullptr, uint16_t* acts_img = nullptr) {
   svk_handle* h = R.h;
   const svk_config& c = h->cfg;
   const int H = c.hidden_channels, C = c.inter_channels;
@@ -856,7 +872,9 @@ void run_mel_encoder(Runner& R, const float* mel, const float* mask, int T, floa
   a.out_mask = mask, a.mask_stride = T;
   a.e[0].y = hbuf, a.e[0].C = H, a.e[0].use_mask = 1;
   R.run(a, SVK_LAYER_PRE_ENC);
-  R.wn(h->enc_in, h->enc_rs, hbuf, acts, out, mask, T);
+  const bool images = x_img && acts_img && R.wn_uses_images(h->enc_in, h->enc_rs);
+  if (images) R.note(launch_split_image(hbuf, R.B, H, T, 1.0f, x_img, R.stream));  // pre_enc runs on the FFMA kernel
+  R.wn(h->enc_in, h->enc_rs, hbuf, acts, out, mask, T, images ? x_img : nullptr, images ? acts_img : nullptr);
   // stats = proj(x) * x_mask; m, logs = split(stats) (models.py:44-46)
   ConvArgs p = R.base(h->proj, out, H, 0, T, T, 1, 0, T, T);
   p.out_mask = mask, p.mask_stride = T;
@@ -867,7 +885,8 @@ void run_mel_encoder(Runner& R, const float* mel, const float* mask, int T, floa
 }
 
 // ResidualCouplingBlock.forward(reverse=True) in place on z (models.py:77-79, modules.py:324-343).
-void run_flow_reverse(Runner& R, float* z, const float* mask, int T, float* hbuf, float* acts, float* out) {
+void run_flow_reverse(Runner& R, float* z, const float* mask, int T, float* hbuf, float* acts, float* out,
+                      uint16_t* x_img = nullptr, uint16_t* acts_img = nullptr) {
   svk_handle* h = R.h;
   const svk_config& c = h->cfg;
   const int H = c.hidden_channels, C = c.inter_channels, half = C / 2;
@@ -877,8 +896,11 @@ void run_flow_reverse(Runner& R, float* z, const float* mask, int T, float* hbuf
     ConvArgs a = R.base(L.pre, z, C, L.orient ? half : 0, T, T, 1, 0, T, T);
     a.out_mask = mask, a.mask_stride = T;
     a.e[0].y = hbuf, a.e[0].C = H, a.e[0].use_mask = 1;
+    const bool images = x_img && acts_img && R.wn_uses_images(L.in, L.rs);
+    if (images && L.pre.tc) a.e[0].split = x_img, a.e[0].split_slope = 1.0f;
     R.run(a, SVK_LAYER_FLOW_PRE);
-    R.wn(L.in, L.rs, hbuf, acts, out, mask, T);
+    if (images && !L.pre.tc) R.note(launch_split_image(hbuf, R.B, H, T, 1.0f, x_img, R.stream));
+    R.wn(L.in, L.rs, hbuf, acts, out, mask, T, images ? x_img : nullptr, images ? acts_img : nullptr);
     // x1 = (x1 - post(h) * mask) * mask, written over x1's storage channels
     ConvArgs p = R.base(L.post, out, H, 0, T, T, 1, 0, T, T);
     p.out_mask = mask, p.mask_stride = T;
@@ -959,10 +981,12 @@ extern "C" int svk_infer(svk_handle* h, const float* mel, const int64_t* lengths
   h->launches = 0;
   Runner R{h, (cudaStream_t)stream, B};
   R.note(launch_sequence_mask(lengths, B, T, mask, R.stream));
-  run_mel_encoder(R, mel, mask, T, ws + p.hbuf, ws + p.acts, ws + p.out, lat_m, lat_logs);
+  uint16_t* ximg = reinterpret_cast<uint16_t*>(ws + p.ximg);
+  uint16_t* aimg = reinterpret_cast<uint16_t*>(ws + p.aimg);
+  run_mel_encoder(R, mel, mask, T, ws + p.hbuf, ws + p.acts, ws + p.out, lat_m, lat_logs, ximg, aimg);
   // z_p = m_p + eps * exp(logs_p) * noise_scale (models.py:336)
   R.note(launch_sample(lat_m, lat_logs, eps, noise_scale, lat_zp, lat_z, (int64_t)B * c.inter_channels * T, R.stream));
-  run_flow_reverse(R, lat_z, mask, T, ws + p.hbuf, ws + p.acts, ws + p.out);
+  run_flow_reverse(R, lat_z, mask, T, ws + p.hbuf, ws + p.acts, ws + p.out, ximg, aimg);
   if (c.n_flows & 1) {  // odd number of Flips leaves storage reversed: materialise the last Flip
     float* tmp = ws + p.lat[1];
     R.note(launch_flip(lat_z, B, c.inter_channels, T, tmp, R.stream));
@@ -1031,13 +1055,14 @@ extern "C" int svk_mel_encoder(svk_handle* h, const float* mel, const int64_t* l
   if (!mel || !lengths || !x_out || !m || !logs || !mask || B <= 0 || T <= 0)
     return fail(SVK_ERR_INVALID, "svk_mel_encoder: bad argument");
   const size_t n = align_up((size_t)B * h->cfg.hidden_channels * T, 64);
-  if (!workspace || workspace_bytes < 2 * n * sizeof(float)) return fail(SVK_ERR_WORKSPACE, "svk_mel_encoder: workspace too small");
+  if (!workspace || workspace_bytes < 4 * n * sizeof(float)) return fail(SVK_ERR_WORKSPACE, "svk_mel_encoder: workspace too small");
   CUDA_TRY(cudaSetDevice(h->device));
   float* ws = (float*)workspace;
   h->launches = 0;
   Runner R{h, (cudaStream_t)stream, B};
   R.note(launch_sequence_mask(lengths, B, T, mask, R.stream));
-  run_mel_encoder(R, mel, mask, T, ws, ws + n, x_out, m, logs);
+  run_mel_encoder(R, mel, mask, T, ws, ws + n, x_out, m, logs, reinterpret_cast<uint16_t*>(ws + 2 * n),
+                  reinterpret_cast<uint16_t*>(ws + 3 * n));
   if (R.err != cudaSuccess) return fail(SVK_ERR_CUDA, "svk_mel_encoder: %s", cudaGetErrorString(R.err));
   return SVK_OK;
 }
@@ -1048,12 +1073,13 @@ extern "C" int svk_flow_reverse(svk_handle* h, float* z, const float* mask, int 
   if (!z || !mask || B <= 0 || T <= 0) return fail(SVK_ERR_INVALID, "svk_flow_reverse: bad argument");
   const svk_config& c = h->cfg;
   const size_t n = align_up((size_t)B * c.hidden_channels * T, 64), nl = align_up((size_t)B * c.inter_channels * T, 64);
-  if (!workspace || workspace_bytes < (3 * n + nl) * sizeof(float)) return fail(SVK_ERR_WORKSPACE, "svk_flow_reverse: workspace too small");
+  if (!workspace || workspace_bytes < (5 * n + nl) * sizeof(float)) return fail(SVK_ERR_WORKSPACE, "svk_flow_reverse: workspace too small");
   CUDA_TRY(cudaSetDevice(h->device));
   float* ws = (float*)workspace;
   h->launches = 0;
   Runner R{h, (cudaStream_t)stream, B};
-  run_flow_reverse(R, z, mask, T, ws, ws + n, ws + 2 * n);
+  run_flow_reverse(R, z, mask, T, ws, ws + n, ws + 2 * n, reinterpret_cast<uint16_t*>(ws + 3 * n + nl),
+                   reinterpret_cast<uint16_t*>(ws + 4 * n + nl));
   if (c.n_flows & 1) {
     float* tmp = ws + 3 * n;
     R.note(launch_flip(z, B, c.inter_channels, T, tmp, R.stream));
