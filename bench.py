@@ -236,7 +236,7 @@ def run_b200_arm(args):
     cfg = load_cfg()
     dims = W.dims_from_model_kwargs(513, **cfg["model"])
     net = SynthesizerTrn(513, cfg["train"]["segment_size"] // cfg["data"]["hop_length"], n_speakers=cfg["data"]["n_speakers"],
-                         **cfg["model"])
+                         engine=args.engine, **cfg["model"])
     net.load_state_dict({k: torch.from_numpy(v) for k, v in W.make_state_dict(dims, seed=1234).items()})
     net = net.cuda().eval()
 
@@ -418,10 +418,12 @@ def run_b200_arm(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": "bf16" if args.engine == "bf16" else "f32", "data": "synthetic",
         "rtf": (ms_per_step / 1e3) / (samples_per_step_rank / SAMPLE_RATE),
-        "config": {"workload": f"iitp_base.json full path (MelEncoder+flow^-1+Generator), {B}x80x{T} mel per GPU, fp32 "
-                               f"(BASELINE configs[2]{'; configs[4] sharding, weak' if world > 1 else ''})",
+        "config": {"workload": f"iitp_base.json full path (MelEncoder+flow^-1+Generator), {B}x80x{T} mel per GPU, "
+                               + ("bf16 operands / fp32 accumulate (BASELINE configs[3] arithmetic)" if args.engine == "bf16" else
+                                  f"fp32 (BASELINE configs[2]{'; configs[4] sharding, weak' if world > 1 else ''})"),
+                   "engine": args.engine,
                    "batch_per_gpu": B, "global_batch": B * world, "frames": T, "noise_scale": NOISE_SCALE,
                    "weights": "seeded recipe svk_weights.make_state_dict(seed=1234), random init (no checkpoint exists)",
                    "sharding": "utterances, no data-path collective" if world > 1 else "none",
@@ -471,6 +473,9 @@ def main():
     ap.add_argument("--frames", type=int, default=1024)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--engine", default="tc", choices=["tc", "fp32", "bf16"],
+                    help="tc = tcgen05 fp16x3 (fp32-class, the default and the headline), fp32 = FFMA, "
+                         "bf16 = BASELINE configs[3] arithmetic (use with --batch-per-gpu 64 --frames 512)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-profile", default=None, help="write the per-layer launch table (CUDA-event times) to this file")
     args = ap.parse_args()

@@ -49,6 +49,11 @@ extern "C" {
                                   allow it runs as a 3-product fp16 split (hi*hi + hi*lo + lo*hi,
                                   fp32 accumulate in TMEM) on tcgen05; the rest stays on FFMA.
                                   Meets the same 1e-4 bar as SVK_PRECISION_FP32.            */
+#define SVK_PRECISION_BF16 2   /* BASELINE configs[3]: bf16 operands (activations stored in HBM as bf16
+                                  operand images, weights bf16), ONE tcgen05 pass per conv, fp32
+                                  accumulate in TMEM, fp32 residual stream.  No reference counterpart
+                                  (the reference has no reduced-precision inference): not bound by the
+                                  1e-4 bar; tests state its tolerance (SNR vs the fp64 oracle).   */
 
 /*
  * Effective hyper-parameters of SynthesizerTrn.__init__ (reference models.py:266-314).

@@ -31,6 +31,7 @@
 // layer's whole weight image fits the ring, weights are loaded once and stay resident for every tile
 // of the CTA -- and the accumulator full/empty pair.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -220,6 +221,21 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// 8 fp32 -> 8 bf16 (round to nearest even), one 16 B row of a single-plane operand tile
+__device__ __forceinline__ uint4 pack_bf16x8(const float* v) {
+  uint4 r;
+  __nv_bfloat162 t;
+  t = __floats2bfloat162_rn(v[0], v[1]);
+  r.x = *reinterpret_cast<const uint32_t*>(&t);
+  t = __floats2bfloat162_rn(v[2], v[3]);
+  r.y = *reinterpret_cast<const uint32_t*>(&t);
+  t = __floats2bfloat162_rn(v[4], v[5]);
+  r.z = *reinterpret_cast<const uint32_t*>(&t);
+  t = __floats2bfloat162_rn(v[6], v[7]);
+  r.w = *reinterpret_cast<const uint32_t*>(&t);
+  return r;
+}
+
 // ------------------------------------------------------------------------------------- kernel
 // item -> (output-channel tile, utterance, time tile); consecutive items are adjacent time tiles of
 // one utterance and one channel tile, so a wave of CTAs shares weights and halos in L2.
@@ -249,10 +265,12 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
   const int N = ta.N, nw = ta.nw, na = ta.na;
   const int K = a.K, dil = a.dil;
   const int rows = ta.rows;                       // staged time rows per chunk (multiple of 8)
+  const int planes = ta.planes;                   // 2: fp16 hi + lo (fp32-class), 1: single bf16 pass
   const uint32_t a_plane = (uint32_t)rows * 16u;  // one k-group plane of A
-  const uint32_t a_stage = a_plane * KG * 2u;     // hi + lo
-  const uint32_t w_plane2 = (uint32_t)N * 32u;    // one k-group plane of B: N hi rows then N lo rows
+  const uint32_t a_stage = a_plane * KG * planes;  // hi (+ lo)
+  const uint32_t w_plane2 = (uint32_t)N * 16u * planes;  // one k-group plane of B: N hi rows (then N lo rows)
   const uint32_t w_stage = w_plane2 * KG;
+  const int acc_cols = planes * N;                // TMEM columns of one accumulator stage: main (+ cross)
   float* bias_s = reinterpret_cast<float*>(smem + HEADER_BYTES);  // [ntiles_n * N], staged once per CTA
   uint8_t* a_smem = smem + HEADER_BYTES + ta.bias_bytes;
   uint8_t* w_smem = a_smem + (size_t)na * a_stage;
@@ -303,7 +321,9 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
     // their low words (start address >> 4 | LBO) advance by 32-bit adds.
     {
       // f16 x f16 -> f32, both operands K-major, M = 128
-      const uint32_t idesc1 = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+      // (planes == 1: bf16 x bf16, a/b format fields = 1)
+      const uint32_t fmt = planes == 1 ? ((1u << 7) | (1u << 10)) : 0u;
+      const uint32_t idesc1 = (1u << 4) | fmt | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * N) >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t desc_hi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
       const uint32_t a_lo0 = ((smem_u32(a_smem) & 0x3FFFFu) >> 4) | ((a_plane >> 4) << 16);
@@ -323,7 +343,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
         const int s = i & (nacc - 1);
         mbar_wait_u32(bar_acc_empty + 8u * s, ((uint32_t)(i >> nacc_shift) & 1u) ^ 1u);  // epilogue drained this stage
         tc_fence_after();
-        const uint32_t dmain = tmem + (uint32_t)(s * 2 * N), dcross = dmain + (uint32_t)N;
+        const uint32_t dmain = tmem + (uint32_t)(s * acc_cols), dcross = dmain + (uint32_t)N;
         const bool wait_w = !resident || i == 0;
         uint32_t acc = 0;
         for (int ch = 0; ch < nchunks; ++ch) {
@@ -337,10 +357,15 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
             }
             if (leader) {
               const uint32_t bw = w_lo0 + (uint32_t)wst * w_stage16;
-              umma_f16_lo(dmain, ah, bw, desc_hi, idesc2, acc);  // [main | cross] (+)= xh . [wh | wl]
-              umma_f16_lo(dcross, ah + lo_plane16, bw, desc_hi, idesc1, 1u);  // cross += xl . wh
-              umma_f16_lo(dmain, ah + ks_a16, bw + ks_b16, desc_hi, idesc2, 1u);
-              umma_f16_lo(dcross, ah + ks_a16 + lo_plane16, bw + ks_b16, desc_hi, idesc1, 1u);
+              if (planes == 2) {
+                umma_f16_lo(dmain, ah, bw, desc_hi, idesc2, acc);  // [main | cross] (+)= xh . [wh | wl]
+                umma_f16_lo(dcross, ah + lo_plane16, bw, desc_hi, idesc1, 1u);  // cross += xl . wh
+                umma_f16_lo(dmain, ah + ks_a16, bw + ks_b16, desc_hi, idesc2, 1u);
+                umma_f16_lo(dcross, ah + ks_a16 + lo_plane16, bw + ks_b16, desc_hi, idesc1, 1u);
+              } else {
+                umma_f16_lo(dmain, ah, bw, desc_hi, idesc1, acc);  // main (+)= bf16(x) . bf16(w)
+                umma_f16_lo(dmain, ah + ks_a16, bw + ks_b16, desc_hi, idesc1, 1u);
+              }
               if (!resident) umma_commit_u32(bar_w_empty + 8u * wst);
             }
             acc = 1u;
@@ -414,15 +439,20 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
             qv = qv > 0.f ? qv : qv * slope;
             v[c] = mrow ? qv * mk : qv;
           }
-  #pragma unroll
-          for (int kg = 0; kg < KG; ++kg) {
-            uint4 h, l;
-            split2(v[kg * 8 + 0], v[kg * 8 + 1], h.x, l.x);
-            split2(v[kg * 8 + 2], v[kg * 8 + 3], h.y, l.y);
-            split2(v[kg * 8 + 4], v[kg * 8 + 5], h.z, l.z);
-            split2(v[kg * 8 + 6], v[kg * 8 + 7], h.w, l.w);
-            Ahi[kg * rows + r] = h;
-            Alo[kg * rows + r] = l;
+            if (planes == 2) {
+#pragma unroll
+            for (int kg = 0; kg < KG; ++kg) {
+              uint4 h, l;
+              split2(v[kg * 8 + 0], v[kg * 8 + 1], h.x, l.x);
+              split2(v[kg * 8 + 2], v[kg * 8 + 3], h.y, l.y);
+              split2(v[kg * 8 + 4], v[kg * 8 + 5], h.z, l.z);
+              split2(v[kg * 8 + 6], v[kg * 8 + 7], h.w, l.w);
+              Ahi[kg * rows + r] = h;
+              Alo[kg * rows + r] = l;
+            }
+          } else {
+#pragma unroll
+            for (int kg = 0; kg < KG; ++kg) Ahi[kg * rows + r] = pack_bf16x8(&v[kg * 8]);
           }
         }
         fence_proxy_async_smem();
@@ -537,7 +567,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
       const int o_tile = ntile * N;
       mbar_wait(&hdr->acc_full[s], (uint32_t)(i >> nacc_shift) & 1u);
       tc_fence_after();
-      const uint32_t tsub = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(s * 2 * N);
+      const uint32_t tsub = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(s * acc_cols);
 
       if (mode == MODE_STORE) {
         // y = ((acc/s + bias) + (res + acc_in)) / post_div * mask, tanh  (same element is read then
@@ -549,7 +579,12 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
 
           uint32_t m[16], c[16];
           tmem_ld16(tsub + (uint32_t)n0, m);
-          tmem_ld16(tsub + (uint32_t)(N + n0), c);
+          if (planes == 2) {
+            tmem_ld16(tsub + (uint32_t)(N + n0), c);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) c[e] = 0u;
+          }
           const float4* b4 = reinterpret_cast<const float4*>(bias_s + o_tile + n0);
           const ChunkIO io_c = chunk_io(b, o_tile + n0, t, tl);
           tmem_wait_ld();
@@ -582,13 +617,17 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
               float w8[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) w8[e] = v[8 * g8 + e] > 0.f ? v[8 * g8 + e] : v[8 * g8 + e] * io_c.sp_slope;
-              uint4 h, l;
-              split2(w8[0], w8[1], h.x, l.x);
-              split2(w8[2], w8[3], h.y, l.y);
-              split2(w8[4], w8[5], h.z, l.z);
-              split2(w8[6], w8[7], h.w, l.w);
-              *reinterpret_cast<uint4*>(sp) = h;
-              *reinterpret_cast<uint4*>(sp + sp_plane * (size_t)a.e[o_tile + n0 >= a.split ? 1 : 0].C) = l;
+              if (planes == 2) {
+                uint4 h, l;
+                split2(w8[0], w8[1], h.x, l.x);
+                split2(w8[2], w8[3], h.y, l.y);
+                split2(w8[4], w8[5], h.z, l.z);
+                split2(w8[6], w8[7], h.w, l.w);
+                *reinterpret_cast<uint4*>(sp) = h;
+                *reinterpret_cast<uint4*>(sp + sp_plane * (size_t)a.e[o_tile + n0 >= a.split ? 1 : 0].C) = l;
+              } else {
+                *reinterpret_cast<uint4*>(sp) = pack_bf16x8(w8);
+              }
               sp += (size_t)a.y_stride * 8;
             }
           }
@@ -618,7 +657,12 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
           uint32_t m[16], c[16];
           float g[16];
           tmem_ld16(tsub + (uint32_t)n0, m);
-          tmem_ld16(tsub + (uint32_t)(N + n0), c);
+          if (planes == 2) {
+            tmem_ld16(tsub + (uint32_t)(N + n0), c);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) c[e] = 0u;
+          }
           tmem_wait_ld();
 #pragma unroll
           for (int e4 = 0; e4 < 4; ++e4) {
@@ -629,7 +673,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
             g[4 * e4 + 3] = tanhf(fmaf(__uint_as_float(m[4 * e4 + 3]) + __uint_as_float(c[4 * e4 + 3]), unscale, q.w));
           }
           tmem_ld16(tsub + (uint32_t)(hN + n0), m);
-          tmem_ld16(tsub + (uint32_t)(N + hN + n0), c);
+          if (planes == 2) tmem_ld16(tsub + (uint32_t)(N + hN + n0), c);
           tmem_wait_ld();
 #pragma unroll
           for (int e4 = 0; e4 < 4; ++e4) {
@@ -645,13 +689,17 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
             uint16_t* sp = a.e[0].split + (((size_t)b * (a.e[0].C >> 3) + ((a.e[0].ch_off + ntile * hN + n0) >> 3)) * a.y_stride + t) * 8;
 #pragma unroll
             for (int g8 = 0; g8 < 2; ++g8) {
-              uint4 h, l;
-              split2(g[8 * g8 + 0], g[8 * g8 + 1], h.x, l.x);
-              split2(g[8 * g8 + 2], g[8 * g8 + 3], h.y, l.y);
-              split2(g[8 * g8 + 4], g[8 * g8 + 5], h.z, l.z);
-              split2(g[8 * g8 + 6], g[8 * g8 + 7], h.w, l.w);
-              *reinterpret_cast<uint4*>(sp) = h;
-              *reinterpret_cast<uint4*>(sp + sp_plane * (size_t)a.e[0].C) = l;
+              if (planes == 2) {
+                uint4 h, l;
+                split2(g[8 * g8 + 0], g[8 * g8 + 1], h.x, l.x);
+                split2(g[8 * g8 + 2], g[8 * g8 + 3], h.y, l.y);
+                split2(g[8 * g8 + 4], g[8 * g8 + 5], h.z, l.z);
+                split2(g[8 * g8 + 6], g[8 * g8 + 7], h.w, l.w);
+                *reinterpret_cast<uint4*>(sp) = h;
+                *reinterpret_cast<uint4*>(sp + sp_plane * (size_t)a.e[0].C) = l;
+              } else {
+                *reinterpret_cast<uint4*>(sp) = pack_bf16x8(&g[8 * g8]);
+              }
               sp += (size_t)a.y_stride * 8;
             }
           }
@@ -669,7 +717,12 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
         for (int n0 = n_lo; n0 < n_hi; n0 += 16) {
           uint32_t m[16], c[16];
           tmem_ld16(tsub + (uint32_t)n0, m);
-          tmem_ld16(tsub + (uint32_t)(N + n0), c);
+          if (planes == 2) {
+            tmem_ld16(tsub + (uint32_t)(N + n0), c);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) c[e] = 0u;
+          }
           const int o0 = o_tile + n0;
           float bv[16];
 #pragma unroll
@@ -727,7 +780,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
 // fp32 [B, C, L] -> operand image [hi|lo][B][C/8][L][8] of leaky_relu(x, slope): one thread = one
 // (channel group, time) cell: 8 coalesced channel-row reads, two 16 B stores.
 __global__ void __launch_bounds__(256) split_image_kernel(const float* __restrict__ x, int B, int C, int L, float slope,
-                                                          uint16_t* __restrict__ img) {
+                                                          uint16_t* __restrict__ img, int planes) {
   const int t = blockIdx.x * 256 + threadIdx.x;
   const int cg = blockIdx.y, b = blockIdx.z;
   if (t >= L) return;
@@ -738,12 +791,16 @@ __global__ void __launch_bounds__(256) split_image_kernel(const float* __restric
     const float q = __ldg(xr + (size_t)e * L);
     v[e] = q > 0.f ? q : q * slope;
   }
+  const size_t cell = (((size_t)b * (C >> 3) + cg) * L + t) * 8;
+  if (planes == 1) {
+    *reinterpret_cast<uint4*>(img + cell) = pack_bf16x8(v);
+    return;
+  }
   uint4 h, l;
   split2(v[0], v[1], h.x, l.x);
   split2(v[2], v[3], h.y, l.y);
   split2(v[4], v[5], h.z, l.z);
   split2(v[6], v[7], h.w, l.w);
-  const size_t cell = (((size_t)b * (C >> 3) + cg) * L + t) * 8;
   *reinterpret_cast<uint4*>(img + cell) = h;
   *reinterpret_cast<uint4*>(img + (size_t)B * C * L + cell) = l;
 }
@@ -753,9 +810,9 @@ __global__ void __launch_bounds__(256) split_image_kernel(const float* __restric
 // ------------------------------------------------------------------------------- host helpers
 int conv_tc_rows(int K, int dil) { return (128 + (K - 1) * dil + 7) & ~7; }
 
-size_t conv_tc_packed_halves(int Cin, int Cout, int K, int N) {
+size_t conv_tc_packed_halves(int Cin, int Cout, int K, int N, int planes) {
   const int ntiles = (Cout + N - 1) / N, nchunks = Cin / KC;
-  return (size_t)ntiles * nchunks * K * N * KC * 2;
+  return (size_t)ntiles * nchunks * K * N * KC * planes;
 }
 
 // Power-of-two scale that brings max|w| into [512, 1024): fp16 hi keeps 11 bits, lo another 11.
@@ -772,23 +829,29 @@ float conv_tc_weight_scale(const float* w, size_t n) {
 }
 
 // wv(o, c, j) is the logical fp32 weight; image = [ntile][chunk][tap][kgroup][hi n | lo n][8].
-void conv_tc_pack(const float* w_ock, int Cout, int Cin, int K, int N, float scale, uint16_t* out) {
+// planes == 1: the same image with a single bf16 plane (scale must be 1).
+void conv_tc_pack(const float* w_ock, int Cout, int Cin, int K, int N, float scale, uint16_t* out, int planes) {
   const int ntiles = (Cout + N - 1) / N, nchunks = Cin / KC;
   size_t idx = 0;
   for (int nt = 0; nt < ntiles; ++nt)
     for (int ch = 0; ch < nchunks; ++ch)
       for (int j = 0; j < K; ++j)
         for (int kg = 0; kg < KG; ++kg)
-          for (int part = 0; part < 2; ++part)
+          for (int part = 0; part < planes; ++part)
             for (int n = 0; n < N; ++n)
               for (int e = 0; e < 8; ++e) {
                 const int o = nt * N + n, c = ch * KC + kg * 8 + e;
                 float v = 0.f;
                 if (o < Cout) v = w_ock[((size_t)o * Cin + c) * K + j] * scale;
-                const __half h = __float2half_rn(v);
-                const __half l = __float2half_rn(v - __half2float(h));
-                const __half pick = part ? l : h;
-                out[idx++] = *reinterpret_cast<const uint16_t*>(&pick);
+                if (planes == 1) {
+                  const __nv_bfloat16 bv = __float2bfloat16_rn(v);
+                  out[idx++] = *reinterpret_cast<const uint16_t*>(&bv);
+                } else {
+                  const __half h = __float2half_rn(v);
+                  const __half l = __float2half_rn(v - __half2float(h));
+                  const __half pick = part ? l : h;
+                  out[idx++] = *reinterpret_cast<const uint16_t*>(&pick);
+                }
               }
 }
 
@@ -796,10 +859,11 @@ void conv_tc_pack(const float* w_ock, int Cout, int Cin, int K, int N, float sca
 // 227 KB goes to the weight ring; `resident` when every (chunk, tap) stage of the layer fits at once.
 size_t conv_tc_bias_bytes(int Cout, int N) { return (((size_t)((Cout + N - 1) / N) * N * 4) + 127) & ~(size_t)127; }
 
-void conv_tc_plan(int Cin, int Cout, int K, int dil, int N, bool tma, int* na, int* nw, int* resident, size_t* smem_bytes) {
+void conv_tc_plan(int Cin, int Cout, int K, int dil, int N, bool tma, int planes, int* na, int* nw, int* resident,
+                  size_t* smem_bytes) {
   const size_t fixed = HEADER_BYTES + conv_tc_bias_bytes(Cout, N);
   const size_t budget = 227 * 1024 - fixed;
-  const size_t a_stage = (size_t)conv_tc_rows(K, dil) * 16 * KG * 2, w_stage = (size_t)N * 32 * KG;
+  const size_t a_stage = (size_t)conv_tc_rows(K, dil) * 16 * KG * planes, w_stage = (size_t)N * 16 * planes * KG;
   const int per_tile = (Cin / KC) * K, ntiles_n = (Cout + N - 1) / N;
   int A = 4;
   if (A * a_stage + 2 * w_stage > budget) A = 2;
@@ -825,10 +889,11 @@ void conv_tc_plan(int Cin, int Cout, int K, int dil, int N, bool tma, int* na, i
   *smem_bytes = fixed + A * a_stage + (size_t)W * w_stage;
 }
 
-cudaError_t launch_split_image(const float* x, int B, int C, int L, float slope, uint16_t* img, cudaStream_t stream) {
-  if (C % 8 != 0) return cudaErrorInvalidValue;
+cudaError_t launch_split_image(const float* x, int B, int C, int L, float slope, uint16_t* img, int planes,
+                               cudaStream_t stream) {
+  if (C % 8 != 0 || (planes != 1 && planes != 2)) return cudaErrorInvalidValue;
   if (B <= 0 || C <= 0 || L <= 0) return cudaSuccess;
-  split_image_kernel<<<dim3((L + 255) / 256, C / 8, B), 256, 0, stream>>>(x, B, C, L, slope, img);
+  split_image_kernel<<<dim3((L + 255) / 256, C / 8, B), 256, 0, stream>>>(x, B, C, L, slope, img, planes);
   return cudaGetLastError();
 }
 
@@ -854,14 +919,14 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 // Operand image [hi|lo][B*C/8][L][8] fp16 as a 4-D tensor; box = (8, rows, 4 k-groups, hi+lo) = one A stage.
-cudaError_t make_image_map(const uint16_t* img, int B, int C, int L, int rows, CUtensorMap* map) {
+cudaError_t make_image_map(const uint16_t* img, int B, int C, int L, int rows, int planes, CUtensorMap* map) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return cudaErrorNotSupported;
-  const cuuint64_t dims[4] = {8, (cuuint64_t)L, (cuuint64_t)B * (C / 8), 2};
+  const cuuint64_t dims[4] = {8, (cuuint64_t)L, (cuuint64_t)B * (C / 8), (cuuint64_t)planes};
   const cuuint64_t strides[3] = {16, (cuuint64_t)L * 16, (cuuint64_t)B * (C / 8) * L * 16};
-  const cuuint32_t box[4] = {8, (cuuint32_t)rows, (cuuint32_t)KG, 2};
+  const cuuint32_t box[4] = {8, (cuuint32_t)rows, (cuuint32_t)KG, (cuuint32_t)planes};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<uint16_t*>(img), dims, strides, box, estr,
+  const CUresult r = fn(map, planes == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<uint16_t*>(img), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
@@ -888,11 +953,12 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
   if (a.mode == MODE_GATE && (ta.N % 32 != 0 || a.Cout % 2)) return cudaErrorInvalidValue;
   if (a.B <= 0 || a.Lout <= 0 || a.Cout <= 0) return cudaSuccess;
   size_t smem = 0;
-  conv_tc_plan(a.Cin, a.Cout, a.K, a.dil, ta.N, ta.x_split != nullptr, &ta.na, &ta.nw, &ta.resident, &smem);
+  if (ta.planes != 1) ta.planes = 2;
+  conv_tc_plan(a.Cin, a.Cout, a.K, a.dil, ta.N, ta.x_split != nullptr, ta.planes, &ta.na, &ta.nw, &ta.resident, &smem);
   if (ta.nw < 2 && !ta.resident) return cudaErrorInvalidValue;
   // accumulator ring: as many (main + cross) stages as fit the 512 TMEM columns, at least 2, power of two
   ta.nacc = 2;
-  while (ta.nacc < MAXACC && 2 * ta.nacc * 2 * ta.N <= 512) ta.nacc *= 2;
+  while (ta.nacc < MAXACC && 2 * ta.nacc * ta.planes * ta.N <= 512) ta.nacc *= 2;
   // epilogue warp groups that alternate tiles: only when each group can own >= 2 accumulator stages
   {
     const int quarters = (ta.x_split ? EPI_WARPS_TMA : EPI_WARPS) / 4;
@@ -900,7 +966,7 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
     while (ta.epi_groups * 2 <= quarters && quarters % (ta.epi_groups * 2) == 0 && ta.nacc >= 4 * ta.epi_groups) ta.epi_groups *= 2;
   }
   int cols = 32;
-  while (cols < ta.nacc * 2 * ta.N) cols <<= 1;
+  while (cols < ta.nacc * ta.planes * ta.N) cols <<= 1;
   ta.tmem_cols = cols;
   ta.rows = conv_tc_rows(a.K, a.dil);
   ta.bias_bytes = (int)conv_tc_bias_bytes(a.Cout, ta.N);
@@ -934,7 +1000,7 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
   memset(&map, 0, sizeof(map));
   if (ta.x_split) {
     if (a.x_C % 8 || a.x_ch_off % 8 || a.x_stride != a.Lin) return cudaErrorInvalidValue;
-    cudaError_t e = make_image_map(ta.x_split, a.B, a.x_C, a.Lin, ta.rows, &map);
+    cudaError_t e = make_image_map(ta.x_split, a.B, a.x_C, a.Lin, ta.rows, ta.planes, &map);
     if (e != cudaSuccess) return e;
     conv_tc_kernel<true><<<grid, THREADS_TMA, smem, stream>>>(ta, map);
   } else {

@@ -79,6 +79,7 @@ struct ConvTcArgs {
   const uint16_t* wtc;  // packed image, see conv_tc_pack
   float unscale;        // 1 / weight scale (power of two)
   int N;                // output channels per tile (multiple of 16, <= 128)
+  int planes;           // 2 (default when 0): fp16 hi/lo three-product scheme; 1: single bf16 pass, fp32 accumulate
   const uint16_t* x_split;  // non-null: input comes from this operand image (geometry [B, c.x_C, c.Lin]) by TMA;
                             // leaky_relu / mask were applied when it was written, c.x / pre_slope / in_mask unused
   // filled by launch_conv_tc:
@@ -86,14 +87,16 @@ struct ConvTcArgs {
   FastDiv div_t, div_b;  // by ntiles_t and by B (work-item decoding)
 };
 int conv_tc_rows(int K, int dil);
-size_t conv_tc_packed_halves(int Cin, int Cout, int K, int N);
+size_t conv_tc_packed_halves(int Cin, int Cout, int K, int N, int planes = 2);
 float conv_tc_weight_scale(const float* w, size_t n);
-void conv_tc_pack(const float* w_ock, int Cout, int Cin, int K, int N, float scale, uint16_t* out);
-void conv_tc_plan(int Cin, int Cout, int K, int dil, int N, bool tma, int* na, int* nw, int* resident, size_t* smem_bytes);
+void conv_tc_pack(const float* w_ock, int Cout, int Cin, int K, int N, float scale, uint16_t* out, int planes = 2);
+void conv_tc_plan(int Cin, int Cout, int K, int dil, int N, bool tma, int planes, int* na, int* nw, int* resident,
+                  size_t* smem_bytes);
 cudaError_t launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream);
 // fp32 [B, C, L] -> operand image of leaky_relu(x, slope) (C % 8 == 0); bytes = 4 * B * C * L
-cudaError_t launch_split_image(const float* x, int B, int C, int L, float slope, uint16_t* img, cudaStream_t stream);
-inline size_t split_image_halves(int B, int C, int L) { return (size_t)2 * B * C * L; }
+cudaError_t launch_split_image(const float* x, int B, int C, int L, float slope, uint16_t* img, int planes,
+                               cudaStream_t stream);
+inline size_t split_image_halves(int B, int C, int L, int planes = 2) { return (size_t)planes * B * C * L; }
 
 // elementwise / small kernels
 cudaError_t launch_sequence_mask(const int64_t* lengths, int B, int T, float* mask, cudaStream_t s);

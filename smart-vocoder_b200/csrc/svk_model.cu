@@ -123,6 +123,8 @@ struct svk_handle {
   void* host_dev = nullptr;
   size_t host_dev_bytes = 0;
 
+  bool tensor_engine() const { return cfg.precision == SVK_PRECISION_TC || cfg.precision == SVK_PRECISION_BF16; }
+  int planes() const { return cfg.precision == SVK_PRECISION_BF16 ? 1 : 2; }  // operand-image planes (conv_tc.cu)
   int hop() const {
     int h = 1;
     for (int i = 0; i < cfg.n_upsamples; ++i) h *= cfg.upsample_rates[i];
@@ -265,7 +267,7 @@ int tc_tile_n(int Cout, int granule) {
 template <class WF, class BF>
 void pack_tc(svk_handle* h, PackedConv* pc, WF wv, BF bv, int gate_half) {
   const int Cin = pc->Cin, Cout = pc->Cout, K = pc->K;
-  if (h->cfg.precision != SVK_PRECISION_TC || Cin % TC_KC != 0 || Cout < 16) return;
+  if (!h->tensor_engine() || Cin % TC_KC != 0 || Cout < 16) return;
   const int N = tc_tile_n(Cout, gate_half ? 32 : 16);
   const int ntiles = (Cout + N - 1) / N;
   const int CoutV = ntiles * N;
@@ -283,10 +285,11 @@ void pack_tc(svk_handle* h, PackedConv* pc, WF wv, BF bv, int gate_half) {
     for (int c = 0; c < Cin; ++c)
       for (int j = 0; j < K; ++j) w[((size_t)ov * Cin + c) * K + j] = wv(o, c, j);
   }
-  const float scale = conv_tc_weight_scale(w.data(), w.size());
+  const int planes = h->planes();
+  const float scale = planes == 2 ? conv_tc_weight_scale(w.data(), w.size()) : 1.0f;  // bf16 has fp32's range
   pc->tc_off = align_up(h->h_tcblob.size(), 64);
-  h->h_tcblob.resize(pc->tc_off + conv_tc_packed_halves(Cin, CoutV, K, N));
-  conv_tc_pack(w.data(), CoutV, Cin, K, N, scale, h->h_tcblob.data() + pc->tc_off);
+  h->h_tcblob.resize(pc->tc_off + conv_tc_packed_halves(Cin, CoutV, K, N, planes));
+  conv_tc_pack(w.data(), CoutV, Cin, K, N, scale, h->h_tcblob.data() + pc->tc_off, planes);
   pc->tc_b_off = align_up(h->h_blob.size(), 64);
   h->h_blob.resize(pc->tc_b_off + CoutV, 0.f);
   for (int ov = 0; ov < CoutV; ++ov) {
@@ -383,7 +386,7 @@ extern "C" int svk_create(const svk_config* cfg, int device, svk_handle** out) {
   if (c.n_upsamples < 1 || c.n_upsamples > SVK_MAX_UPSAMPLES) return fail(SVK_ERR_INVALID, "n_upsamples out of range");
   if (c.n_resblock_kernels < 1 || c.n_resblock_kernels > SVK_MAX_RESBLOCK_KERNELS)
     return fail(SVK_ERR_INVALID, "n_resblock_kernels out of range");
-  if (c.precision != SVK_PRECISION_FP32 && c.precision != SVK_PRECISION_TC)
+  if (c.precision != SVK_PRECISION_FP32 && c.precision != SVK_PRECISION_TC && c.precision != SVK_PRECISION_BF16)
     return fail(SVK_ERR_INVALID, "unsupported precision %d", c.precision);
   if (c.hidden_channels % 8 || c.inter_channels % 16 || c.n_mel % 8)
     return fail(SVK_ERR_INVALID, "n_mel, hidden_channels must be multiples of 8 and inter_channels of 16");
@@ -628,6 +631,7 @@ struct Runner {
       ta.wtc = h->d_tcblob + pc->tc_off;
       ta.unscale = pc->tc_unscale;
       ta.N = pc->tc_N;
+      ta.planes = h->planes();
       ta.x_split = x_split;
       err = launch_conv_tc(ta, stream);
     } else if (x_split) {
@@ -650,7 +654,7 @@ struct Runner {
   void wn(const std::vector<PackedConv>& in, const std::vector<PackedConv>& rs, float* x, float* acts,
           float* out, const float* mask, int T, uint16_t* x_img = nullptr, uint16_t* acts_img = nullptr) {
     const int H = h->cfg.hidden_channels, n = (int)in.size(), k = h->cfg.wn_kernel;
-    bool images = x_img && acts_img && h->cfg.precision == SVK_PRECISION_TC && H % 32 == 0;
+    bool images = x_img && acts_img && h->tensor_engine() && H % 32 == 0;
     for (int i = 0; i < n && images; ++i) images = in[i].tc && rs[i].tc;
     for (int i = 0; i < n; ++i) {
       ConvArgs a = base(in[i], x, H, 0, T, T, 1, (k - 1) / 2, T, T);
@@ -673,7 +677,7 @@ struct Runner {
     }
   }
   bool wn_uses_images(const std::vector<PackedConv>& in, const std::vector<PackedConv>& rs) const {
-    if (h->cfg.precision != SVK_PRECISION_TC || h->cfg.hidden_channels % 32) return false;
+    if (!h->tensor_engine() || h->cfg.hidden_channels % 32) return false;
     for (size_t i = 0; i < in.size(); ++i)
       if (!in[i].tc || !rs[i].tc) return false;
     return true;
@@ -681,7 +685,7 @@ struct Runner {
 
   // True when every conv of the block runs on the tcgen05 engine with operand-image I/O.
   bool resblock_uses_images(const ResBlock& rb) const {
-    if (h->cfg.precision != SVK_PRECISION_TC || rb.C % 16) return false;
+    if (!h->tensor_engine() || rb.C % 16) return false;
     for (int l = 0; l < SVK_RESBLOCK_PAIRS; ++l)
       if (!rb.c1[l].tc || !rb.c2[l].tc) return false;
     return true;
@@ -754,7 +758,7 @@ DecoderPlan plan_decoder(const svk_handle* h, int B, int L) {
     const size_t v = (size_t)h->stage_channels(i) * len;
     if (v > mx) mx = v;
   }
-  return DecoderPlan{align_up(mx * (size_t)B, 64), h->cfg.precision == SVK_PRECISION_TC ? 7 : 4};
+  return DecoderPlan{align_up(mx * (size_t)B, 64), h->tensor_engine() ? 7 : 4};
 }
 
 // Generator.forward (models.py:141-160).  z rows have stride z_stride; in_mask (optional) fuses
@@ -804,7 +808,7 @@ void run_decoder(Runner& R, const float* z, int z_stride, const float* in_mask, 
     const int nk = c.n_resblock_kernels;
     bool images = img[0] != nullptr;
     for (int j = 0; j < nk; ++j) images = images && R.resblock_uses_images(h->resblocks[i * nk + j]);
-    if (images) R.note(launch_split_image(X, R.B, C, Lout, 0.1f, img[0], R.stream));  // shared by the nk blocks
+    if (images) R.note(launch_split_image(X, R.B, C, Lout, 0.1f, img[0], h->planes(), R.stream));  // shared by the nk blocks
     for (int j = 0; j < nk; ++j) {
       const ResBlock& rb = h->resblocks[i * nk + j];
       const float* acc = j ? XS : nullptr;
@@ -873,7 +877,7 @@ void run_mel_encoder(Runner& R, const float* mel, const float* mask, int T, floa
   a.e[0].y = hbuf, a.e[0].C = H, a.e[0].use_mask = 1;
   R.run(a, SVK_LAYER_PRE_ENC);
   const bool images = x_img && acts_img && R.wn_uses_images(h->enc_in, h->enc_rs);
-  if (images) R.note(launch_split_image(hbuf, R.B, H, T, 1.0f, x_img, R.stream));  // pre_enc runs on the FFMA kernel
+  if (images) R.note(launch_split_image(hbuf, R.B, H, T, 1.0f, x_img, h->planes(), R.stream));  // pre_enc runs on the FFMA kernel
   R.wn(h->enc_in, h->enc_rs, hbuf, acts, out, mask, T, images ? x_img : nullptr, images ? acts_img : nullptr);
   // stats = proj(x) * x_mask; m, logs = split(stats) (models.py:44-46)
   ConvArgs p = R.base(h->proj, out, H, 0, T, T, 1, 0, T, T);
@@ -899,7 +903,7 @@ void run_flow_reverse(Runner& R, float* z, const float* mask, int T, float* hbuf
     const bool images = x_img && acts_img && R.wn_uses_images(L.in, L.rs);
     if (images && L.pre.tc) a.e[0].split = x_img, a.e[0].split_slope = 1.0f;
     R.run(a, SVK_LAYER_FLOW_PRE);
-    if (images && !L.pre.tc) R.note(launch_split_image(hbuf, R.B, H, T, 1.0f, x_img, R.stream));
+    if (images && !L.pre.tc) R.note(launch_split_image(hbuf, R.B, H, T, 1.0f, x_img, h->planes(), R.stream));
     R.wn(L.in, L.rs, hbuf, acts, out, mask, T, images ? x_img : nullptr, images ? acts_img : nullptr);
     // x1 = (x1 - post(h) * mask) * mask, written over x1's storage channels
     ConvArgs p = R.base(L.post, out, H, 0, T, T, 1, 0, T, T);
@@ -1126,7 +1130,7 @@ extern "C" int svk_resblock1(svk_handle* h, int index, const float* x, int B, in
   Runner R{h, (cudaStream_t)stream, B};
   if (R.resblock_uses_images(rb)) {
     uint16_t* x_img = reinterpret_cast<uint16_t*>(ws + n);
-    R.note(launch_split_image(x, B, rb.C, L, 0.1f, x_img, R.stream));
+    R.note(launch_split_image(x, B, rb.C, L, 0.1f, x_img, h->planes(), R.stream));
     R.resblock_images(rb, x, x_img, reinterpret_cast<uint16_t*>(ws + 2 * n), ws, reinterpret_cast<uint16_t*>(ws + 3 * n), y,
                       nullptr, 1.0f, L);
   } else {

@@ -27,7 +27,8 @@ SVK_RESBLOCK_PAIRS = 3
 
 PRECISION_FP32 = 0   # fp32 FFMA everywhere
 PRECISION_TC = 1     # tcgen05 3-product fp16 split (fp32-class results), the default engine
-PRECISIONS = {"fp32": PRECISION_FP32, "ffma": PRECISION_FP32, "tc": PRECISION_TC}
+PRECISION_BF16 = 2   # bf16 operand images + weights, one tcgen05 pass, fp32 accumulate (BASELINE configs[3])
+PRECISIONS = {"fp32": PRECISION_FP32, "ffma": PRECISION_FP32, "tc": PRECISION_TC, "bf16": PRECISION_BF16}
 
 
 class SvkError(RuntimeError):

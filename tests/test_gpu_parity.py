@@ -268,6 +268,27 @@ def test_resblock_and_generator_vs_oracle(net, base_sd, base_dims):
     assert np.abs(_np(net.dec(dev(z))) - orc.generator(base_sd, base_dims, z)).max() <= TOL
 
 
+# ------------------------------------------------------------------------ bf16 engine (BASELINE configs[3])
+def test_bf16_engine_against_oracle(base_cfg, base_sd):
+    """bf16 operands (activation images and weights), one tcgen05 pass, fp32 accumulate, fp32 residual stream.
+    The reference has no reduced-precision inference path, so the tolerance is ours to state:
+    waveform SNR >= 30 dB against the reference's fp64 output and max-abs <= 0.05 on a signal of amplitude ~0.9;
+    everything that is integer / indexing work stays bit-exact."""
+    from gpu_util import build_net
+    net16 = build_net(base_cfg["model"], base_sd, engine="bf16")
+    g = load_golden("infer_base_b2_t40")
+    o, mask, (z, z_p, m_p, logs_p) = _run_infer(net16, g)
+    assert np.array_equal(_np(mask), g["ref32_x_mask"])
+    ref = g["ref64_o"]
+    err = _np(o).astype(np.float64) - ref
+    snr = 10 * np.log10((ref ** 2).sum() / (err ** 2).sum())
+    print("bf16 engine: waveform SNR %.1f dB, max-abs %.3e (|ref| max %.3f); z max-abs %.3e" %
+          (snr, np.abs(err).max(), np.abs(ref).max(), np.abs(_np(z) - g["ref64_z"]).max()))
+    assert snr >= 30.0 and np.abs(err).max() <= 0.05
+    assert np.abs(_np(z) - g["ref64_z"]).max() <= 0.05
+    assert net16.last_launch_count() > 100
+
+
 # ------------------------------------------------------------------------ full-size properties
 def test_full_size_window_vs_oracle_and_batch_independence(net, base_sd, base_dims):
     """BASELINE config 3 shape (B=16, T=1024).  The path is convolutional with a receptive field of

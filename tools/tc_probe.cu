@@ -93,7 +93,7 @@ int main(int argc, char** argv) {
   uint16_t *dximg = nullptr, *dyimg = nullptr;
   if (f_tma) {
     CK(cudaMalloc(&dximg, split_image_halves(B, Cin, L) * 2));
-    CK(launch_split_image(dx, B, Cin, L, slope, dximg, 0));
+    CK(launch_split_image(dx, B, Cin, L, slope, dximg, 2, 0));
     ta.x_split = dximg;
   }
   if (f_split) {
@@ -223,7 +223,7 @@ int main(int argc, char** argv) {
   const double flops = 2.0 * B * (double)L * Cout * Cin * K;
   int pna = 0, pnw = 0, pres = 0;
   size_t psmem = 0;
-  conv_tc_plan(Cin, Cout, K, dil, N, f_tma, &pna, &pnw, &pres, &psmem);
+  conv_tc_plan(Cin, Cout, K, dil, N, f_tma, 2, &pna, &pnw, &pres, &psmem);
   printf("B=%d Cin=%d Cout=%d K=%d dil=%d L=%d N=%d na=%d nw=%d resident=%d smem=%zu res=%d ref=%s | maxabs %.3e rms %.3e (ref rms %.3e) "
          "signed-rel-bias %.3e nan %zu bad %zu flags=%s",
          B, Cin, Cout, K, dil, L, N, pna, pnw, pres, psmem, use_res, cpu_ref ? "cpu64" : "ffma", maxabs, sqrt(sumsq / ny),
