@@ -485,6 +485,9 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
       float* y;
       uint16_t* sp;  // operand-image position of (hi plane, first channel group of the chunk, row t), or null
       float sp_slope;
+      const uint16_t* rimg;  // residual image position (hi plane), or null
+      float r_inv;           // 1 / res_slope
+      size_t plane;          // halves between the hi and lo planes of the destination's images
       ptrdiff_t step;
       int um, nvalid;
     };
@@ -500,6 +503,9 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
       io.y = d.y ? d.y + off + t : nullptr;
       io.sp = d.split ? d.split + (((size_t)b * (d.C >> 3) + ((d.ch_off + rel0) >> 3)) * a.y_stride + t) * 8 : nullptr;
       io.sp_slope = d.split_slope;
+      io.rimg = d.res_img ? d.res_img + (((size_t)b * (d.C >> 3) + ((d.ch_off + rel0) >> 3)) * a.y_stride + tl) * 8 : nullptr;
+      io.r_inv = 1.0f / d.res_slope;
+      io.plane = sp_plane * (size_t)d.C;
       io.step = (ptrdiff_t)d.ch_sign * a.y_stride;
       io.um = d.use_mask;
       io.nvalid = max(0, min(16, a.Cout - o0));
@@ -507,7 +513,23 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
     };
     auto load16 = [&](const ChunkIO& io, float (&q)[16]) {
       if (io.nvalid == 16) {
-        if (io.res) {
+        if (io.rimg) {
+          // residual from its operand image: 4 x 16 B loads, r = hi + lo with the leaky_relu inverted
+#pragma unroll
+          for (int g8 = 0; g8 < 2; ++g8) {
+            const uint4 hq = *reinterpret_cast<const uint4*>(io.rimg + (size_t)g8 * a.y_stride * 8);
+            const uint4 lq = *reinterpret_cast<const uint4*>(io.rimg + (size_t)g8 * a.y_stride * 8 + io.plane);
+            const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w}, lw[4] = {lq.x, lq.y, lq.z, lq.w};
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) {
+              const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e2]));
+              const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e2]));
+              const float v0 = hf.x + lf.x, v1 = hf.y + lf.y;
+              q[8 * g8 + 2 * e2] = v0 >= 0.f ? v0 : v0 * io.r_inv;
+              q[8 * g8 + 2 * e2 + 1] = v1 >= 0.f ? v1 : v1 * io.r_inv;
+            }
+          }
+        } else if (io.res) {
 #pragma unroll
           for (int e = 0; e < 16; ++e) q[e] = io.res[e * io.step];
         } else {
@@ -959,11 +981,13 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
   // accumulator ring: as many (main + cross) stages as fit the 512 TMEM columns, at least 2, power of two
   ta.nacc = 2;
   while (ta.nacc < MAXACC && 2 * ta.nacc * ta.planes * ta.N <= 512) ta.nacc *= 2;
-  // epilogue warp groups that alternate tiles: only when each group can own >= 2 accumulator stages
+  // epilogue warp groups that alternate tiles: the largest divisor of the warps-per-quarter count that
+  // still leaves every group two accumulator stages (wide layers: one group, columns split instead)
   {
     const int quarters = (ta.x_split ? EPI_WARPS_TMA : EPI_WARPS) / 4;
     ta.epi_groups = 1;
-    while (ta.epi_groups * 2 <= quarters && quarters % (ta.epi_groups * 2) == 0 && ta.nacc >= 4 * ta.epi_groups) ta.epi_groups *= 2;
+    for (int g = 2; g <= quarters; ++g)
+      if (quarters % g == 0 && ta.nacc >= 2 * g && ta.nacc >= 4) ta.epi_groups = g;
   }
   int cols = 32;
   while (cols < ta.nacc * ta.planes * ta.N) cols <<= 1;
@@ -992,10 +1016,14 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
     configured[dev] = true;
   }
   const int grid = ta.items < sm_count[dev] ? ta.items : sm_count[dev];
-  for (int sd = 0; sd < 2; ++sd)
+  for (int sd = 0; sd < 2; ++sd) {
+    if (a.e[sd].res_img && (a.mode != MODE_STORE || ta.planes == 1 || a.e[sd].ch_sign != 1 || a.e[sd].ch_off % 8 || a.e[sd].C % 8 ||
+                            a.Cout % 16 || a.e[sd].res || !(a.e[sd].res_slope > 0.f)))
+      return cudaErrorInvalidValue;
     if (a.e[sd].split && (a.mode == MODE_SHUFFLE || a.e[sd].ch_sign != 1 || a.e[sd].ch_off % 8 || a.e[sd].C % 8 ||
                           (a.mode == MODE_STORE ? a.Cout % 16 : a.Cout % 32)))
       return cudaErrorInvalidValue;
+  }
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   if (ta.x_split) {

@@ -21,6 +21,11 @@ struct EpiDesc {
   // then be null when nothing reads the fp32 tensor.  Needs ch_sign == +1 and ch_off % 8 == 0.
   uint16_t* split;
   float split_slope;
+  // Optional residual taken from an operand image instead of `res` (hi/lo engine only): the image holds
+  // leaky_relu(r, res_slope) with the destination tensor's geometry; the epilogue inverts the leaky_relu
+  // (r = v >= 0 ? v : v / res_slope).  Lets a residual stream live in HBM as images only.
+  const uint16_t* res_img;
+  float res_slope;
 };
 
 enum ConvMode : int {

@@ -598,7 +598,9 @@ struct Runner {
       for (int s = 0; s < 2; ++s) {
         const double n_s = s == 0 ? (a.split < a.Cout ? a.split : a.Cout) : (a.split < a.Cout ? a.Cout - a.split : 0);
         const double per = 4.0 * B * (double)out_len * n_s;
-        bytes += per * ((a.e[s].y ? 1 : 0) + (a.e[s].split ? 1 : 0) + (a.e[s].res ? 1 : 0) + (a.e[s].acc_in ? 1 : 0));
+        const double img = h->planes() * 0.5;  // an operand image is 2 B per plane per element
+        bytes += per * ((a.e[s].y ? 1 : 0) + (a.e[s].split ? img : 0) + (a.e[s].res ? 1 : 0) + (a.e[s].res_img ? img : 0) +
+                        (a.e[s].acc_in ? 1 : 0));
       }
     }
     r.bytes = bytes;
@@ -622,7 +624,10 @@ struct Runner {
     const PackedConv* pc = cur;
     const bool use_tc = pc && pc->tc && a.wp == h->d_blob + pc->w_off;
     const bool open = prof_open(layer, a, cout_logical, out_len, macs);
-    if (open) h->prof_records.back().engine = use_tc ? 1 : 0;
+    if (open) {
+      h->prof_records.back().engine = use_tc ? 1 : 0;
+      if (x_split) h->prof_records.back().bytes -= (4.0 - 2.0 * h->planes()) * B * (double)a.Cin * a.Lin;  // image input
+    }
     if (use_tc) {
       ConvTcArgs ta;
       memset(&ta, 0, sizeof(ta));
@@ -709,9 +714,17 @@ struct Runner {
       run(a, SVK_LAYER_RESBLOCK_CONV1, src_img);
       ConvArgs b = base(rb.c2[l], nullptr, C, 0, L, L, 1, (rb.k - 1) / 2, L, L);
       b.pre_slope = 0.1f;
-      b.e[0].res = src, b.e[0].C = C;
+      b.e[0].C = C;
+      // x + xt (modules.py:220).  On the wide, tensor-bound layers of the hi/lo engine the residual stream
+      // between the pairs of a block lives in HBM as its operand image only: the epilogue rebuilds
+      // x = hi + lo (leaky_relu inverted, ~2^-22 relative) instead of reading a second, fp32 copy (measured:
+      // -7..-11 % on C >= 128, k >= 7; the narrow layers are bound by epilogue instruction latency and lose,
+      // so they keep the fp32 copy).  A block's input and output are always fp32.
+      const bool img_stream = h->planes() == 2 && (C >= 256 || (C >= 128 && rb.k >= 7));
+      if (l > 0 && img_stream) b.e[0].res_img = src_img, b.e[0].res_slope = 0.1f;
+      else b.e[0].res = src;
       if (l < SVK_RESBLOCK_PAIRS - 1) {
-        b.e[0].y = cur;
+        b.e[0].y = img_stream ? nullptr : cur;
         b.e[0].split = cur_img, b.e[0].split_slope = 0.1f;
       } else {
         b.e[0].y = dst, b.e[0].acc_in = acc_in, b.post_div = post_div;
