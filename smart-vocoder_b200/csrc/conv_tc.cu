@@ -8,10 +8,13 @@
 // PERSISTENT, warp-specialised kernel: one CTA per SM walks a static round-robin list of work items
 // (item = one [128 time steps] x [N output channels] tile of one utterance).
 //     M = time (128 rows per MMA), N = output channels, K = input channels x taps
-//     A = activations, K-major, NO swizzle:  A_s[hi|lo][kgroup(8 ch)][row = time][16 B]
-//         -> a conv tap is a ROW shift, i.e. a 16 B-granular change of the descriptor start
-//            address (SBO = 128 B makes 8-row groups contiguous, so any row offset is legal);
-//            one staged tile with a (K-1)*dil halo serves every tap -- no im2col, no re-staging.
+//     A = activations, K-major, 64 B-swizzled:  A_s[hi|lo][row = time][32 ch x 2 B], the four 16 B
+//         chunks of a row XOR-ed with address bits 7-8 (CU_TENSOR_MAP_SWIZZLE_64B / UMMA layout 4)
+//         -> a conv tap is a ROW shift = +64 B per row on the descriptor's start address.  The tensor
+//            core de-swizzles on absolute address bits (tools/swizzle_probe.cu: any row shift is exact
+//            with base offset 0), and 8 consecutive rows always hit 8 distinct bank groups, so a shifted
+//            tile reads at full rate (a no-swizzle tile loses 1.6x on every tap that is not a multiple
+//            of 8 rows).  One staged tile with a (K-1)*dil halo serves every tap: no im2col.
 //     B = weights per (32-channel chunk, tap), K-major, no swizzle: B_s[kgroup][hi n | lo n][16 B],
 //         pre-split/pre-packed at load time in exactly this image (one cp.async.bulk per stage).
 //         Because hi and lo rows are adjacent, ONE MMA with N' = 2N computes xh.wh into the main
@@ -161,13 +164,13 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 // Same MMA with descriptors given as (low word, shared high word): no 64-bit arithmetic per issue.
-__device__ __forceinline__ void umma_f16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
-                                            uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
-      "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit_u32(uint32_t bar_addr) {
@@ -266,13 +269,13 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
   const int K = a.K, dil = a.dil;
   const int rows = ta.rows;                       // staged time rows per chunk (multiple of 8)
   const int planes = ta.planes;                   // 2: fp16 hi + lo (fp32-class), 1: single bf16 pass
-  const uint32_t a_plane = (uint32_t)rows * 16u;  // one k-group plane of A
-  const uint32_t a_stage = a_plane * KG * planes;  // hi (+ lo)
+  const uint32_t a_plane = (uint32_t)rows * 64u;  // one plane of A: rows x (32 ch x 2 B), 64 B-swizzled
+  const uint32_t a_stage = a_plane * planes;       // hi (+ lo)
   const uint32_t w_plane2 = (uint32_t)N * 16u * planes;  // one k-group plane of B: N hi rows (then N lo rows)
   const uint32_t w_stage = w_plane2 * KG;
   const int acc_cols = planes * N;                // TMEM columns of one accumulator stage: main (+ cross)
   float* bias_s = reinterpret_cast<float*>(smem + HEADER_BYTES);  // [ntiles_n * N], staged once per CTA
-  uint8_t* a_smem = smem + HEADER_BYTES + ta.bias_bytes;
+  uint8_t* a_smem = smem + ta.a_off;  // 1024 B-aligned: the swizzle is a function of absolute address bits
   uint8_t* w_smem = a_smem + (size_t)na * a_stage;
   const int nchunks = a.Cin / KC;
   const int per_tile = nchunks * K;  // weight stages per item
@@ -325,13 +328,14 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
       const uint32_t fmt = planes == 1 ? ((1u << 7) | (1u << 10)) : 0u;
       const uint32_t idesc1 = (1u << 4) | fmt | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * N) >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t desc_hi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
-      const uint32_t a_lo0 = ((smem_u32(a_smem) & 0x3FFFFu) >> 4) | ((a_plane >> 4) << 16);
+      const uint32_t b_hi = (128u >> 4) | (1u << 14);                // B: no swizzle, SBO = 128 B, version 1
+      const uint32_t a_hi = (512u >> 4) | (1u << 14) | (4u << 29);   // A: SWIZZLE_64B, SBO = 8 rows x 64 B, base offset 0
+      const uint32_t a_lo0 = ((smem_u32(a_smem) & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t w_lo0 = ((smem_u32(w_smem) & 0x3FFFFu) >> 4) | ((w_plane2 >> 4) << 16);
       const uint32_t a_stage16 = a_stage >> 4, w_stage16 = w_stage >> 4;
-      const uint32_t lo_plane16 = (a_plane * KG) >> 4;  // hi planes -> lo planes of one A stage
-      const uint32_t ks_a16 = (2 * a_plane) >> 4, ks_b16 = (2 * w_plane2) >> 4;
-      const uint32_t dil16 = (uint32_t)dil;             // one tap = dil rows = dil * 16 B
+      const uint32_t lo_plane16 = a_plane >> 4;  // hi plane -> lo plane of one A stage
+      const uint32_t ks_a16 = 32u >> 4, ks_b16 = (2 * w_plane2) >> 4;  // next 16 channels: +32 B inside the A row
+      const uint32_t dil16 = (uint32_t)dil * 4u;        // one tap = dil rows = dil * 64 B
       const uint32_t bar_a_full = smem_u32(&hdr->a_full[0]), bar_a_empty = smem_u32(&hdr->a_empty[0]);
       const uint32_t bar_w_full = smem_u32(&hdr->w_full[0]), bar_w_empty = smem_u32(&hdr->w_empty[0]);
       const uint32_t bar_acc_full = smem_u32(&hdr->acc_full[0]), bar_acc_empty = smem_u32(&hdr->acc_empty[0]);
@@ -358,13 +362,13 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
             if (leader) {
               const uint32_t bw = w_lo0 + (uint32_t)wst * w_stage16;
               if (planes == 2) {
-                umma_f16_lo(dmain, ah, bw, desc_hi, idesc2, acc);  // [main | cross] (+)= xh . [wh | wl]
-                umma_f16_lo(dcross, ah + lo_plane16, bw, desc_hi, idesc1, 1u);  // cross += xl . wh
-                umma_f16_lo(dmain, ah + ks_a16, bw + ks_b16, desc_hi, idesc2, 1u);
-                umma_f16_lo(dcross, ah + ks_a16 + lo_plane16, bw + ks_b16, desc_hi, idesc1, 1u);
+                umma_f16_lo(dmain, ah, bw, a_hi, b_hi, idesc2, acc);  // [main | cross] (+)= xh . [wh | wl]
+                umma_f16_lo(dcross, ah + lo_plane16, bw, a_hi, b_hi, idesc1, 1u);  // cross += xl . wh
+                umma_f16_lo(dmain, ah + ks_a16, bw + ks_b16, a_hi, b_hi, idesc2, 1u);
+                umma_f16_lo(dcross, ah + ks_a16 + lo_plane16, bw + ks_b16, a_hi, b_hi, idesc1, 1u);
               } else {
-                umma_f16_lo(dmain, ah, bw, desc_hi, idesc1, acc);  // main (+)= bf16(x) . bf16(w)
-                umma_f16_lo(dmain, ah + ks_a16, bw + ks_b16, desc_hi, idesc1, 1u);
+                umma_f16_lo(dmain, ah, bw, a_hi, b_hi, idesc1, acc);  // main (+)= bf16(x) . bf16(w)
+                umma_f16_lo(dmain, ah + ks_a16, bw + ks_b16, a_hi, b_hi, idesc1, 1u);
               }
               if (!resident) umma_commit_u32(bar_w_empty + 8u * wst);
             }
@@ -382,13 +386,13 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
   } else if (warp < kFirstEpi) {
     if constexpr (kTma) {
       // ---------------------------------------------- activation loader: one TMA box per 32-channel chunk
-      // The source tensor is the fp16 operand image [hi|lo][B*C/8][L][8] written by the producing
-      // layer's epilogue (or split_image_kernel); box (8, rows, 4 k-groups, 2) lands exactly in the
-      // A stage layout.  Rows outside [0, L) are zero-filled by the TMA unit = the conv's zero padding
+      // The source tensor is the fp16 operand image [hi|lo][B*C/32][L][32] written by the producing
+      // layer's epilogue (or split_image_kernel); box (32 ch, rows, 1, planes) with the 64 B swizzle
+      // lands exactly in the A stage layout.  Rows outside [0, L) are zero-filled by the TMA unit = the conv's zero padding
       // (leaky_relu and mask were applied when the image was written).
       if (warp == 2 && lane == 0) {
         const int total_q = n_my * nchunks;
-        const int cg0 = a.x_ch_off >> 3, cgs = a.x_C >> 3;
+        const int cg0 = a.x_ch_off >> 5, cgs = a.x_C >> 5;
         int as = 0;
         uint32_t ph = 0;
         int q = 0;
@@ -399,7 +403,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
           for (int ch = 0; ch < nchunks; ++ch, ++q) {
             mbar_wait(&hdr->a_empty[as], ph ^ 1);
             mbar_arrive_expect_tx(&hdr->a_full[as], a_stage);
-            tma_load_4d(a_smem + (size_t)as * a_stage, &tmap, 0, t0, b * cgs + cg0 + ch * KG, 0, &hdr->a_full[as]);
+            tma_load_4d(a_smem + (size_t)as * a_stage, &tmap, 0, t0, b * cgs + cg0 + ch, 0, &hdr->a_full[as]);
             if (++as == na) as = 0, ph ^= 1;
           }
         }
@@ -422,7 +426,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
         const int t0 = tt * 128;
         const int as = q & (na - 1);
         mbar_wait(&hdr->a_empty[as], ((uint32_t)(q >> na_shift) & 1u) ^ 1u);
-        uint4* Ahi = reinterpret_cast<uint4*>(a_smem + (size_t)as * a_stage);
+        uint4* Ahi = reinterpret_cast<uint4*>(a_smem + (size_t)as * a_stage);  // row r = 4 x 16 B, chunk kg at kg ^ ((r >> 1) & 3)
         uint4* Alo = Ahi + KG * rows;
         const float* mrow = a.in_mask ? a.in_mask + (size_t)b * a.mask_stride : nullptr;
         const float* xb = a.x + ((size_t)b * a.x_C + a.x_ch_off + ch * KC) * a.x_stride;
@@ -439,7 +443,9 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
             qv = qv > 0.f ? qv : qv * slope;
             v[c] = mrow ? qv * mk : qv;
           }
-            if (planes == 2) {
+            // 64 B swizzle: chunk position = chunk ^ (address bits 7-8 of the row); both planes start 512 B-aligned
+          const int swz = (int)(((smem_u32(Ahi) + (uint32_t)r * 64u) >> 7) & 3u);
+          if (planes == 2) {
 #pragma unroll
             for (int kg = 0; kg < KG; ++kg) {
               uint4 h, l;
@@ -447,12 +453,12 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
               split2(v[kg * 8 + 2], v[kg * 8 + 3], h.y, l.y);
               split2(v[kg * 8 + 4], v[kg * 8 + 5], h.z, l.z);
               split2(v[kg * 8 + 6], v[kg * 8 + 7], h.w, l.w);
-              Ahi[kg * rows + r] = h;
-              Alo[kg * rows + r] = l;
+              Ahi[r * KG + (kg ^ swz)] = h;
+              Alo[r * KG + (kg ^ swz)] = l;
             }
           } else {
 #pragma unroll
-            for (int kg = 0; kg < KG; ++kg) Ahi[kg * rows + r] = pack_bf16x8(&v[kg * 8]);
+            for (int kg = 0; kg < KG; ++kg) Ahi[r * KG + (kg ^ swz)] = pack_bf16x8(&v[kg * 8]);
           }
         }
         fence_proxy_async_smem();
@@ -501,9 +507,11 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
       io.res = d.res ? d.res + off + tl : nullptr;
       io.acc = d.acc_in ? d.acc_in + off + tl : nullptr;
       io.y = d.y ? d.y + off + t : nullptr;
-      io.sp = d.split ? d.split + (((size_t)b * (d.C >> 3) + ((d.ch_off + rel0) >> 3)) * a.y_stride + t) * 8 : nullptr;
+      const int dch0 = d.ch_off + rel0;  // first destination channel of the chunk (multiple of 16 when images are used)
+      const size_t cell = (((size_t)b * (d.C >> 5) + (dch0 >> 5)) * a.y_stride) * 32 + (dch0 & 31);  // + t * 32
+      io.sp = d.split ? d.split + cell + (size_t)t * 32 : nullptr;
       io.sp_slope = d.split_slope;
-      io.rimg = d.res_img ? d.res_img + (((size_t)b * (d.C >> 3) + ((d.ch_off + rel0) >> 3)) * a.y_stride + tl) * 8 : nullptr;
+      io.rimg = d.res_img ? d.res_img + cell + (size_t)tl * 32 : nullptr;
       io.r_inv = 1.0f / d.res_slope;
       io.plane = sp_plane * (size_t)d.C;
       io.step = (ptrdiff_t)d.ch_sign * a.y_stride;
@@ -517,8 +525,8 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
           // residual from its operand image: 4 x 16 B loads, r = hi + lo with the leaky_relu inverted
 #pragma unroll
           for (int g8 = 0; g8 < 2; ++g8) {
-            const uint4 hq = *reinterpret_cast<const uint4*>(io.rimg + (size_t)g8 * a.y_stride * 8);
-            const uint4 lq = *reinterpret_cast<const uint4*>(io.rimg + (size_t)g8 * a.y_stride * 8 + io.plane);
+            const uint4 hq = *reinterpret_cast<const uint4*>(io.rimg + g8 * 8);
+            const uint4 lq = *reinterpret_cast<const uint4*>(io.rimg + g8 * 8 + io.plane);
             const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w}, lw[4] = {lq.x, lq.y, lq.z, lq.w};
 #pragma unroll
             for (int e2 = 0; e2 < 4; ++e2) {
@@ -650,7 +658,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
               } else {
                 *reinterpret_cast<uint4*>(sp) = pack_bf16x8(w8);
               }
-              sp += (size_t)a.y_stride * 8;
+              sp += 8;  // next 8 channels of the same 64 B image row
             }
           }
           if (!io_c.y) {
@@ -708,7 +716,8 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
           const int nval = max(0, min(16, (a.Cout >> 1) - (ntile * hN + n0)));
           if (a.e[0].split && tin && nval == 16) {
             // acts as the operand image of the res_skip conv (modules.py:169): no fp32 copy needed
-            uint16_t* sp = a.e[0].split + (((size_t)b * (a.e[0].C >> 3) + ((a.e[0].ch_off + ntile * hN + n0) >> 3)) * a.y_stride + t) * 8;
+            const int gch0 = a.e[0].ch_off + ntile * hN + n0;
+            uint16_t* sp = a.e[0].split + (((size_t)b * (a.e[0].C >> 5) + (gch0 >> 5)) * a.y_stride + t) * 32 + (gch0 & 31);
 #pragma unroll
             for (int g8 = 0; g8 < 2; ++g8) {
               if (planes == 2) {
@@ -722,7 +731,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
               } else {
                 *reinterpret_cast<uint4*>(sp) = pack_bf16x8(&g[8 * g8]);
               }
-              sp += (size_t)a.y_stride * 8;
+              sp += 8;
             }
           }
           if (ybase) {
@@ -799,32 +808,35 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
   if (warp == 0) tmem_dealloc(tmem, ta.tmem_cols);
 }
 
-// fp32 [B, C, L] -> operand image [hi|lo][B][C/8][L][8] of leaky_relu(x, slope): one thread = one
-// (channel group, time) cell: 8 coalesced channel-row reads, two 16 B stores.
+// fp32 [B, C, L] -> operand image [hi|lo][B][C/32][L][32] of leaky_relu(x, slope): one thread = one
+// (32-channel group, time) cell: 32 coalesced channel-row reads, one 64 B row per plane written.
 __global__ void __launch_bounds__(256) split_image_kernel(const float* __restrict__ x, int B, int C, int L, float slope,
                                                           uint16_t* __restrict__ img, int planes) {
   const int t = blockIdx.x * 256 + threadIdx.x;
   const int cg = blockIdx.y, b = blockIdx.z;
   if (t >= L) return;
-  const float* xr = x + ((size_t)b * C + cg * 8) * L + t;
-  float v[8];
+  const float* xr = x + ((size_t)b * C + cg * 32) * L + t;
+  float v[32];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
+  for (int e = 0; e < 32; ++e) {
     const float q = __ldg(xr + (size_t)e * L);
     v[e] = q > 0.f ? q : q * slope;
   }
-  const size_t cell = (((size_t)b * (C >> 3) + cg) * L + t) * 8;
-  if (planes == 1) {
-    *reinterpret_cast<uint4*>(img + cell) = pack_bf16x8(v);
-    return;
+  uint16_t* cell = img + (((size_t)b * (C >> 5) + cg) * L + t) * 32;
+#pragma unroll
+  for (int g8 = 0; g8 < 4; ++g8) {
+    if (planes == 1) {
+      *reinterpret_cast<uint4*>(cell + g8 * 8) = pack_bf16x8(&v[g8 * 8]);
+    } else {
+      uint4 h, l;
+      split2(v[g8 * 8 + 0], v[g8 * 8 + 1], h.x, l.x);
+      split2(v[g8 * 8 + 2], v[g8 * 8 + 3], h.y, l.y);
+      split2(v[g8 * 8 + 4], v[g8 * 8 + 5], h.z, l.z);
+      split2(v[g8 * 8 + 6], v[g8 * 8 + 7], h.w, l.w);
+      *reinterpret_cast<uint4*>(cell + g8 * 8) = h;
+      *reinterpret_cast<uint4*>(cell + (size_t)B * C * L + g8 * 8) = l;
+    }
   }
-  uint4 h, l;
-  split2(v[0], v[1], h.x, l.x);
-  split2(v[2], v[3], h.y, l.y);
-  split2(v[4], v[5], h.z, l.z);
-  split2(v[6], v[7], h.w, l.w);
-  *reinterpret_cast<uint4*>(img + cell) = h;
-  *reinterpret_cast<uint4*>(img + (size_t)B * C * L + cell) = l;
 }
 
 }  // namespace
@@ -883,7 +895,7 @@ size_t conv_tc_bias_bytes(int Cout, int N) { return (((size_t)((Cout + N - 1) / 
 
 void conv_tc_plan(int Cin, int Cout, int K, int dil, int N, bool tma, int planes, int* na, int* nw, int* resident,
                   size_t* smem_bytes) {
-  const size_t fixed = HEADER_BYTES + conv_tc_bias_bytes(Cout, N);
+  const size_t fixed = (HEADER_BYTES + conv_tc_bias_bytes(Cout, N) + 1023) & ~(size_t)1023;  // A ring starts 1024 B-aligned
   const size_t budget = 227 * 1024 - fixed;
   const size_t a_stage = (size_t)conv_tc_rows(K, dil) * 16 * KG * planes, w_stage = (size_t)N * 16 * planes * KG;
   const int per_tile = (Cin / KC) * K, ntiles_n = (Cout + N - 1) / N;
@@ -913,9 +925,9 @@ void conv_tc_plan(int Cin, int Cout, int K, int dil, int N, bool tma, int planes
 
 cudaError_t launch_split_image(const float* x, int B, int C, int L, float slope, uint16_t* img, int planes,
                                cudaStream_t stream) {
-  if (C % 8 != 0 || (planes != 1 && planes != 2)) return cudaErrorInvalidValue;
+  if (C % 32 != 0 || (planes != 1 && planes != 2)) return cudaErrorInvalidValue;
   if (B <= 0 || C <= 0 || L <= 0) return cudaSuccess;
-  split_image_kernel<<<dim3((L + 255) / 256, C / 8, B), 256, 0, stream>>>(x, B, C, L, slope, img, planes);
+  split_image_kernel<<<dim3((L + 255) / 256, C / 32, B), 256, 0, stream>>>(x, B, C, L, slope, img, planes);
   return cudaGetLastError();
 }
 
@@ -940,16 +952,16 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// Operand image [hi|lo][B*C/8][L][8] fp16 as a 4-D tensor; box = (8, rows, 4 k-groups, hi+lo) = one A stage.
+// Operand image [hi|lo][B*C/32][L][32] as a 4-D tensor; box = (32 ch, rows, 1, planes) = one A stage, 64 B swizzle.
 cudaError_t make_image_map(const uint16_t* img, int B, int C, int L, int rows, int planes, CUtensorMap* map) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return cudaErrorNotSupported;
-  const cuuint64_t dims[4] = {8, (cuuint64_t)L, (cuuint64_t)B * (C / 8), (cuuint64_t)planes};
-  const cuuint64_t strides[3] = {16, (cuuint64_t)L * 16, (cuuint64_t)B * (C / 8) * L * 16};
-  const cuuint32_t box[4] = {8, (cuuint32_t)rows, (cuuint32_t)KG, (cuuint32_t)planes};
+  const cuuint64_t dims[4] = {32, (cuuint64_t)L, (cuuint64_t)B * (C / 32), (cuuint64_t)planes};
+  const cuuint64_t strides[3] = {64, (cuuint64_t)L * 64, (cuuint64_t)B * (C / 32) * L * 64};
+  const cuuint32_t box[4] = {32, (cuuint32_t)rows, 1, (cuuint32_t)planes};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult r = fn(map, planes == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<uint16_t*>(img), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
@@ -994,6 +1006,7 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
   ta.tmem_cols = cols;
   ta.rows = conv_tc_rows(a.K, a.dil);
   ta.bias_bytes = (int)conv_tc_bias_bytes(a.Cout, ta.N);
+  ta.a_off = (HEADER_BYTES + ta.bias_bytes + 1023) & ~1023;
   ta.bias_count = ((a.Cout + ta.N - 1) / ta.N) * ta.N;
   ta.ntiles_t = (a.Lout + 127) / 128;
   const int ntiles_n = (a.Cout + ta.N - 1) / ta.N;
@@ -1017,17 +1030,17 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
   }
   const int grid = ta.items < sm_count[dev] ? ta.items : sm_count[dev];
   for (int sd = 0; sd < 2; ++sd) {
-    if (a.e[sd].res_img && (a.mode != MODE_STORE || ta.planes == 1 || a.e[sd].ch_sign != 1 || a.e[sd].ch_off % 8 || a.e[sd].C % 8 ||
+    if (a.e[sd].res_img && (a.mode != MODE_STORE || ta.planes == 1 || a.e[sd].ch_sign != 1 || a.e[sd].ch_off % 16 || a.e[sd].C % 32 ||
                             a.Cout % 16 || a.e[sd].res || !(a.e[sd].res_slope > 0.f)))
       return cudaErrorInvalidValue;
-    if (a.e[sd].split && (a.mode == MODE_SHUFFLE || a.e[sd].ch_sign != 1 || a.e[sd].ch_off % 8 || a.e[sd].C % 8 ||
+    if (a.e[sd].split && (a.mode == MODE_SHUFFLE || a.e[sd].ch_sign != 1 || a.e[sd].ch_off % 16 || a.e[sd].C % 32 ||
                           (a.mode == MODE_STORE ? a.Cout % 16 : a.Cout % 32)))
       return cudaErrorInvalidValue;
   }
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   if (ta.x_split) {
-    if (a.x_C % 8 || a.x_ch_off % 8 || a.x_stride != a.Lin) return cudaErrorInvalidValue;
+    if (a.x_C % 32 || a.x_ch_off % 32 || a.x_stride != a.Lin) return cudaErrorInvalidValue;
     cudaError_t e = make_image_map(ta.x_split, a.B, a.x_C, a.Lin, ta.rows, ta.planes, &map);
     if (e != cudaSuccess) return e;
     conv_tc_kernel<true><<<grid, THREADS_TMA, smem, stream>>>(ta, map);

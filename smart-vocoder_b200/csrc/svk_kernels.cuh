@@ -17,8 +17,8 @@ struct EpiDesc {
   int ch_sign;          // +1, or -1 to write channels in reversed order (folded Flip)
   int use_mask;         // multiply by out_mask[b, t]
   // Optional second output for the tcgen05 engine: leaky_relu(y, split_slope) as the fp16 hi/lo operand
-  // image [hi|lo][B][C/8][L = y_stride][8] that the consuming conv loads by TMA (conv_tc.cu).  `y` may
-  // then be null when nothing reads the fp32 tensor.  Needs ch_sign == +1 and ch_off % 8 == 0.
+  // image [hi|lo][B][C/32][L = y_stride][32] that the consuming conv loads by TMA (conv_tc.cu).  `y` may
+  // then be null when nothing reads the fp32 tensor.  Needs ch_sign == +1, ch_off % 16 == 0, C % 32 == 0.
   uint16_t* split;
   float split_slope;
   // Optional residual taken from an operand image instead of `res` (hi/lo engine only): the image holds
@@ -88,7 +88,7 @@ struct ConvTcArgs {
   const uint16_t* x_split;  // non-null: input comes from this operand image (geometry [B, c.x_C, c.Lin]) by TMA;
                             // leaky_relu / mask were applied when it was written, c.x / pre_slope / in_mask unused
   // filled by launch_conv_tc:
-  int rows, tmem_cols, na, nw, resident, items, ntiles_t, bias_bytes, bias_count, nacc, epi_groups;
+  int rows, tmem_cols, na, nw, resident, items, ntiles_t, bias_bytes, bias_count, nacc, epi_groups, a_off;
   FastDiv div_t, div_b;  // by ntiles_t and by B (work-item decoding)
 };
 int conv_tc_rows(int K, int dil);
@@ -98,7 +98,7 @@ void conv_tc_pack(const float* w_ock, int Cout, int Cin, int K, int N, float sca
 void conv_tc_plan(int Cin, int Cout, int K, int dil, int N, bool tma, int planes, int* na, int* nw, int* resident,
                   size_t* smem_bytes);
 cudaError_t launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream);
-// fp32 [B, C, L] -> operand image of leaky_relu(x, slope) (C % 8 == 0); bytes = 4 * B * C * L
+// fp32 [B, C, L] -> operand image of leaky_relu(x, slope) (C % 32 == 0); bytes = 2 * planes * B * C * L
 cudaError_t launch_split_image(const float* x, int B, int C, int L, float slope, uint16_t* img, int planes,
                                cudaStream_t stream);
 inline size_t split_image_halves(int B, int C, int L, int planes = 2) { return (size_t)planes * B * C * L; }

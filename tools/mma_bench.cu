@@ -54,12 +54,15 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
 __device__ __forceinline__ uint32_t idesc_f16(int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24); }
 
 enum Pattern { P_SAME128, P_SAME256, P_SHIFT128, P_PAIR_OVERLAP, P_TRIPLE_V1, P_ALT2, P_PAIR_DISJOINT, P_SAME64, P_SAME32,
-               P_SW128_128, P_SW128_256, P_PAIR_SMALL64, P_PAIR_SMALL32, P_GROUPED_PAIR, P_COUNT };
+               P_SW128_128, P_SW128_256, P_PAIR_SMALL64, P_PAIR_SMALL32, P_GROUPED_PAIR,
+               P_SW128_SHIFT128, P_SW64_SHIFT128, P_SW64_SHIFT64, P_SW64_SHIFT32, P_SW64_PAIR128, P_SW64_PAIR32, P_COUNT };
 static const char* kNames[] = {"same D, N=128", "same D, N=256", "same D, N=128, A row-shifted per MMA", "v2 pair: N=256->D0, N=128->D0+128 (overlap)",
                                "v1 triple: D1,D1,D0 (N=128)", "alternate D0,D1 (N=128)", "pair: N=256->D0, N=128->D256 (disjoint)",
                                "same D, N=64", "same D, N=32", "SW128 same D, N=128", "SW128 same D, N=256",
                                "v2 pair at N=64: N=128->D0, N=64->D0+64", "v2 pair at N=32: N=64->D0, N=32->D0+32",
-                               "v2 pair grouped: 8x(N=256->D0) then 8x(N=128->D0+128)"};
+                               "v2 pair grouped: 8x(N=256->D0) then 8x(N=128->D0+128)",
+                               "SW128 A row-shifted per MMA, N=128", "SW64 A row-shifted per MMA, N=128", "SW64 A row-shifted, N=64",
+                               "SW64 A row-shifted, N=32", "SW64 A row-shifted, v2 pair N=256/128", "SW64 A row-shifted, v2 pair N=64/32"};
 
 // One MMA of pattern P at iteration `it` (all descriptor values are loop-invariant registers).
 template <int P>
@@ -97,6 +100,20 @@ __device__ __forceinline__ void issue(int it, uint32_t tmem, uint64_t dA, uint64
   if constexpr (P == P_ALT2) umma_f16(tmem + (it & 1) * 128, dA, dB, idesc_f16(128), it > 1);
   if constexpr (P == P_SW128_128) umma_f16(tmem, sA + (uint64_t)((it & 3) * 2), sB + (uint64_t)((it & 3) * 2), idesc_f16(128), acc);
   if constexpr (P == P_SW128_256) umma_f16(tmem, sA + (uint64_t)((it & 3) * 2), sB + (uint64_t)((it & 3) * 2), idesc_f16(256), acc);
+  // swizzled A (row shift = (it % 11) rows), B stays in the no-swizzle image like conv_tc.cu
+  if constexpr (P == P_SW128_SHIFT128) umma_f16(tmem, sA + (uint64_t)((it % 11) * 8 + (it & 3) * 2), dB, idesc_f16(128), acc);
+  const uint64_t s64 = (sA & ~(7ull << 61) & ~(0x3FFFull << 32)) | (4ull << 61) | ((uint64_t)(512 >> 4) << 32);
+  if constexpr (P == P_SW64_SHIFT128) umma_f16(tmem, s64 + (uint64_t)((it % 11) * 4 + (it & 1) * 2), dB, idesc_f16(128), acc);
+  if constexpr (P == P_SW64_SHIFT64) umma_f16(tmem, s64 + (uint64_t)((it % 11) * 4 + (it & 1) * 2), dB, idesc_f16(64), acc);
+  if constexpr (P == P_SW64_SHIFT32) umma_f16(tmem, s64 + (uint64_t)((it % 11) * 4 + (it & 1) * 2), dB, idesc_f16(32), acc);
+  if constexpr (P == P_SW64_PAIR128) {
+    if ((it & 1) == 0) umma_f16(tmem, s64 + (uint64_t)((it % 11) * 4), dB, idesc_f16(256), acc);
+    else umma_f16(tmem + 128, s64 + (uint64_t)(2048 + (it % 11) * 4), dB, idesc_f16(128), 1);
+  }
+  if constexpr (P == P_SW64_PAIR32) {
+    if ((it & 1) == 0) umma_f16(tmem, s64 + (uint64_t)((it % 11) * 4), dB, idesc_f16(64), acc);
+    else umma_f16(tmem + 32, s64 + (uint64_t)(2048 + (it % 11) * 4), dB, idesc_f16(32), 1);
+  }
 }
 
 template <int P>

@@ -128,7 +128,7 @@ int main(int argc, char** argv) {
       for (int b = 0; b < B; ++b)
         for (int o = 0; o < Cout; ++o)
           for (int t = 0; t < L; ++t) {
-            const size_t cell = (((size_t)b * (Cout / 8) + o / 8) * L + t) * 8 + o % 8;
+            const size_t cell = (((size_t)b * (Cout / 32) + o / 32) * L + t) * 32 + o % 32;
             const float v = __half2float(*reinterpret_cast<const __half*>(&himgy[cell])) +
                             __half2float(*reinterpret_cast<const __half*>(&himgy[(size_t)B * Cout * L + cell]));
             hy[((size_t)b * Cout + o) * L + t] = v >= 0.f ? v : v / out_slope;
@@ -209,7 +209,7 @@ int main(int argc, char** argv) {
     for (int b = 0; b < B; ++b)
       for (int o = 0; o < Cout; ++o)
         for (int t = 0; t < L; ++t) {
-          const size_t cell = (((size_t)b * (Cout / 8) + o / 8) * L + t) * 8 + o % 8;
+          const size_t cell = (((size_t)b * (Cout / 32) + o / 32) * L + t) * 32 + o % 32;
           const float v = __half2float(*reinterpret_cast<const __half*>(&himgy[cell])) +
                           __half2float(*reinterpret_cast<const __half*>(&himgy[(size_t)B * Cout * L + cell]));
           const float y = hy[((size_t)b * Cout + o) * L + t];
