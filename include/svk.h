@@ -148,6 +148,7 @@ int64_t svk_last_launch_count(const svk_handle *h);
 #define SVK_LAYER_RESBLOCK_CONV1 9   /* dilated */
 #define SVK_LAYER_RESBLOCK_CONV2 10
 #define SVK_LAYER_CONV_POST 11
+#define SVK_LAYER_RESBLOCK_PAIR 12 /* fused convs1[l] + convs2[l] + residual of a ResBlock1 (narrow stages) */
 typedef struct svk_launch_record {
   int32_t layer;      /* SVK_LAYER_* */
   int32_t cin, cout;  /* logical channels */

@@ -103,6 +103,32 @@ cudaError_t launch_split_image(const float* x, int B, int C, int L, float slope,
                                cudaStream_t stream);
 inline size_t split_image_halves(int B, int C, int L, int planes = 2) { return (size_t)planes * B * C * L; }
 
+// ---- fused ResBlock1 conv pair on the narrow stages (conv_tc_pair.cu): xt = conv1(x_img) stays on the SM,
+// y = conv2(leaky_relu(xt)) + residual.  Weights are conv_tc_pack images with N = C, planes = 2.
+struct ConvPairArgs {
+  const uint16_t* x_img;  // operand image of leaky_relu(x) [B, C, L]
+  int B, C, L, K, dil1;   // both convs have K taps; conv1 dilation dil1, conv2 dilation 1
+  const uint16_t* w1;
+  const uint16_t* w2;
+  const float* bias1;     // [C]
+  const float* bias2;
+  float unscale1, unscale2;
+  float xt_slope;         // leaky_relu between the convs
+  const float* res;       // fp32 residual [B, C, L], or null
+  const uint16_t* res_img;  // ... or its operand image (leaky_relu(res, res_slope))
+  float res_slope;
+  const float* acc_in;    // optional running sum added after the residual
+  float post_div;         // 1.0f = none
+  float* y;               // fp32 output or null
+  uint16_t* y_img;        // operand image of leaky_relu(y, y_slope) or null
+  float y_slope;
+  // filled by launch_conv_tc_pair:
+  int rows1, rows2, TO, h, ntiles_t, items, na, nw, resident, a_off, a2_off, w_off;
+  FastDiv div_t;
+};
+bool conv_tc_pair_supported(int C, int K, int dil1);
+cudaError_t launch_conv_tc_pair(const ConvPairArgs& a, cudaStream_t stream);
+
 // elementwise / small kernels
 cudaError_t launch_sequence_mask(const int64_t* lengths, int B, int T, float* mask, cudaStream_t s);
 cudaError_t launch_flip(const float* x, int B, int C, int T, float* y, cudaStream_t s);

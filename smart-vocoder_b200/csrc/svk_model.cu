@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <array>
@@ -111,6 +112,8 @@ struct svk_handle {
   std::vector<ResBlock> resblocks;
 
   int64_t launches = 0;
+  bool fuse_pairs = true;  // fused ResBlock conv pairs on the narrow stages ($SVK_FUSE_PAIRS=0 disables: A/B measurements)
+  bool fuse_pairs_all = false;
 
   // svk_profile_begin/end state
   bool profiling = false;
@@ -415,6 +418,7 @@ extern "C" int svk_create(const svk_config* cfg, int device, svk_handle** out) {
   svk_handle* h = new svk_handle();
   h->cfg = c;
   h->device = device;
+  if (const char* e = getenv("SVK_FUSE_PAIRS")) h->fuse_pairs = atoi(e) != 0, h->fuse_pairs_all = atoi(e) == 2;
   build_key_spec(h);
   *out = h;
   return SVK_OK;
@@ -652,6 +656,43 @@ struct Runner {
     h->launches++;
   }
 
+  // Fused conv pair of a ResBlock1 (conv_tc_pair.cu) with the same per-launch accounting as run().
+  bool pair_fusable(const ResBlock& rb, int l) const {
+    if (!h->fuse_pairs || h->planes() != 2) return false;
+    // Fusing removes HBM traffic but not MMA work (and recomputes a (K-1)-row halo per item).  Measured at
+    // 16 x 1024 frames: k = 3 pairs are HBM-bound and gain 25 %, k >= 7 pairs are bound by the per-MMA floor of
+    // narrow tiles and lose 0-25 %  ->  only the 3-tap blocks are fused ($SVK_FUSE_PAIRS=2 fuses every block).
+    if (h->fuse_pairs_all == false && rb.k > 3) return false;
+    return conv_tc_pair_supported(rb.C, rb.k, rb.dil[l]) && rb.c1[l].tc && rb.c2[l].tc && rb.c1[l].tc_N == rb.C &&
+           rb.c2[l].tc_N == rb.C;
+  }
+  void run_pair(const ResBlock& rb, int l, ConvPairArgs p) {
+    if (err != cudaSuccess) return;
+    const PackedConv &c1 = rb.c1[l], &c2 = rb.c2[l];
+    p.B = B, p.C = rb.C, p.K = rb.k, p.dil1 = rb.dil[l];
+    p.w1 = h->d_tcblob + c1.tc_off, p.w2 = h->d_tcblob + c2.tc_off;
+    p.bias1 = h->d_blob + c1.tc_b_off, p.bias2 = h->d_blob + c2.tc_b_off;
+    p.unscale1 = c1.tc_unscale, p.unscale2 = c2.tc_unscale;
+    p.xt_slope = 0.1f;
+    bool open = false;
+    if (h->profiling && h->prof_records.size() < h->prof_cap) {
+      svk_launch_record r;
+      memset(&r, 0, sizeof(r));
+      r.layer = SVK_LAYER_RESBLOCK_PAIR, r.cin = rb.C, r.cout = rb.C, r.k = rb.k, r.dilation = rb.dil[l], r.batch = B;
+      r.length = p.L, r.engine = 1;
+      const double E = (double)B * rb.C * p.L;
+      r.flops = 2.0 * 2.0 * E * rb.C * rb.k;  // both convs
+      r.bytes = 4.0 * E * (1 + (p.res || p.res_img ? 1 : 0) + (p.acc_in ? 1 : 0) + (p.y ? 1 : 0) + (p.y_img ? 1 : 0)) +
+                2.0 * 4.0 * rb.C * rb.C * rb.k;
+      h->prof_records.push_back(r);
+      cudaEventRecord(h->prof_events[2 * (h->prof_records.size() - 1)], stream);
+      open = true;
+    }
+    err = launch_conv_tc_pair(p, stream);
+    prof_close(open);
+    h->launches++;
+  }
+
   // modules.WN.forward, g=None (modules.py:148-176).  x is updated in place, result in `out`.
   // With x_img / acts_img (tcgen05 engine) the convs read operand images by TMA: x_img must hold the image of
   // the incoming x; every res_skip epilogue rewrites it together with x, the gate epilogue writes acts only
@@ -703,6 +744,29 @@ struct Runner {
                        uint16_t* cur_img, float* dst, const float* acc_in, float post_div, int L,
                        uint16_t* dst_img = nullptr) {
     const int C = rb.C;
+    bool fuse = true;
+    for (int l = 0; l < SVK_RESBLOCK_PAIRS; ++l) fuse = fuse && pair_fusable(rb, l);
+    if (fuse) {
+      // narrow stages: one launch per pair, xt never leaves the SM (conv_tc_pair.cu).  The pair kernel reads its
+      // input image with a halo, so images ping-pong: x_img -> cur_img -> xt_img (free here) -> dst_img.
+      for (int l = 0; l < SVK_RESBLOCK_PAIRS; ++l) {
+        ConvPairArgs p;
+        memset(&p, 0, sizeof(p));
+        p.L = L;
+        p.x_img = l == 0 ? x_img : (l == 1 ? cur_img : xt_img);
+        p.res = l == 0 ? x : cur;  // fp32 residual stream: same element read then written by one thread
+        p.post_div = 1.0f;
+        if (l < SVK_RESBLOCK_PAIRS - 1) {
+          p.y = cur;
+          p.y_img = l == 0 ? cur_img : xt_img, p.y_slope = 0.1f;
+        } else {
+          p.y = dst, p.acc_in = acc_in, p.post_div = post_div;
+          p.y_img = dst_img, p.y_slope = 0.1f;
+        }
+        run_pair(rb, l, p);
+      }
+      return;
+    }
     for (int l = 0; l < SVK_RESBLOCK_PAIRS; ++l) {
       const float* src = l == 0 ? x : cur;
       const uint16_t* src_img = l == 0 ? x_img : cur_img;

@@ -67,7 +67,7 @@ class SvkLaunchRecord(ctypes.Structure):
 
 
 LAYER_NAMES = {0: "other", 1: "pre_enc", 2: "wn_in", 3: "wn_res_skip", 4: "proj", 5: "flow_pre", 6: "flow_post",
-               7: "conv_pre", 8: "upsample", 9: "resblock_conv1", 10: "resblock_conv2", 11: "conv_post"}
+               7: "conv_pre", 8: "upsample", 9: "resblock_conv1", 10: "resblock_conv2", 11: "conv_post", 12: "resblock_pair"}
 
 _lib: Optional[ctypes.CDLL] = None
 
