@@ -636,6 +636,34 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
               if (o < a.Cout && tq >= 0 && tq < a.shuf_Lout) ybase[(size_t)co * a.y_stride + tq] = v[e];
             }
           }
+          if (a.e[0].split && sh == 2 && o0 + 16 <= a.Cout) {
+            // stride-2 upsamplers: this thread holds 8 consecutive real channels at two output steps -> it also
+            // writes the operand image of leaky_relu(y) that the stage's ResBlocks read (16 B per step and plane)
+            const int co0 = a.e[0].ch_off + (o0 >> 1);
+#pragma unroll
+            for (int r2 = 0; r2 < 2; ++r2) {
+              const int tq = 2 * t + r2 - a.shuf_p;
+              if (tq < 0 || tq >= a.shuf_Lout) continue;
+              float w8[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float q = v[2 * e + r2];
+                w8[e] = q > 0.f ? q : q * a.e[0].split_slope;
+              }
+              uint16_t* sp = a.e[0].split + (((size_t)b * (a.e[0].C >> 5) + (co0 >> 5)) * a.y_stride + tq) * 32 + (co0 & 31);
+              if (planes == 2) {
+                uint4 hq, lq;
+                split2(w8[0], w8[1], hq.x, lq.x);
+                split2(w8[2], w8[3], hq.y, lq.y);
+                split2(w8[4], w8[5], hq.z, lq.z);
+                split2(w8[6], w8[7], hq.w, lq.w);
+                *reinterpret_cast<uint4*>(sp) = hq;
+                *reinterpret_cast<uint4*>(sp + sp_plane * (size_t)a.e[0].C) = lq;
+              } else {
+                *reinterpret_cast<uint4*>(sp) = pack_bf16x8(w8);
+              }
+            }
+          }
         }
       }
       // every tcgen05.ld of this stage has completed (wait::ld above): hand the stage back
@@ -841,8 +869,9 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
     if (a.e[sd].res_img && (a.mode != MODE_STORE || ta.planes == 1 || a.e[sd].ch_sign != 1 || a.e[sd].ch_off % 16 || a.e[sd].C % 32 ||
                             a.Cout % 16 || a.e[sd].res || !(a.e[sd].res_slope > 0.f)))
       return cudaErrorInvalidValue;
-    if (a.e[sd].split && (a.mode == MODE_SHUFFLE || a.e[sd].ch_sign != 1 || a.e[sd].ch_off % 16 || a.e[sd].C % 32 ||
-                          (a.mode == MODE_STORE ? a.Cout % 16 : a.Cout % 32)))
+    if (a.e[sd].split && (a.e[sd].ch_sign != 1 || a.e[sd].ch_off % 16 || a.e[sd].C % 32 ||
+                          (a.mode == MODE_STORE ? a.Cout % 16 : a.Cout % 32) ||
+                          (a.mode == MODE_SHUFFLE && (a.shuf_s != 2 || a.shuf_Lout != a.y_stride))))
       return cudaErrorInvalidValue;
   }
   CUtensorMap map;

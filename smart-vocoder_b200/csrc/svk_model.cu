@@ -849,12 +849,12 @@ void run_decoder(Runner& R, const float* z, int z_stride, const float* in_mask, 
   if (plan.n_bufs == 7)
     for (int i = 0; i < 3; ++i) img[i] = reinterpret_cast<uint16_t*>(ws + (4 + i) * plan.buf_floats);
   const int U = c.upsample_initial_channel;
-  const uint16_t* prev_img = nullptr;  // operand image of leaky_relu(prev, 0.1) when the producer wrote one
+  int pi = -1;  // index of the image buffer holding leaky_relu(prev, 0.1) when the producer wrote one, else -1
   {
     ConvArgs a = R.base(h->conv_pre, z, c.inter_channels, 0, z_stride, L, 1, 3, L, L);
     a.in_mask = in_mask, a.mask_stride = z_stride;
     a.e[0].y = buf[1], a.e[0].C = U;
-    if (img[0] && h->conv_pre.tc && h->ups[0].tc) a.e[0].split = img[0], a.e[0].split_slope = 0.1f, prev_img = img[0];
+    if (img[0] && h->conv_pre.tc && h->ups[0].tc) a.e[0].split = img[0], a.e[0].split_slope = 0.1f, pi = 0;
     R.run(a, SVK_LAYER_CONV_PRE);
   }
   const float* prev = buf[1];
@@ -870,6 +870,17 @@ void run_decoder(Runner& R, const float* z, int z_stride, const float* in_mask, 
     if (prev == XS) {  // previous stage summed into buf[3]; rotate so it is not overwritten early
       XS = buf[1], XT = buf[3];
     }
+    const int nk = c.n_resblock_kernels;
+    bool images = img[0] != nullptr;
+    for (int j = 0; j < nk; ++j) images = images && R.resblock_uses_images(h->resblocks[i * nk + j]);
+    // Image buffer roles of this stage.  A stride-2 upsampler writes the stage's x image from its own epilogue
+    // (it may not overwrite the image it is reading: next buffer); otherwise split_image_kernel makes it from X
+    // after the upsampler has finished with its input image (same buffer is fine).
+    const bool up_writes_img = images && up.tc && up.s == 2 && (up.Cout % 16) == 0 && C % 32 == 0;
+    const int xi = up_writes_img ? (pi < 0 ? 0 : (pi + 1) % 3) : (pi < 0 ? 0 : pi);
+    uint16_t* x_img = img[xi];
+    uint16_t* xt_img = img[(xi + 1) % 3];
+    uint16_t* cur_img = img[(xi + 2) % 3];
     // ups[i](leaky_relu(x, 0.1)) (models.py:147-149)
     {
       const int nq = (Lout - 1 + up.p) / up.s + 1;
@@ -878,24 +889,22 @@ void run_decoder(Runner& R, const float* z, int z_stride, const float* in_mask, 
       a.mode = MODE_SHUFFLE;
       a.shuf_s = up.s, a.shuf_p = up.p, a.shuf_Lout = Lout;
       a.e[0].y = X, a.e[0].C = C;
-      R.run(a, SVK_LAYER_UPSAMPLE, up.tc ? prev_img : nullptr);
-      prev_img = nullptr;
+      if (up_writes_img) a.e[0].split = x_img, a.e[0].split_slope = 0.1f;
+      R.run(a, SVK_LAYER_UPSAMPLE, (up.tc && pi >= 0) ? img[pi] : nullptr);
     }
     // xs = sum_j resblock_j(x); x = xs / num_kernels (models.py:150-155)
-    const int nk = c.n_resblock_kernels;
-    bool images = img[0] != nullptr;
-    for (int j = 0; j < nk; ++j) images = images && R.resblock_uses_images(h->resblocks[i * nk + j]);
-    if (images) R.note(launch_split_image(X, R.B, C, Lout, 0.1f, img[0], h->planes(), R.stream));  // shared by the nk blocks
+    if (images && !up_writes_img) R.note(launch_split_image(X, R.B, C, Lout, 0.1f, x_img, h->planes(), R.stream));  // shared by the nk blocks
+    const bool next_wants_img = images && i + 1 < c.n_upsamples && h->ups[i + 1].tc && C % 32 == 0;
     for (int j = 0; j < nk; ++j) {
       const ResBlock& rb = h->resblocks[i * nk + j];
       const float* acc = j ? XS : nullptr;
       const float div = j == nk - 1 ? (float)nk : 1.0f;
-      // the last block's final epilogue also writes the next upsampler's operand image
-      uint16_t* next_img = (images && j == nk - 1 && i + 1 < c.n_upsamples && h->ups[i + 1].tc && C % 16 == 0) ? img[0] : nullptr;
-      if (images) R.resblock_images(rb, X, img[0], img[1], CUR, img[2], XS, acc, div, Lout, next_img);
+      // the last block's final epilogue also writes the next upsampler's operand image (over x_img, dead by then)
+      uint16_t* next_img = (next_wants_img && j == nk - 1) ? x_img : nullptr;
+      if (images) R.resblock_images(rb, X, x_img, xt_img, CUR, cur_img, XS, acc, div, Lout, next_img);
       else R.resblock(rb, X, XT, CUR, XS, acc, div, Lout);
     }
-    if (images && i + 1 < c.n_upsamples && h->ups[i + 1].tc && C % 16 == 0) prev_img = img[0];
+    pi = next_wants_img ? xi : -1;
     prev = XS, prevC = C, len = Lout;
   }
   // tanh(conv_post(leaky_relu(x)))  -- default slope 0.01 (models.py:156-158)
