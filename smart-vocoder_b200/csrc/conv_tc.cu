@@ -195,6 +195,37 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
           mbar_wait_u32(bar_a_full + 8u * ast, aph);
           tc_fence_after();
           uint32_t ah = a_lo0 + (uint32_t)ast * a_stage16;  // tap 0, ks 0, hi planes
+          if (!wait_w) {
+            // resident weights, already seen: nothing to wait for or release per tap.  Narrow layers live here
+            // and are bound by how fast this lane can issue (their MMAs take ~45 cycles), so the loop is bare:
+            // 4 MMAs + 2 adds per tap.
+            if (leader) {
+              uint32_t bw = w_lo0 + (uint32_t)(ch * K) * w_stage16;
+              if (planes == 2) {
+#pragma unroll 1
+                for (int j = 0; j < K; ++j) {
+                  umma_f16_lo(dmain, ah, bw, a_hi, b_hi, idesc2, acc);
+                  umma_f16_lo(dcross, ah + lo_plane16, bw, a_hi, b_hi, idesc1, 1u);
+                  umma_f16_lo(dmain, ah + ks_a16, bw + ks_b16, a_hi, b_hi, idesc2, 1u);
+                  umma_f16_lo(dcross, ah + ks_a16 + lo_plane16, bw + ks_b16, a_hi, b_hi, idesc1, 1u);
+                  acc = 1u;
+                  ah += dil16, bw += w_stage16;
+                }
+              } else {
+#pragma unroll 1
+                for (int j = 0; j < K; ++j) {
+                  umma_f16_lo(dmain, ah, bw, a_hi, b_hi, idesc1, acc);
+                  umma_f16_lo(dmain, ah + ks_a16, bw + ks_b16, a_hi, b_hi, idesc1, 1u);
+                  acc = 1u;
+                  ah += dil16, bw += w_stage16;
+                }
+              }
+              umma_commit_u32(bar_a_empty + 8u * ast);
+            }
+            acc = 1u;
+            if (++ast == na) ast = 0, aph ^= 1;
+            continue;
+          }
           for (int j = 0; j < K; ++j) {
             if (wait_w) {
               mbar_wait_u32(bar_w_full + 8u * wst, wph);
