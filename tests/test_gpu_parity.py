@@ -313,3 +313,57 @@ def test_full_size_window_vs_oracle_and_batch_independence(net, base_sd, base_di
     with inject_eps(eps[11:12]), torch.no_grad():
         o1 = _np(net.infer(dev(mel[11:12]), dev(lengths[11:12], torch.int64), noise_scale=0.667)[0])
     assert np.array_equal(o1[0], o[11])
+
+
+def test_config2_resblocks_at_b1_t1024(net, base_sd, base_dims):
+    """BASELINE configs[1]: batch 1, 80x1024 mel, decoder ResBlock convs only.  Stage-1 blocks (C=128 at
+    64 samples per frame -> L = 65536) through svk_resblock1; a ResBlock1 is local (halo 12 / 36 / 60 samples for
+    k = 3 / 7 / 11), so the fp64 oracle on a cropped window must reproduce the interior."""
+    import svk_runtime as rt
+    from gpu_util import dev
+    rng = np.random.Generator(np.random.Philox(key=[2, 1024]))
+    C, L = 128, 64 * 1024
+    x = rng.standard_normal((1, C, L)).astype(np.float32)
+    orc = Oracle(np.float64)
+    for idx in (3, 4, 5):
+        k = base_dims.resblock_kernel_sizes[idx % 3]
+        xd, y = dev(x), torch.empty(1, C, L, device="cuda")
+        ws = torch.empty(rt.lib().svk_resblock1_workspace_bytes(net._handle.ptr, idx, 1, L), dtype=torch.uint8, device="cuda")
+        rt.check(rt.lib().svk_resblock1(net._handle.ptr, idx, xd.data_ptr(), 1, L, y.data_ptr(), ws.data_ptr(), ws.numel(),
+                                        torch.cuda.current_stream().cuda_stream))
+        yh = _np(y)
+        assert np.isfinite(yh).all()
+        for w0 in (0, 30000, L - 400):  # left edge (zero padding), interior across tile borders, right edge
+            lo, hi = max(0, w0 - 64), min(L, w0 + 400 + 64)
+            ref = orc.resblock1(base_sd, f"dec.resblocks.{idx}", x[:, :, lo:hi], k, (1, 3, 5))
+            a0 = w0 if lo == 0 else w0  # interior [w0, w0+400) is >= 60 samples from any artificial cut
+            a1 = min(L, w0 + 400)
+            assert np.abs(yh[0, :, a0:a1] - ref[0, :, a0 - lo:a1 - lo]).max() <= TOL, (idx, w0)
+
+
+def test_config4_bf16_at_b64_t512(base_cfg, base_sd):
+    """BASELINE configs[3] shape: batch 64, 80x512 mel, bf16 operands with fp32 accumulate.  No reference
+    counterpart exists; the fp32-class engine (itself within 1e-4 of the reference) is the yardstick: per-utterance
+    waveform SNR >= 30 dB, and utterances stay independent (batch item alone == inside the batch, bit for bit)."""
+    from gpu_util import build_net, dev, inject_eps
+    B, T = 64, 512
+    rng = np.random.Generator(np.random.Philox(key=[64, 512]))
+    mel = (rng.standard_normal((B, 80, T)) * 2 - 5).astype(np.float32)
+    eps = rng.standard_normal((B, 192, T)).astype(np.float32)
+    lengths = np.full(B, T, np.int64)
+    outs = {}
+    for eng in ("bf16", "tc"):
+        net_e = build_net(base_cfg["model"], base_sd, engine=eng)
+        with inject_eps(eps), torch.no_grad():
+            outs[eng] = _np(net_e.infer(dev(mel), dev(lengths, torch.int64), noise_scale=0.667)[0]).astype(np.float64)
+        if eng == "bf16":
+            with inject_eps(eps[40:41]), torch.no_grad():
+                alone = _np(net_e.infer(dev(mel[40:41]), dev(lengths[40:41], torch.int64), noise_scale=0.667)[0])
+            assert np.array_equal(alone[0].astype(np.float64), outs[eng][40])
+        del net_e
+        torch.cuda.empty_cache()
+    assert outs["bf16"].shape == (B, 1, 256 * T) and np.isfinite(outs["bf16"]).all()
+    err = outs["bf16"] - outs["tc"]
+    snr = 10 * np.log10((outs["tc"] ** 2).sum(axis=(1, 2)) / (err ** 2).sum(axis=(1, 2)))
+    print("bf16 vs tc at 64x512: SNR min %.1f dB, median %.1f dB" % (snr.min(), np.median(snr)))
+    assert snr.min() >= 30.0
