@@ -345,7 +345,7 @@ def run_b200_arm(args):
     avg_ms = top["ms"] / top["n"]
     achieved_tf = (top["flops"] / top["n"]) / (avg_ms / 1e3) / 1e12
     hbm_gbs = (top["bytes"] / top["n"]) / (avg_ms / 1e3) / 1e9
-    traffic, traffic_src = None, None
+    traffic, traffic_src, traffic_alg = None, None, None
     tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(tpath):
         try:
@@ -353,6 +353,7 @@ def run_b200_arm(args):
             ent = tj.get("families", {}).get(f"{eng}:cin{top_cin}:k{top_k}")
             if ent:
                 traffic, traffic_src = ent.get("dram_bytes_per_launch"), tj.get("source")
+                traffic_alg = ent.get("algorithmic_bytes_of_this_launch")
         except Exception:
             traffic = None
     tc_peak = peaks["bf16_tflops_sustained"]
@@ -372,6 +373,8 @@ def run_b200_arm(args):
         "tensor_raw": {"achieved": 3 * achieved_tf, "frac": 3 * achieved_tf / peak_tf} if eng == "tc" else None,
         "peak_source": peak_src,
         "traffic": traffic, "traffic_source": traffic_src,
+        "traffic_launch_algorithmic_bytes": traffic_alg,  # of the captured launch (a conv2 with fp32 + image outputs);
+                                                          # algorithmic_bytes_per_launch below averages the family
         "timing": "CUDA-event pair around every launch on the launching stream, second pass of the same K steps "
                   "(profiled_pass_ms_per_step); `value` comes from the first pass without per-launch events",
         "launches_in_group": top["n"], "avg_launch_ms": avg_ms, "share_of_step": top["ms"] / prof_total_ms,
