@@ -48,7 +48,7 @@ namespace svk {
 namespace {
 
 constexpr int NA_MAX = 8;   // A ring depth limit (producer warps: 2 or 4, the groups own alternate slots; TMA: up to 8)
-constexpr int MAXNW = 16;   // weight ring depth limit
+constexpr int MAXNW = 24;   // weight ring depth limit
 constexpr int MAXACC = 8;   // accumulator ring depth limit (512 TMEM columns / 2N, power of two)
 #ifndef SVK_TC_PROD_WARPS
 #define SVK_TC_PROD_WARPS 8
@@ -61,7 +61,6 @@ constexpr int THREADS = 64 + 32 * (PROD_WARPS + EPI_WARPS);  // 576
 constexpr int PROD_GROUP = 128;                              // threads per producer group (one time row each)
 constexpr int PROD_GROUPS = PROD_WARPS / 4;                  // groups take alternate chunks
 constexpr int EPI_SPLIT = EPI_WARPS / 4;                     // warps sharing one TMEM lane quarter split the columns
-constexpr int EPI_THREADS = 32 * EPI_WARPS;
 constexpr int FIRST_EPI_WARP = 2 + PROD_WARPS;
 // TMA-input variant (activations already in HBM as fp16 hi/lo operand images): warps 0..3 are the
 // weight producer, the MMA issuer, the activation TMA issuer and a spare; the rest is epilogue.
@@ -81,7 +80,7 @@ struct __align__(8) SmemHeader {
   uint32_t tmem_base;
   uint32_t pad;
 };
-constexpr int HEADER_BYTES = 640;
+constexpr int HEADER_BYTES = 768;
 static_assert(sizeof(SmemHeader) <= HEADER_BYTES, "header");
 
 // ------------------------------------------------------------------------------------- kernel
@@ -120,7 +119,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
   uint8_t* w_smem = a_smem + (size_t)na * a_stage;
   const int nchunks = a.Cin / KC;
   const int per_tile = nchunks * K;  // weight stages per item
-  const int items = ta.items, ntiles_t = ta.ntiles_t;
+  const int items = ta.items;
   const int resident = ta.resident;
   const int n_my = (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int nacc = ta.nacc, nacc_shift = 31 - __clz(nacc);  // accumulator stages (power of two)
@@ -805,6 +804,11 @@ void conv_tc_plan(int Cin, int Cout, int K, int dil, int N, bool tma, int planes
   if (W > MAXNW) W = MAXNW;
   int res = 0;
   if (ntiles_n == 1 && per_tile <= W) res = 1, W = per_tile;
+  if (!res && tma && ntiles_n == 1 && per_tile <= MAXNW && (size_t)per_tile * w_stage + 2 * a_stage <= budget) {
+    // TMA-fed layers prefer resident weights even with a 2-deep A ring: the MMA lane then runs the bare issue
+    // loop (no per-tap wait / release), which is what bounds narrow layers (C = 64, k = 11: 22 stages of 8 KB)
+    res = 1, W = per_tile, A = 2;
+  }
   if (tma) {
     // TMA-fed A ring: the ring depth is the prefetch distance that hides HBM latency (no registers
     // involved), so it takes whatever the weights leave: all stages when resident, else >= 6 weight stages
