@@ -215,6 +215,32 @@ int svk_rq_spline(const float *x_dev, const float *uw_dev, const float *uh_dev, 
                   float min_bin_height, float min_derivative, float *y_dev, float *logabsdet_dev,
                   int32_t *bin_dev, void *stream);
 
+/* ---- mel front-end (the step before infer in both callers) -----------------
+ * Replaces mel_processing.spectrogram_torch (mel_processing.py:51-69), spec_to_mel_torch (:72-81) and
+ * mel_spectrogram_torch (:84-112) as inference.ipynb:100-111 / train.py:266-272 use them (center=False).
+ *   y    [B, n_samples] fp32 waveform in [-1, 1]      T = svk_frontend_frames(n_samples)
+ *   spec [B, n_fft/2+1, T] = sqrt(re^2 + im^2 + 1e-6) of the Hann(win_size) STFT, hop `hop_size`, over
+ *        the signal reflect-padded by (n_fft - hop_size)/2 per side
+ *   mel  [B, n_mels, T]    = log(clamp(mel_basis @ spec, 1e-5))
+ * fmax <= 0 means None (sampling_rate / 2), as in configs/iitp_base.json.  The handle owns the window,
+ * twiddle and mel-basis tables on its device; calls are stream-ordered, no allocation, no sync. */
+typedef struct svk_frontend svk_frontend;
+int svk_frontend_create(int n_fft, int hop_size, int win_size, int sampling_rate, int n_mels, float fmin,
+                        float fmax, int device, svk_frontend **out);
+void svk_frontend_destroy(svk_frontend *f);
+int64_t svk_frontend_frames(const svk_frontend *f, int64_t n_samples);
+int svk_spectrogram(svk_frontend *f, const float *y_dev, int B, int64_t n_samples, float *spec_dev,
+                    void *stream);
+int svk_spec_to_mel(svk_frontend *f, const float *spec_dev, int B, int64_t T, float *mel_dev, void *stream);
+/* Fused: the linear spectrogram stays in shared memory (spec_dev may be NULL; non-NULL also stores it). */
+int svk_mel_spectrogram(svk_frontend *f, const float *y_dev, int B, int64_t n_samples, float *mel_dev,
+                        float *spec_dev, void *stream);
+/* Host-side table builders (no device needed): librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax) with its
+ * defaults htk=False, norm="slaney" (mel_processing.py:76,95; third-party, restated) -> [n_mels, n_fft/2+1];
+ * torch.hann_window(win_size) in fp32 centred in n_fft taps (mel_processing.py:59-60) -> [n_fft]. */
+int svk_mel_basis(int sampling_rate, int n_fft, int n_mels, float fmin, float fmax, float *basis_host);
+int svk_hann_window(int win_size, int n_fft, float *window_host);
+
 #ifdef __cplusplus
 }
 #endif

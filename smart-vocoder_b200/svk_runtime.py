@@ -101,6 +101,14 @@ SIGNATURES = {
     "svk_flip": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "svk_weight_norm": (_i, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "svk_rq_spline": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp]),
+    "svk_frontend_create": (_i, [_i, _i, _i, _i, _i, _f, _f, _i, ctypes.POINTER(_vp)]),
+    "svk_frontend_destroy": (None, [_vp]),
+    "svk_frontend_frames": (_i64, [_vp, _i64]),
+    "svk_spectrogram": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
+    "svk_spec_to_mel": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
+    "svk_mel_spectrogram": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp]),
+    "svk_mel_basis": (_i, [_i, _i, _i, _f, _f, _vp]),
+    "svk_hann_window": (_i, [_i, _i, _vp]),
 }
 
 
