@@ -127,6 +127,30 @@ int svk_infer(svk_handle *h, const float *mel_dev, const int64_t *lengths_dev, c
 int svk_infer_host(svk_handle *h, const float *mel, const int64_t *lengths, const float *eps,
                    float noise_scale, int B, int T, int max_len, float *o, float *x_mask, float *z,
                    float *z_p, float *m_p, float *logs_p);
+/* ---- windowed / chunked synthesis (streaming and T >> 1024) ----------------
+ * svk_infer_window computes the PCM of frames [t0, t1) of the utterance batch EXACTLY as the whole-
+ * utterance svk_infer would: the window is widened by svk_halo_frames() frames of context per side
+ * (WN stacks + flow + decoder receptive field; 110 for iitp_base.json), clipped at the true sequence
+ * ends, and only the interior is stored.  mel / eps / lengths are the FULL tensors ([B,n_mel,T],
+ * [B,inter,T], [B]); o receives [B, hop*(t1-t0)] with row stride o_row_stride floats (so a chunk can
+ * be written in place into a full [B,1,hop*T] buffer, or into a buffer of its own for streaming);
+ * the optional latents receive [B, inter, t1-t0] with row stride lat_row_stride.  Workspace:
+ * svk_window_workspace_bytes(B, t1-t0) -- bounded by the chunk, not by T.
+ * svk_infer_chunked walks the windows of `chunk_frames` frames over [0, T) and fills o / x_mask /
+ * latents of the svk_infer layout.  No reference counterpart (the reference synthesises whole
+ * utterances, models.py:331-339); parity = equality with svk_infer on the same inputs.  max_len as in
+ * svk_infer (<= 0: None): windows must lie inside [0, min(T, max_len)); svk_infer_chunked returns latents
+ * only when max_len does not shorten the output. */
+int svk_halo_frames(const svk_handle *h);
+size_t svk_window_workspace_bytes(const svk_handle *h, int B, int frames);
+int svk_infer_window(svk_handle *h, const float *mel_dev, const int64_t *lengths_dev, const float *eps_dev,
+                     float noise_scale, int B, int T, int max_len, int t0, int t1, float *o_dev, int64_t o_row_stride,
+                     float *z_dev, float *z_p_dev, float *m_p_dev, float *logs_p_dev, int64_t lat_row_stride,
+                     void *workspace_dev, size_t workspace_bytes, void *stream);
+int svk_infer_chunked(svk_handle *h, const float *mel_dev, const int64_t *lengths_dev, const float *eps_dev,
+                      float noise_scale, int B, int T, int max_len, int chunk_frames, float *o_dev, float *x_mask_dev,
+                      float *z_dev, float *z_p_dev, float *m_p_dev, float *logs_p_dev, void *workspace_dev,
+                      size_t workspace_bytes, void *stream);
 /* Kernels launched by the most recent svk_infer / module call on this handle. */
 int64_t svk_last_launch_count(const svk_handle *h);
 

@@ -30,6 +30,16 @@ __global__ void sequence_mask_kernel(const int64_t* __restrict__ lengths, int B,
   }
 }
 
+// Lengths seen by a time window [a, a + w) of the batch: clamp(length - a, 0, w) (integer; svk_infer_window).
+__global__ void window_lengths_kernel(const int64_t* __restrict__ lengths, int B, int64_t a, int64_t w,
+                                      int64_t* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) {
+    const int64_t v = lengths[b] - a;
+    out[b] = v < 0 ? 0 : (v > w ? w : v);
+  }
+}
+
 // modules.Flip (modules.py:272): torch.flip(x, [1])
 __global__ void flip_kernel(const float* __restrict__ x, int B, int C, int T, float* __restrict__ y) {
   const int64_t n = (int64_t)B * C * T;
@@ -168,6 +178,12 @@ __global__ void rq_spline_kernel(const float* __restrict__ x, const float* __res
 cudaError_t launch_sequence_mask(const int64_t* lengths, int B, int T, float* mask, cudaStream_t s) {
   if ((int64_t)B * T == 0) return cudaSuccess;
   sequence_mask_kernel<<<ew_blocks((int64_t)B * T), EW_THREADS, 0, s>>>(lengths, B, T, mask);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_window_lengths(const int64_t* lengths, int B, int64_t a, int64_t w, int64_t* out, cudaStream_t s) {
+  if (B == 0) return cudaSuccess;
+  window_lengths_kernel<<<(B + EW_THREADS - 1) / EW_THREADS, EW_THREADS, 0, s>>>(lengths, B, a, w, out);
   return cudaGetLastError();
 }
 

@@ -1137,6 +1137,142 @@ extern "C" int svk_infer_host(svk_handle* h, const float* mel, const int64_t* le
   return SVK_OK;
 }
 
+// ------------------------------------------------------------- windowed / chunked synthesis (8(f) rank 3)
+namespace {
+
+// Frames of context per side after which a window's output equals the whole-utterance result:
+// WN stacks (k-1)/2 per layer (modules.py:133), decoder receptive field propagated back through
+// conv_post, the ResBlock1 dilations (modules.py:191-206) and the transposed convs.
+int halo_frames(const svk_handle* h) {
+  const svk_config& c = h->cfg;
+  const int wn = (c.wn_kernel - 1) / 2;
+  int halo = 3;  // conv_post k=7 at the output rate
+  for (int i = c.n_upsamples - 1; i >= 0; --i) {
+    int rb = 0;
+    for (int j = 0; j < c.n_resblock_kernels; ++j) {
+      int r = 0;
+      const int hk = (c.resblock_kernel_sizes[j] - 1) / 2;
+      for (int l = 0; l < SVK_RESBLOCK_PAIRS; ++l) r += hk * (c.resblock_dilations[j][l] + 1);
+      rb = r > rb ? r : rb;
+    }
+    halo += rb;
+    const int s = c.upsample_rates[i];
+    halo = (halo + s - 1) / s + 1;  // ConvTranspose1d k = 2s: an output reads inputs floor((t+p-k+1)/s) .. floor((t+p)/s)
+  }
+  halo += 3;  // conv_pre k=7
+  return halo + c.enc_layers * wn + c.n_flows * c.flow_layers * wn;
+}
+
+struct WindowPlan {
+  int64_t W;  // widest window: frames + 2 * halo
+  size_t mel, eps, len, o, lat[4], ws, ws_bytes, total;  // byte offsets
+};
+
+WindowPlan plan_window(const svk_handle* h, int B, int frames) {
+  const svk_config& c = h->cfg;
+  WindowPlan p;
+  p.W = (int64_t)frames + 2 * halo_frames(h);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  p.mel = take((size_t)B * c.n_mel * p.W * 4);
+  p.eps = take((size_t)B * c.inter_channels * p.W * 4);
+  p.len = take((size_t)B * 8);
+  p.o = take((size_t)B * h->hop() * p.W * 4);
+  for (int i = 0; i < 4; ++i) p.lat[i] = take((size_t)B * c.inter_channels * p.W * 4);
+  p.ws_bytes = svk_workspace_bytes(h, B, (int)p.W, 0);
+  p.ws = take(p.ws_bytes);
+  p.total = off;
+  return p;
+}
+
+}  // namespace
+
+extern "C" int svk_halo_frames(const svk_handle* h) { return h ? halo_frames(h) : 0; }
+
+extern "C" size_t svk_window_workspace_bytes(const svk_handle* h, int B, int frames) {
+  if (!h || B <= 0 || frames <= 0) return 0;
+  return plan_window(h, B, frames).total;
+}
+
+extern "C" int svk_infer_window(svk_handle* h, const float* mel, const int64_t* lengths, const float* eps,
+                                float noise_scale, int B, int T, int max_len, int t0, int t1, float* o, int64_t o_row_stride,
+                                float* z, float* z_p, float* m_p, float* logs_p, int64_t lat_row_stride,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  SVK_TRY(check_ready(h, "svk_infer_window"));
+  if (!mel || !lengths || !eps || !o) return fail(SVK_ERR_INVALID, "svk_infer_window: null mel/lengths/eps/o");
+  const int Tp = max_len > 0 && max_len < T ? max_len : T;  // decoder input is (z * mask)[:, :, :max_len] (models.py:338)
+  if (B <= 0 || T <= 0 || t0 < 0 || t1 <= t0 || t1 > Tp) return fail(SVK_ERR_INVALID, "svk_infer_window: need 0 <= t0 < t1 <= min(T, max_len)");
+  const svk_config& c = h->cfg;
+  const int hop = h->hop(), halo = halo_frames(h);
+  const WindowPlan p = plan_window(h, B, t1 - t0);
+  if (!workspace || workspace_bytes < p.total)
+    return fail(SVK_ERR_WORKSPACE, "svk_infer_window: workspace %zu < %zu bytes (svk_window_workspace_bytes)", workspace_bytes, p.total);
+  if (o_row_stride < (int64_t)hop * (t1 - t0)) return fail(SVK_ERR_INVALID, "svk_infer_window: o_row_stride shorter than the window");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  // window with context, clipped at the true sequence ends (where the reference zero-pads too)
+  const int a = t0 - halo > 0 ? t0 - halo : 0, b = t1 + halo < T ? t1 + halo : T, w = b - a;
+  char* d = (char*)workspace;
+  float* mel_w = (float*)(d + p.mel);
+  float* eps_w = (float*)(d + p.eps);
+  int64_t* len_w = (int64_t*)(d + p.len);
+  float* o_w = (float*)(d + p.o);
+  CUDA_TRY(cudaMemcpy2DAsync(mel_w, (size_t)w * 4, mel + a, (size_t)T * 4, (size_t)w * 4, (size_t)B * c.n_mel, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaMemcpy2DAsync(eps_w, (size_t)w * 4, eps + a, (size_t)T * 4, (size_t)w * 4, (size_t)B * c.inter_channels, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(launch_window_lengths(lengths, B, a, w, len_w, s));
+  float* user[4] = {z, z_p, m_p, logs_p};
+  float* lat[4];
+  for (int i = 0; i < 4; ++i) lat[i] = user[i] ? (float*)(d + p.lat[i]) : nullptr;
+  // the encoder and the flow see frames up to b; the decoder stops at the true end Tp when the window crosses it
+  const int wd = b > Tp ? Tp - a : w;
+  SVK_TRY(svk_infer(h, mel_w, len_w, eps_w, noise_scale, B, w, wd < w ? wd : 0, o_w, nullptr, lat[0], lat[1], lat[2], lat[3],
+                    d + p.ws, p.ws_bytes, stream));
+  const int64_t launches = h->launches;
+  const size_t n = (size_t)(t1 - t0);
+  CUDA_TRY(cudaMemcpy2DAsync(o, (size_t)o_row_stride * 4, o_w + (size_t)(t0 - a) * hop, (size_t)wd * hop * 4, n * hop * 4, (size_t)B,
+                             cudaMemcpyDeviceToDevice, s));
+  for (int i = 0; i < 4; ++i)
+    if (user[i]) {
+      if (lat_row_stride < (int64_t)n) return fail(SVK_ERR_INVALID, "svk_infer_window: lat_row_stride shorter than the window");
+      CUDA_TRY(cudaMemcpy2DAsync(user[i], (size_t)lat_row_stride * 4, lat[i] + (t0 - a), (size_t)w * 4, n * 4,
+                                 (size_t)B * c.inter_channels, cudaMemcpyDeviceToDevice, s));
+    }
+  h->launches = launches;
+  return SVK_OK;
+}
+
+extern "C" int svk_infer_chunked(svk_handle* h, const float* mel, const int64_t* lengths, const float* eps,
+                                 float noise_scale, int B, int T, int max_len, int chunk_frames, float* o, float* x_mask, float* z,
+                                 float* z_p, float* m_p, float* logs_p, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  SVK_TRY(check_ready(h, "svk_infer_chunked"));
+  if (chunk_frames <= 0) return fail(SVK_ERR_INVALID, "svk_infer_chunked: chunk_frames must be positive");
+  if (B <= 0 || T <= 0 || !o) return fail(SVK_ERR_INVALID, "svk_infer_chunked: bad argument");
+  const int hop = h->hop();
+  const int Tp = max_len > 0 && max_len < T ? max_len : T;
+  if (Tp < T && (z || z_p || m_p || logs_p))
+    return fail(SVK_ERR_INVALID, "svk_infer_chunked: latents with max_len < T are not supported (use svk_infer)");
+  int64_t total = 0;
+  for (int t0 = 0; t0 < Tp; t0 += chunk_frames) {
+    const int t1 = t0 + chunk_frames < Tp ? t0 + chunk_frames : Tp;
+    SVK_TRY(svk_infer_window(h, mel, lengths, eps, noise_scale, B, T, max_len, t0, t1, o + (size_t)t0 * hop, (int64_t)hop * Tp,
+                             z ? z + t0 : nullptr, z_p ? z_p + t0 : nullptr, m_p ? m_p + t0 : nullptr,
+                             logs_p ? logs_p + t0 : nullptr, T, workspace, workspace_bytes, stream));
+    total += h->launches;
+  }
+  if (x_mask) {
+    const cudaError_t e = launch_sequence_mask(lengths, B, T, x_mask, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(SVK_ERR_CUDA, "svk_infer_chunked: %s", cudaGetErrorString(e));
+    total++;
+  }
+  h->launches = total;
+  return SVK_OK;
+}
+
 // ----------------------------------------------------------------------------- module-level ops
 extern "C" int svk_mel_encoder(svk_handle* h, const float* mel, const int64_t* lengths, int B, int T, float* x_out,
                                float* m, float* logs, float* mask, void* workspace, size_t workspace_bytes,

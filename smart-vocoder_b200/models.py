@@ -274,6 +274,67 @@ class SynthesizerTrn(nn.Module):
     def last_launch_count(self) -> int:
         return self._handle.last_launch_count() if self._handle else 0
 
+    # ------------------------------------------------------------------ chunked / streaming synthesis
+    def halo_frames(self) -> int:
+        """Frames of context per side that make a window's PCM equal to the whole-utterance result."""
+        self._need_cuda()
+        return int(rt.lib().svk_halo_frames(self._handle.ptr))
+
+    def _chunk_inputs(self, x, x_lengths, eps):
+        self._need_cuda(x, x_lengths)
+        x = self._f32(x, "x")
+        if x.dim() != 3 or x.shape[1] != self.dims.n_mel:
+            raise RuntimeError(f"expected input[B, {self.dims.n_mel}, T], got {list(x.shape)}")
+        B, _, T = x.shape
+        lengths = x_lengths.to(torch.int64).contiguous()
+        if eps is None:  # same single draw over the whole utterance as models.py:336
+            eps = torch.randn_like(torch.empty(B, self.dims.inter_channels, T, device=self._device, dtype=torch.float32))
+        eps = self._f32(eps, "eps")
+        if tuple(eps.shape) != (B, self.dims.inter_channels, T):
+            raise RuntimeError(f"eps: expected [{B}, {self.dims.inter_channels}, {T}], got {list(eps.shape)}")
+        return x, lengths, eps, B, T
+
+    def infer_chunked(self, x, x_lengths, chunk_frames=256, noise_scale=1, max_len=None, eps=None):
+        """``infer`` with bounded workspace: the time axis is walked in windows of ``chunk_frames`` frames, each
+        recomputed with ``halo_frames()`` frames of context, so the result equals ``infer`` on the same inputs
+        (svk_infer_chunked).  Same return value as ``infer`` (models.py:331-339)."""
+        x, lengths, eps, B, T = self._chunk_inputs(x, x_lengths, eps)
+        Tp = self._clip_len(T, max_len)
+        if B == 0 or T == 0 or Tp == 0:
+            raise ValueError("infer_chunked: empty batch / zero frames")
+        C, dev = self.dims.inter_channels, self._device
+        want_lat = Tp == T
+        lat = [torch.empty(B, C, T, device=dev, dtype=torch.float32) if want_lat else None for _ in range(4)]
+        x_mask = torch.empty(B, 1, T, device=dev, dtype=torch.float32)
+        o = torch.empty(B, 1, self.dims.hop * Tp, device=dev, dtype=torch.float32)
+        chunk = min(int(chunk_frames), Tp)
+        nbytes = int(rt.lib().svk_window_workspace_bytes(self._handle.ptr, B, chunk))
+        ws = self._ws.get(nbytes, dev)
+        with torch.cuda.device(dev):
+            rt.check(rt.lib().svk_infer_chunked(self._handle.ptr, _ptr(x), _ptr(lengths), _ptr(eps), float(noise_scale), B, T,
+                                                Tp, chunk, _ptr(o), _ptr(x_mask), _ptr(lat[0]), _ptr(lat[1]), _ptr(lat[2]),
+                                                _ptr(lat[3]), _ptr(ws), nbytes, self._stream()))
+        return o, x_mask, tuple(lat)
+
+    def infer_stream(self, x, x_lengths, chunk_frames=64, noise_scale=1, max_len=None, eps=None):
+        """Generator over PCM chunks ``[B, 1, hop * frames]`` in time order (svk_infer_window): the first audio is
+        available after one window instead of after the whole utterance.  Concatenated along time the chunks equal
+        ``infer``'s ``o`` on the same inputs."""
+        x, lengths, eps, B, T = self._chunk_inputs(x, x_lengths, eps)
+        Tp = self._clip_len(T, max_len)
+        chunk = max(1, min(int(chunk_frames), Tp))
+        nbytes = int(rt.lib().svk_window_workspace_bytes(self._handle.ptr, B, chunk))
+        ws = self._ws.get(nbytes, self._device)
+        hop = self.dims.hop
+        for t0 in range(0, Tp, chunk):
+            t1 = min(t0 + chunk, Tp)
+            o = torch.empty(B, 1, hop * (t1 - t0), device=self._device, dtype=torch.float32)
+            with torch.cuda.device(self._device):
+                rt.check(rt.lib().svk_infer_window(self._handle.ptr, _ptr(x), _ptr(lengths), _ptr(eps), float(noise_scale), B, T,
+                                                   Tp, t0, t1, _ptr(o), hop * (t1 - t0), None, None, None, None, 0, _ptr(ws),
+                                                   nbytes, self._stream()))
+            yield o
+
     # ------------------------------------------------------------------ sub-module views
     def _dec_forward(self, x, g=None):
         """Generator.forward(x, g=None) (models.py:141-160)."""

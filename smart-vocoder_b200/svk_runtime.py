@@ -85,6 +85,10 @@ SIGNATURES = {
     "svk_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "svk_infer": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "svk_infer_host": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "svk_halo_frames": (_i, [_vp]),
+    "svk_window_workspace_bytes": (_sz, [_vp, _i, _i]),
+    "svk_infer_window": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
+    "svk_infer_chunked": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "svk_last_launch_count": (_i64, [_vp]),
     "svk_profile_begin": (_i, [_vp, _i]),
     "svk_profile_end": (_i, [_vp, _vp, _i, ctypes.POINTER(_i)]),
