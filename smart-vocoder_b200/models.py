@@ -335,6 +335,22 @@ class SynthesizerTrn(nn.Module):
                                                    nbytes, self._stream()))
             yield o
 
+    def infer_window(self, x, x_lengths, eps, lo, hi, noise_scale=1):
+        """PCM ``[B, 1, hop * (hi - lo)]`` of frames [lo, hi) of ``x`` (svk_infer_window): equal to the same slice of
+        ``infer(x, ...)``'s output when ``x`` itself carries ``halo_frames()`` frames of context around [lo, hi) or
+        reaches the true sequence ends.  Building block of ``svk_parallel.time_sharded_infer``."""
+        x, lengths, eps, B, T = self._chunk_inputs(x, x_lengths, eps)
+        lo, hi = int(lo), int(hi)
+        nbytes = int(rt.lib().svk_window_workspace_bytes(self._handle.ptr, B, max(hi - lo, 1)))
+        ws = self._ws.get(nbytes, self._device)
+        hop = self.dims.hop
+        o = torch.empty(B, 1, hop * max(hi - lo, 0), device=self._device, dtype=torch.float32)
+        with torch.cuda.device(self._device):
+            rt.check(rt.lib().svk_infer_window(self._handle.ptr, _ptr(x), _ptr(lengths), _ptr(eps), float(noise_scale), B, T, 0,
+                                               lo, hi, _ptr(o), hop * (hi - lo), None, None, None, None, 0, _ptr(ws), nbytes,
+                                               self._stream()))
+        return o
+
     # ------------------------------------------------------------------ sub-module views
     def _dec_forward(self, x, g=None):
         """Generator.forward(x, g=None) (models.py:141-160)."""

@@ -8,6 +8,11 @@ process model mirrors its training launcher (one process per GPU, env:// rendezv
 
 `sharded_infer` is backend-agnostic: tests run it over gloo on CPU tensors with a stand-in
 `infer_fn`; bench.py runs it over NCCL with `SynthesizerTrn.infer`.
+
+`time_sharded_infer` shards ONE batch of very long utterances along time instead: rank r
+synthesises frames [t0_r, t1_r) from a window widened by `halo` frames of context per side (svk_halo_frames),
+which reproduces the whole-utterance result exactly, so again there is no data-path collective -- only the
+scatter of the overlapping input windows and the gather of the PCM segments.
 """
 from __future__ import annotations
 
@@ -84,4 +89,49 @@ def sharded_infer(infer_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tensor]
         _gather(pcm_local, [full[a:b] for a, b in bounds], root, group)
         return full
     _gather(pcm_local, None, root, group)
+    return None
+
+
+def time_shard_bounds(T: int, world_size: int, halo: int) -> List[Tuple[int, int, int, int]]:
+    """Per rank (t0, t1, a, b): frames [t0, t1) are the rank's own, [a, b) is the window it needs as input
+    (own frames + `halo` frames of context per side, clipped to [0, T))."""
+    out = []
+    for t0, t1 in shard_bounds(T, world_size):
+        if t1 > t0:
+            out.append((t0, t1, max(0, t0 - halo), min(T, t1 + halo)))
+        else:
+            out.append((t0, t1, t0, t1))
+    return out
+
+
+def time_sharded_infer(window_fn: Callable[[torch.Tensor, torch.Tensor, torch.Tensor, int, int], torch.Tensor],
+                       mel: Optional[torch.Tensor], lengths: Optional[torch.Tensor], eps: Optional[torch.Tensor],
+                       B: int, n_mel: int, n_lat: int, T: int, samples_per_frame: int, halo: int, device, root: int = 0,
+                       group=None) -> Optional[torch.Tensor]:
+    """Shard `mel [B, n_mel, T]` / `eps [B, n_lat, T]` / `lengths [B]` (on `root`) along TIME.  Every rank receives its
+    halo-widened window and the lengths as seen from the window start, and calls
+    `window_fn(mel_w, lengths_w, eps_w, lo, hi) -> pcm [B, 1, samples_per_frame * (hi - lo)]`, where [lo, hi) are its own
+    frames in window coordinates (SynthesizerTrn.infer_window does exactly this).  Root returns `[B, 1, spf * T]`."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    bounds = time_shard_bounds(T, world, halo)
+    t0, t1, a, b = bounds[rank]
+    w = b - a
+    mel_w = torch.empty(B, n_mel, w, device=device, dtype=torch.float32)
+    eps_w = torch.empty(B, n_lat, w, device=device, dtype=torch.float32)
+    len_w = torch.empty(B if w else 0, device=device, dtype=torch.int64)
+    if rank == root:
+        _scatter(mel_w, [mel[:, :, x:y].contiguous() for _, _, x, y in bounds], root, group)
+        _scatter(eps_w, [eps[:, :, x:y].contiguous() for _, _, x, y in bounds], root, group)
+        _scatter(len_w, [(lengths - x).clamp(0, y - x) if y > x else lengths[:0] for _, _, x, y in bounds], root, group)
+    else:
+        _scatter(mel_w, None, root, group)
+        _scatter(eps_w, None, root, group)
+        _scatter(len_w, None, root, group)
+    spf = samples_per_frame
+    pcm = window_fn(mel_w, len_w, eps_w, t0 - a, t1 - a) if t1 > t0 else torch.empty(B, 1, 0, device=device)
+    if rank == root:
+        parts = [torch.empty(B, 1, spf * (y - x), device=device, dtype=torch.float32) for x, y, _, _ in bounds]
+        _gather(pcm, parts, root, group)
+        return torch.cat(parts, dim=2)
+    _gather(pcm, None, root, group)
     return None

@@ -70,3 +70,71 @@ def test_shard_bounds():
         for w in range(1, 9):
             b = P.shard_bounds(n, w)
             assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+
+
+# ---------------------------------------------------------------------------------- time-axis sharding (8(f) rank 3)
+HALO = 5
+
+
+def _fake_full(mel, lengths, eps):
+    """Stand-in synthesiser with receptive field HALO frames per side and zero padding at the true ends."""
+    B, C, T = mel.shape
+    mask = (torch.arange(T)[None, :] < lengths[:, None]).float()[:, None, :]
+    x = (mel.sum(1, keepdim=True) + eps.sum(1, keepdim=True)) * mask
+    k = torch.arange(1, 2 * HALO + 2, dtype=torch.float32).view(1, 1, -1)
+    y = torch.nn.functional.conv1d(x, k, padding=HALO) * mask
+    return y.repeat_interleave(4, dim=2)
+
+
+def _fake_window(mel_w, len_w, eps_w, lo, hi):
+    return _fake_full(mel_w, len_w, eps_w)[:, :, 4 * lo:4 * hi].contiguous()
+
+
+def _time_worker(rank, world, port, T, q):
+    import sys
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import svk_parallel as P
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        B, C, CL = 3, 4, 2
+        g = torch.Generator().manual_seed(1)
+        mel = torch.randn(B, C, T, generator=g)
+        eps = torch.randn(B, CL, T, generator=g)
+        lengths = torch.tensor([T, max(T - 7, 0), T // 2], dtype=torch.int64)
+        out = P.time_sharded_infer(_fake_window, mel if rank == 0 else None, lengths if rank == 0 else None,
+                                   eps if rank == 0 else None, B, C, CL, T, 4, HALO, torch.device("cpu"))
+        if rank == 0:
+            q.put(bool(torch.equal(out, _fake_full(mel, lengths, eps))))
+        else:
+            assert out is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("T", [64, 33, 3, 1])
+def test_time_sharded_infer_gloo_world2(T):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_time_worker, args=(r, 2, port, T, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
+
+
+def test_time_shard_bounds():
+    import svk_parallel as P
+    assert P.time_shard_bounds(1000, 2, 110) == [(0, 500, 0, 610), (500, 1000, 390, 1000)]
+    assert P.time_shard_bounds(1, 2, 110) == [(0, 1, 0, 1), (1, 1, 1, 1)]
+    for T in (1, 7, 300):
+        for w in (1, 2, 8):
+            b = P.time_shard_bounds(T, w, 110)
+            assert b[0][0] == 0 and b[-1][1] == T
+            assert all(x[2] <= x[0] and x[1] <= x[3] and x[2] >= 0 and x[3] <= T for x in b)
