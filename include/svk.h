@@ -93,8 +93,9 @@ void svk_destroy(svk_handle *h);
 /* ---- weight ingress ------------------------------------------------------------------------
  * Replaces utils.load_checkpoint -> model.load_state_dict  (utils.py:18-43).
  * Called once per state_dict entry with the reference key name ("dec.ups.0.weight_v", ...) and a
- * HOST fp32 tensor.  Keys that are dead at inference (enc_q.*, *.cond_layer.*, dec.cond.*;
- * SURVEY App. C) are accepted and return SVK_IGNORED.  Shapes are checked. */
+ * HOST fp32 tensor.  Keys that no built path reads (*.cond_layer.*, dec.cond.*) are
+ * accepted and return SVK_IGNORED.  enc_q.* keys are optional: svk_infer never reads them, loading
+ * all of them enables svk_posterior_encoder.  Shapes are checked. */
 int svk_load_tensor(svk_handle *h, const char *key, const float *host_data, const int64_t *shape,
                     int ndim);
 /* Folds weight_norm (w = g * v / ||v||, norm over dims != 0; models.py:125, modules.py:128-145,
@@ -197,6 +198,19 @@ int svk_mel_encoder(svk_handle *h, const float *mel_dev, const int64_t *lengths_
 /* ResidualCouplingBlock.forward(reverse=True) (models.py:73-80), in place on z [B,inter,T]. */
 int svk_flow_reverse(svk_handle *h, float *z_dev, const float *mask_dev, int B, int T,
                      void *workspace_dev, size_t workspace_bytes, void *stream);
+/* ---- analysis direction -------------------------------------------------
+ * ResidualCouplingBlock.forward(reverse=False) (models.py:73-76), in place on z [B,inter,T]
+ * (log-determinants are identically zero for mean_only couplings and are not returned, as in the
+ * reference's block).  Workspace >= 5 * B * hidden * T floats. */
+int svk_flow_forward(svk_handle *h, float *z_dev, const float *mask_dev, int B, int T,
+                     void *workspace_dev, size_t workspace_bytes, void *stream);
+/* PosteriorEncoder.forward(x, x_lengths, g=None) (models.py:103-110): spec [B,spec_channels,T] linear
+ * spectrogram, eps [B,inter,T] = the randn_like draw of models.py:109 -> z = (m + eps*exp(logs))*mask,
+ * m, logs [B,inter,T], mask [B,1,T].  Needs the enc_q.* keys (optional for svk_infer; SVK_ERR_STATE
+ * if they were never loaded).  Workspace >= 5 * B * hidden * T floats. */
+int svk_posterior_encoder(svk_handle *h, const float *spec_dev, const int64_t *lengths_dev,
+                          const float *eps_dev, int B, int T, float *z_dev, float *m_dev, float *logs_dev,
+                          float *mask_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
 /* Generator.forward(x, g=None) (models.py:141-160): z [B,inter,L] -> o [B,1,hop*L]. */
 int svk_generator(svk_handle *h, const float *z_dev, int B, int L, float *o_dev, void *workspace_dev,
                   size_t workspace_bytes, void *stream);

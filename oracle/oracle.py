@@ -221,6 +221,40 @@ class Oracle:
                 trace.append(z)
         return z
 
+    def posterior_encoder(self, sd, d, spec, lengths, eps):
+        """PosteriorEncoder.forward with g=None (models.py:103-110) -> (z, m, logs, mask); ``eps`` is the randn_like draw."""
+        spec = self.arr(spec)
+        mask = self.arr(self.sequence_mask(lengths, spec.shape[2]))
+        w, b = self.conv_w(sd, "enc_q.pre")
+        x = self.conv1d(spec, w, b) * mask
+        x = self.wn(sd, "enc_q.enc", x, mask, 16, d.hidden_channels, 5)  # hard-coded 5, 1, 16 (models.py:312)
+        w, b = self.conv_w(sd, "enc_q.proj")
+        stats = self.conv1d(x, w, b) * mask
+        C = d.inter_channels
+        m, logs = np.ascontiguousarray(stats[:, :C]), np.ascontiguousarray(stats[:, C:])
+        z = (m + self.arr(eps) * np.exp(logs)) * mask
+        return z, m, logs, mask
+
+    def coupling_forward(self, sd, prefix: str, d, x, mask) -> np.ndarray:
+        """ResidualCouplingLayer.forward(reverse=False), mean_only (modules.py:324-339): x1 = m + x1 * exp(0) * mask."""
+        half = d.half
+        x0, x1 = x[:, :half], x[:, half:]
+        w, b = self.conv_w(sd, prefix + ".pre")
+        h = self.conv1d(x0, w, b) * mask
+        h = self.wn(sd, prefix + ".enc", h, mask, d.flow_layers, d.hidden_channels, d.wn_kernel)
+        w, b = self.conv_w(sd, prefix + ".post")
+        m = self.conv1d(h, w, b) * mask
+        x1 = m + x1 * self.dtype.type(1.0) * mask
+        return np.ascontiguousarray(np.concatenate([x0, x1], axis=1))
+
+    def flow_forward(self, sd, d, z, mask) -> np.ndarray:
+        """ResidualCouplingBlock.forward(reverse=False) (models.py:73-76): RCL0, Flip, RCL1, Flip, ..."""
+        z = self.arr(z)
+        for f in range(d.n_flows):
+            z = self.coupling_forward(sd, f"flow.flows.{2 * f}", d, z, mask)
+            z = self.flip(z)
+        return z
+
     def resblock1(self, sd, prefix: str, x, kernel: int, dilations: Sequence[int]) -> np.ndarray:
         """ResBlock1.forward with x_mask=None (modules.py:210-223)."""
         for l, dil in enumerate(dilations):

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(WO* WT * 32, 2) conv_ffma_kernel(const ConvArg
       const int tt = lane + 32 * n;
       const int gpos = t0 - a.pad + tt;
       float v = 0.f;
-      if (tt < XW && gpos >= 0 && gpos < a.Lin) {
+      if (tt < XW && gpos >= 0 && gpos < a.Lin && gch < a.x_C) {  // gch >= x_C: zero-padded input channels (Cin % 8 != 0)
         v = __ldg(xrow + gpos);
         v = v > 0.f ? v : v * slope;
         if (mrow) v *= __ldg(mrow + gpos);

@@ -65,6 +65,17 @@ __global__ void sample_kernel(const float* __restrict__ m, const float* __restri
   }
 }
 
+// PosteriorEncoder (models.py:109): z = (m + randn * exp(logs)) * x_mask, in the reference's evaluation order.
+__global__ void posterior_sample_kernel(const float* __restrict__ m, const float* __restrict__ logs,
+                                        const float* __restrict__ eps, const float* __restrict__ mask, int C, int T,
+                                        float* __restrict__ z, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = i % T, b = i / ((int64_t)C * T);
+    z[i] = __fmul_rn(__fadd_rn(m[i], __fmul_rn(eps[i], expf(logs[i]))), mask[b * T + t]);
+  }
+}
+
 // weight_norm fold: one CTA per dim-0 slice.
 __global__ void weight_norm_kernel(const float* __restrict__ v, const float* __restrict__ g,
                                    int64_t inner, float* __restrict__ w) {
@@ -198,6 +209,14 @@ cudaError_t launch_sample(const float* m, const float* logs, const float* eps, f
                           float* z_p, float* z, int64_t n, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   sample_kernel<<<ew_blocks(n), EW_THREADS, 0, s>>>(m, logs, eps, noise_scale, z_p, z, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_posterior_sample(const float* m, const float* logs, const float* eps, const float* mask, int B, int C,
+                                    int T, float* z, cudaStream_t s) {
+  const int64_t n = (int64_t)B * C * T;
+  if (n == 0) return cudaSuccess;
+  posterior_sample_kernel<<<ew_blocks(n), EW_THREADS, 0, s>>>(m, logs, eps, mask, C, T, z, n);
   return cudaGetLastError();
 }
 

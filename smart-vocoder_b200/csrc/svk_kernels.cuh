@@ -135,6 +135,8 @@ cudaError_t launch_window_lengths(const int64_t* lengths, int B, int64_t a, int6
 cudaError_t launch_flip(const float* x, int B, int C, int T, float* y, cudaStream_t s);
 cudaError_t launch_sample(const float* m, const float* logs, const float* eps, float noise_scale,
                           float* z_p, float* z, int64_t n, cudaStream_t s);
+cudaError_t launch_posterior_sample(const float* m, const float* logs, const float* eps, const float* mask, int B, int C,
+                                    int T, float* z, cudaStream_t s);
 cudaError_t launch_weight_norm(const float* v, const float* g, int64_t dim0, int64_t inner, float* w,
                                cudaStream_t s);
 cudaError_t launch_rq_spline(const float* x, const float* uw, const float* uh, const float* ud,

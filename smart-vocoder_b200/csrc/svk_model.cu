@@ -54,7 +54,8 @@ namespace {
 
 struct KeySpec {
   std::vector<int64_t> shape;
-  bool dead;
+  bool dead;      // never read on any built path: accepted and dropped
+  bool optional;  // enc_q.*: only the analysis direction (svk_posterior_encoder) reads them; infer works without
 };
 
 struct HostTensor {
@@ -76,7 +77,7 @@ struct PackedConv {
 };
 
 struct FlowLayers {
-  PackedConv pre, post;
+  PackedConv pre, post, post_fwd;  // post: negated (reverse pass subtracts m), post_fwd: as stored (forward adds m)
   std::vector<PackedConv> in, rs;
   int orient = 0;  // 1: this coupling sees the channel-reversed view (odd number of Flips before it)
 };
@@ -108,6 +109,10 @@ struct svk_handle {
 
   PackedConv pre_enc, proj, conv_pre, conv_post;
   std::vector<PackedConv> enc_in, enc_rs, ups;
+  // PosteriorEncoder (enc_q.*, models.py:83-110): packed when its keys were loaded
+  bool has_posterior = false;
+  PackedConv encq_pre, encq_proj;
+  std::vector<PackedConv> encq_in, encq_rs;
   std::vector<FlowLayers> flows;
   std::vector<ResBlock> resblocks;
 
@@ -140,11 +145,11 @@ struct svk_handle {
 namespace {
 
 void add_key(svk_handle* h, const std::string& key, std::vector<int64_t> shape) {
-  const bool dead = key.rfind("enc_q.", 0) == 0 || key.find(".cond_layer.") != std::string::npos ||
-                    key.rfind("dec.cond.", 0) == 0;
+  const bool dead = key.find(".cond_layer.") != std::string::npos || key.rfind("dec.cond.", 0) == 0;
+  const bool optional = !dead && key.rfind("enc_q.", 0) == 0;
   h->key_order.push_back(key);
-  h->spec[key] = KeySpec{std::move(shape), dead};
-  if (!dead) h->n_live++;
+  h->spec[key] = KeySpec{std::move(shape), dead, optional};
+  if (!dead && !optional) h->n_live++;
 }
 
 void add_wn_keys(svk_handle* h, const std::string& prefix, int hidden, int kernel, int n_layers, int gin) {
@@ -464,19 +469,25 @@ extern "C" int svk_load_tensor(svk_handle* h, const char* key, const float* host
 extern "C" int svk_weight_status(const svk_handle* h, int* n_live, int* n_loaded) {
   if (!h) return fail(SVK_ERR_INVALID, "null handle");
   if (n_live) *n_live = h->n_live;
-  if (n_loaded) *n_loaded = (int)h->raw.size();
+  if (n_loaded) {
+    int n = 0;
+    for (const auto& kv : h->raw) n += h->spec.at(kv.first).optional ? 0 : 1;
+    *n_loaded = n;
+  }
   return SVK_OK;
 }
 
 extern "C" int svk_finalize_weights(svk_handle* h) {
   if (!h) return fail(SVK_ERR_INVALID, "null handle");
   for (const auto& key : h->key_order)
-    if (!h->spec[key].dead && !h->raw.count(key)) return fail(SVK_ERR_STATE, "missing key '%s'", key.c_str());
+    if (!h->spec[key].dead && !h->spec[key].optional && !h->raw.count(key))
+      return fail(SVK_ERR_STATE, "missing key '%s'", key.c_str());
   const svk_config& c = h->cfg;
   const int half = c.inter_channels / 2;
   h->h_blob.clear();
   h->h_tcblob.clear();
   h->enc_in.clear(), h->enc_rs.clear(), h->ups.clear(), h->flows.clear(), h->resblocks.clear();
+  h->encq_in.clear(), h->encq_rs.clear(), h->has_posterior = false;
 
   Folded f;
   SVK_TRY(fold_layer(h, "enc_p.pre_enc", &f));
@@ -509,6 +520,7 @@ extern "C" int svk_finalize_weights(svk_handle* h) {
       L.post = pack_virtual(
           h, g.d1, g.d0, 1, [&](int o, int cc, int) { return -g.w[(size_t)o * g.d1 + cc]; },
           [&](int o) { return -g.b[o]; });
+      L.post_fwd = pack_plain(h, f);  // forward direction: x1 = m + x1 * mask (modules.py:336)
     }
     h->flows.push_back(std::move(L));
   }
@@ -537,6 +549,33 @@ extern "C" int svk_finalize_weights(svk_handle* h) {
     }
   SVK_TRY(fold_layer(h, "dec.conv_post", &f));
   h->conv_post = pack_plain(h, f);
+
+  // PosteriorEncoder(spec_channels, inter, hidden, 5, 1, 16) (models.py:312): optional keys, all or nothing
+  {
+    bool all = c.wn_kernel == 5, any = false;
+    for (const auto& key : h->key_order)
+      if (h->spec[key].optional) {
+        const bool have = h->raw.count(key) != 0;
+        all = all && have, any = any || have;
+      }
+    if (any && !all && c.wn_kernel == 5) return fail(SVK_ERR_STATE, "enc_q.* keys loaded only partially");
+    if (all) {
+      SVK_TRY(fold_layer(h, "enc_q.pre", &f));
+      {
+        // Cin = spec_channels (513) is padded to the FFMA kernel's 8-channel chunk with zero weights; the kernel
+        // reads input channels >= x_C as zeros
+        const Folded& g = f;
+        const int cin_pad = (g.d1 + 7) / 8 * 8;
+        h->encq_pre = pack_virtual(
+            h, cin_pad, g.d0, 1, [&](int o, int cc, int) { return cc < g.d1 ? g.w[(size_t)o * g.d1 + cc] : 0.f; },
+            [&](int o) { return g.b[o]; }, /*want_tc=*/false);
+      }
+      SVK_TRY(pack_wn(h, "enc_q.enc", 16, &h->encq_in, &h->encq_rs));
+      SVK_TRY(fold_layer(h, "enc_q.proj", &f));
+      h->encq_proj = pack_plain(h, f);
+      h->has_posterior = true;
+    }
+  }
 
   CUDA_TRY(cudaSetDevice(h->device));
   if (h->d_blob) cudaFree(h->d_blob);
@@ -1004,6 +1043,59 @@ void run_flow_reverse(Runner& R, float* z, const float* mask, int T, float* hbuf
   }
 }
 
+// PosteriorEncoder.forward, g=None (models.py:103-110): z = (m + eps * exp(logs)) * mask.
+void run_posterior_encoder(Runner& R, const float* spec, const float* eps, const float* mask, int T, float* hbuf,
+                           float* acts, float* out, float* z, float* m, float* logs, uint16_t* x_img, uint16_t* acts_img) {
+  svk_handle* h = R.h;
+  const svk_config& c = h->cfg;
+  const int H = c.hidden_channels, C = c.inter_channels;
+  ConvArgs a = R.base(h->encq_pre, spec, c.spec_channels, 0, T, T, 1, 0, T, T);  // x = pre(x) * x_mask
+  a.out_mask = mask, a.mask_stride = T;
+  a.e[0].y = hbuf, a.e[0].C = H, a.e[0].use_mask = 1;
+  R.run(a, SVK_LAYER_PRE_ENC);
+  const bool images = x_img && acts_img && R.wn_uses_images(h->encq_in, h->encq_rs);
+  if (images) R.note(launch_split_image(hbuf, R.B, H, T, 1.0f, x_img, h->planes(), R.stream));
+  R.wn(h->encq_in, h->encq_rs, hbuf, acts, out, mask, T, images ? x_img : nullptr, images ? acts_img : nullptr);
+  ConvArgs p = R.base(h->encq_proj, out, H, 0, T, T, 1, 0, T, T);  // stats = proj(x) * x_mask
+  p.out_mask = mask, p.mask_stride = T;
+  p.split = C;
+  p.e[0].y = m, p.e[0].C = C, p.e[0].use_mask = 1;
+  p.e[1].y = logs, p.e[1].C = C, p.e[1].use_mask = 1;
+  R.run(p, SVK_LAYER_PROJ);
+  R.note(launch_posterior_sample(m, logs, eps, mask, R.B, C, T, z, R.stream));
+}
+
+// ResidualCouplingBlock.forward(reverse=False) in place on z (models.py:73-76, modules.py:324-339): RCL0, Flip, RCL1, ...
+// Coupling fl has seen fl Flips; with an even number of flows that is the orientation the reverse pass packed
+// (n_flows - fl), so the same folded pre weights serve both directions and storage ends un-flipped.
+void run_flow_forward(Runner& R, float* z, const float* mask, int T, float* hbuf, float* acts, float* out,
+                      uint16_t* x_img = nullptr, uint16_t* acts_img = nullptr) {
+  svk_handle* h = R.h;
+  const svk_config& c = h->cfg;
+  const int H = c.hidden_channels, C = c.inter_channels, half = C / 2;
+  for (int fl = 0; fl < c.n_flows; ++fl) {
+    const FlowLayers& L = h->flows[fl];
+    ConvArgs a = R.base(L.pre, z, C, L.orient ? half : 0, T, T, 1, 0, T, T);
+    a.out_mask = mask, a.mask_stride = T;
+    a.e[0].y = hbuf, a.e[0].C = H, a.e[0].use_mask = 1;
+    const bool images = x_img && acts_img && R.wn_uses_images(L.in, L.rs);
+    if (images && L.pre.tc) a.e[0].split = x_img, a.e[0].split_slope = 1.0f;
+    R.run(a, SVK_LAYER_FLOW_PRE);
+    if (images && !L.pre.tc) R.note(launch_split_image(hbuf, R.B, H, T, 1.0f, x_img, h->planes(), R.stream));
+    R.wn(L.in, L.rs, hbuf, acts, out, mask, T, images ? x_img : nullptr, images ? acts_img : nullptr);
+    // x1 = m + x1 * exp(0) * mask = (post(h) + x1) * mask, written over x1's storage channels
+    ConvArgs p = R.base(L.post_fwd, out, H, 0, T, T, 1, 0, T, T);
+    p.out_mask = mask, p.mask_stride = T;
+    p.e[0].res = z, p.e[0].y = z, p.e[0].C = C, p.e[0].use_mask = 1;
+    if (L.orient) {
+      p.e[0].ch_off = half - 1, p.e[0].ch_sign = -1;
+    } else {
+      p.e[0].ch_off = half, p.e[0].ch_sign = 1;
+    }
+    R.run(p, SVK_LAYER_FLOW_POST);
+  }
+}
+
 }  // namespace
 
 // --------------------------------------------------------------------------------- the hot path
@@ -1313,6 +1405,44 @@ extern "C" int svk_flow_reverse(svk_handle* h, float* z, const float* mask, int 
       R.err = cudaMemcpyAsync(z, tmp, sizeof(float) * (size_t)B * c.inter_channels * T, cudaMemcpyDeviceToDevice, R.stream);
   }
   if (R.err != cudaSuccess) return fail(SVK_ERR_CUDA, "svk_flow_reverse: %s", cudaGetErrorString(R.err));
+  return SVK_OK;
+}
+
+extern "C" int svk_flow_forward(svk_handle* h, float* z, const float* mask, int B, int T, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  SVK_TRY(check_ready(h, "svk_flow_forward"));
+  if (!z || !mask || B <= 0 || T <= 0) return fail(SVK_ERR_INVALID, "svk_flow_forward: bad argument");
+  const svk_config& c = h->cfg;
+  if (c.n_flows & 1) return fail(SVK_ERR_INVALID, "svk_flow_forward: an odd number of flows is not supported");
+  const size_t n = align_up((size_t)B * c.hidden_channels * T, 64);
+  if (!workspace || workspace_bytes < 5 * n * sizeof(float)) return fail(SVK_ERR_WORKSPACE, "svk_flow_forward: workspace too small");
+  CUDA_TRY(cudaSetDevice(h->device));
+  float* ws = (float*)workspace;
+  h->launches = 0;
+  Runner R{h, (cudaStream_t)stream, B};
+  run_flow_forward(R, z, mask, T, ws, ws + n, ws + 2 * n, reinterpret_cast<uint16_t*>(ws + 3 * n),
+                   reinterpret_cast<uint16_t*>(ws + 4 * n));
+  if (R.err != cudaSuccess) return fail(SVK_ERR_CUDA, "svk_flow_forward: %s", cudaGetErrorString(R.err));
+  return SVK_OK;
+}
+
+extern "C" int svk_posterior_encoder(svk_handle* h, const float* spec, const int64_t* lengths, const float* eps, int B,
+                                     int T, float* z, float* m, float* logs, float* mask, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  SVK_TRY(check_ready(h, "svk_posterior_encoder"));
+  if (!h->has_posterior) return fail(SVK_ERR_STATE, "svk_posterior_encoder: enc_q.* weights were not loaded");
+  if (!spec || !lengths || !eps || !z || !m || !logs || !mask || B <= 0 || T <= 0)
+    return fail(SVK_ERR_INVALID, "svk_posterior_encoder: bad argument");
+  const size_t n = align_up((size_t)B * h->cfg.hidden_channels * T, 64);
+  if (!workspace || workspace_bytes < 5 * n * sizeof(float)) return fail(SVK_ERR_WORKSPACE, "svk_posterior_encoder: workspace too small");
+  CUDA_TRY(cudaSetDevice(h->device));
+  float* ws = (float*)workspace;
+  h->launches = 0;
+  Runner R{h, (cudaStream_t)stream, B};
+  R.note(launch_sequence_mask(lengths, B, T, mask, R.stream));
+  run_posterior_encoder(R, spec, eps, mask, T, ws, ws + n, ws + 2 * n, z, m, logs, reinterpret_cast<uint16_t*>(ws + 3 * n),
+                        reinterpret_cast<uint16_t*>(ws + 4 * n));
+  if (R.err != cudaSuccess) return fail(SVK_ERR_CUDA, "svk_posterior_encoder: %s", cudaGetErrorString(R.err));
   return SVK_OK;
 }
 

@@ -9,8 +9,8 @@ What is mirrored (reference file:line):
   * ``state_dict()`` / ``load_state_dict()`` surface   utils.py:18-43      (659 keys)
   * ``infer(x, x_lengths, sid, noise_scale, length_scale, noise_scale_w, max_len)``
         -> ``(o, x_mask, (z, z_p, m_p, logs_p))``      models.py:331-339
-  * sub-module calls ``dec(z)``, ``enc_p(x, x_lengths)``, ``flow(z, mask, reverse=True)``
-                                                       models.py:141-160, 35-47, 73-80
+  * sub-module calls ``dec(z)``, ``enc_p(x, x_lengths)``, ``flow(z, mask, reverse=True|False)``,
+    ``enc_q(spec, lengths)``                           models.py:141-160, 35-47, 73-80, 103-110
 
 All arithmetic runs in hand-written CUDA behind the C ABI of include/svk.h; PyTorch only owns the
 device buffers, the RNG draw and the stream.  Training-time methods are out of scope and raise.
@@ -129,6 +129,7 @@ class SynthesizerTrn(nn.Module):
         self.dec = _SubModule(self, self._dec_forward)
         self.enc_p = _SubModule(self, self._enc_p_forward)
         self.flow = _SubModule(self, self._flow_forward)
+        self.enc_q = _SubModule(self, self._enc_q_forward)
 
     # ------------------------------------------------------------------ nn.Module surface
     def _apply(self, fn, *args, **kwargs):
@@ -159,7 +160,7 @@ class SynthesizerTrn(nn.Module):
     def _upload(self):
         h = self._handle
         for k, v in self._sd.items():
-            if not W.is_dead_key(k):
+            if not W.is_dead_key(k) or W.is_posterior_key(k):  # enc_q.* is optional: only enc_q(...) reads it
                 h.load_tensor(k, v.detach().cpu().numpy())
         h.finalize()
 
@@ -385,19 +386,38 @@ class SynthesizerTrn(nn.Module):
         return xo, m, logs, mask
 
     def _flow_forward(self, x, x_mask, g=None, reverse=False):
-        """ResidualCouplingBlock.forward (models.py:73-80); only reverse=True is on the path."""
-        if not reverse:
-            raise NotImplementedError("flow forward (training direction) is out of scope; use reverse=True")
+        """ResidualCouplingBlock.forward (models.py:73-80): reverse=True is on the infer path, reverse=False is the
+        analysis direction (z -> z_p, models.py:323)."""
         self._need_cuda(x, x_mask)
         z = self._f32(x, "x").clone()
         mask = self._f32(x_mask, "x_mask")
         B, C, T = z.shape
         nbytes = self._handle.workspace_bytes(B, T, T)
         ws = self._ws.get(nbytes, self._device)
+        fn = rt.lib().svk_flow_reverse if reverse else rt.lib().svk_flow_forward
         with torch.cuda.device(self._device):
-            rt.check(rt.lib().svk_flow_reverse(self._handle.ptr, _ptr(z), _ptr(mask), B, T, _ptr(ws), nbytes,
-                                               self._stream()))
+            rt.check(fn(self._handle.ptr, _ptr(z), _ptr(mask), B, T, _ptr(ws), nbytes, self._stream()))
         return z
+
+    def _enc_q_forward(self, x, x_lengths, g=None):
+        """PosteriorEncoder.forward (models.py:103-110): linear spectrogram -> (z, m, logs, x_mask)."""
+        self._need_cuda(x, x_lengths)
+        x = self._f32(x, "x")
+        if x.dim() != 3 or x.shape[1] != self.dims.spec_channels:
+            raise RuntimeError(f"expected input[B, {self.dims.spec_channels}, T], got {list(x.shape)}")
+        B, _, T = x.shape
+        dev, C = self._device, self.dims.inter_channels
+        lengths = x_lengths.to(torch.int64).contiguous()
+        m = torch.empty(B, C, T, device=dev, dtype=torch.float32)
+        eps = torch.randn_like(m).contiguous()  # the draw of models.py:109
+        logs, z = torch.empty_like(m), torch.empty_like(m)
+        mask = torch.empty(B, 1, T, device=dev, dtype=torch.float32)
+        nbytes = self._handle.workspace_bytes(B, T, T)
+        ws = self._ws.get(nbytes, dev)
+        with torch.cuda.device(dev):
+            rt.check(rt.lib().svk_posterior_encoder(self._handle.ptr, _ptr(x), _ptr(lengths), _ptr(eps), B, T, _ptr(z), _ptr(m),
+                                                    _ptr(logs), _ptr(mask), _ptr(ws), nbytes, self._stream()))
+        return z, m, logs, mask
 
     # ------------------------------------------------------------------ out of scope (training)
     def forward(self, x, x_lengths, y, y_lengths, sid=None):

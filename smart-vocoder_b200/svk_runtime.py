@@ -94,6 +94,8 @@ SIGNATURES = {
     "svk_profile_end": (_i, [_vp, _vp, _i, ctypes.POINTER(_i)]),
     "svk_mel_encoder": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "svk_flow_reverse": (_i, [_vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
+    "svk_flow_forward": (_i, [_vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
+    "svk_posterior_encoder": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "svk_generator": (_i, [_vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "svk_resblock1_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "svk_resblock1": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _sz, _vp]),

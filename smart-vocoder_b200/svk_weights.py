@@ -161,6 +161,11 @@ def is_dead_key(key: str) -> bool:
     return key.startswith("enc_q.") or ".cond_layer." in key or key.startswith("dec.cond.")
 
 
+def is_posterior_key(key: str) -> bool:
+    """enc_q.* without its (gin-only) cond_layer: read only by the analysis direction (PosteriorEncoder, models.py:83-110)."""
+    return key.startswith("enc_q.") and ".cond_layer." not in key
+
+
 def _rng_for(seed: int, key: str) -> np.random.Generator:
     return np.random.Generator(np.random.Philox(key=[int(seed), zlib.crc32(key.encode())]))
 

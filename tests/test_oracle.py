@@ -127,3 +127,19 @@ def test_torch_port_matches_reference_golden(base_sd, base_dims):
     assert np.abs(o.numpy() - g["ref32_o"]).max() <= 1e-5
     assert np.abs(o.numpy() - g["ref64_o"]).max() <= 5e-5
     assert np.abs(z.numpy() - g["ref64_z"]).max() <= 5e-5
+
+
+# ---- analysis direction: PosteriorEncoder + flow forward ---------------------------
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 5e-5)])
+def test_oracle_posterior_and_flow_forward_match_reference(base_sd, base_dims, dtype, tol):
+    g = load_golden("posterior_base_b2_t24")
+    orc = Oracle(dtype)
+    z, m, logs, mask = orc.posterior_encoder(base_sd, base_dims, g["spec"], g["lengths"], g["eps"])
+    assert np.array_equal(mask.astype(np.float32), g["ref32_y_mask"])
+    for name, val in (("z", z), ("m_q", m), ("logs_q", logs)):
+        assert np.abs(val - g["ref64_" + name]).max() <= tol, name
+    z_p = orc.flow_forward(base_sd, base_dims, g["ref64_z"], mask)
+    assert np.abs(z_p - g["ref64_z_p"]).max() <= tol
+    if dtype is np.float64:  # the flow is a bijection: reverse(forward(z)) == z
+        back = orc.flow_reverse(base_sd, base_dims, z_p, mask)
+        assert np.abs(back - g["ref64_z"]).max() <= 1e-12
