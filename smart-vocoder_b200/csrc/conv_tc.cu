@@ -136,6 +136,9 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = hdr->tmem_base;
+  // PDL: everything above (and the weight producer below) touches only weights / biases, which no kernel of the
+  // stream writes; every role that reads activations or writes results first waits for the previous grid.
+  griddep_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------ weight producer: one bulk copy per (chunk, tap)
@@ -262,6 +265,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
       // lands exactly in the A stage layout.  Rows outside [0, L) are zero-filled by the TMA unit = the conv's zero padding
       // (leaky_relu and mask were applied when the image was written).
       if (warp == 2 && lane == 0) {
+        griddep_wait();
         const int total_q = n_my * nchunks;
         const int cg0 = a.x_ch_off >> 5, cgs = a.x_C >> 5;
         int as = 0;
@@ -285,6 +289,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
       // Group g stages chunks q = g, g+2, ... of this CTA's chunk sequence (q = tile * nchunks + chunk).
       // One task = one time row x all KC channels of the chunk: 32 independent coalesced loads in
       // flight per thread, then leaky_relu / mask / fp16 hi-lo split and 2 x 4 conflict-free 16 B stores.
+      griddep_wait();
       const int g = (warp - 2) >> 2;
       const int rp = tid - 64 - PROD_GROUP * g;
       const float slope = a.pre_slope;
@@ -346,6 +351,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
     // Narrow layers (several accumulator stages available) instead give whole tiles to alternating warp
     // groups, so the per-tile fixed latency (barrier wait, TMEM load, address set-up) of one group
     // overlaps the other group's tile.
+    griddep_wait();
     const int q4 = warp & 3;
     const int egroups = ta.epi_groups;                 // warp groups that take alternate tiles
     const int esplit = kEpiSplit / egroups;            // warps of one lane quarter sharing a tile's columns
@@ -915,11 +921,9 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
     if (a.x_C % 32 || a.x_ch_off % 32 || a.x_stride != a.Lin) return cudaErrorInvalidValue;
     cudaError_t e = tc_make_image_map(ta.x_split, a.B, a.x_C, a.Lin, ta.rows, ta.planes, &map);
     if (e != cudaSuccess) return e;
-    conv_tc_kernel<true><<<grid, THREADS_TMA, smem, stream>>>(ta, map);
-  } else {
-    conv_tc_kernel<false><<<grid, THREADS, smem, stream>>>(ta, map);
+    return launch_pdl(conv_tc_kernel<true>, grid, THREADS_TMA, smem, stream, ta, map);
   }
-  return cudaGetLastError();
+  return launch_pdl(conv_tc_kernel<false>, grid, THREADS, smem, stream, ta, map);
 }
 
 }  // namespace svk

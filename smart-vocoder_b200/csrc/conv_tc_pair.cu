@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = hdr->tmem_base;
+  griddep_launch_dependents();  // PDL, as in conv_tc.cu: only weights / biases are touched before griddep_wait()
 
   if (warp == 0) {
     // ------------------------------------------------ weight producer
@@ -208,6 +209,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
   } else if (warp < 4) {
     // ------------------------------------------------ x-image loader: one TMA box per 32-channel chunk
     if (warp == 2 && lane == 0) {
+      griddep_wait();
       int as = 0;
       uint32_t ph = 0;
       const int cgs = pa.C >> 5;
@@ -226,6 +228,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
     __syncwarp();
   } else {
     // ------------------------------------------------ epilogue warps
+    griddep_wait();
     const int q4 = warp & 3, part = (warp - 4) >> 2;  // TMEM lane quarter; which half of the 16-column chunks
     const int row = q4 * 32 + lane;
     const int nch = N >> 4, hc = nch >> 1;  // N = 32: one chunk per warp, N = 64: two
@@ -455,8 +458,7 @@ cudaError_t launch_conv_tc_pair(const ConvPairArgs& in, cudaStream_t stream) {
   cudaError_t e = tc_make_image_map(pa.x_img, pa.B, pa.C, pa.L, pa.rows1, 2, &map);
   if (e != cudaSuccess) return e;
   const int grid = pa.items < sm_count[dev] ? pa.items : sm_count[dev];
-  conv_tc_pair_kernel<<<grid, P_THREADS, smem, stream>>>(pa, map);
-  return cudaGetLastError();
+  return launch_pdl(conv_tc_pair_kernel, grid, P_THREADS, smem, stream, pa, map);
 }
 
 }  // namespace svk

@@ -157,6 +157,8 @@ int run_tc(const float* x, int B, int Cin, int L, const std::vector<float>& w_oc
   if (e == cudaSuccess) e = cudaMalloc((void**)&dbias, bpad.size() * 4);
   if (e == cudaSuccess) e = cudaMemcpyAsync(dimg, img.data(), img.size() * 2, cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess) e = cudaMemcpyAsync(dbias, bpad.data(), bpad.size() * 4, cudaMemcpyHostToDevice, s);
+  // the kernel reads weights / biases before its griddep_wait() (programmatic dependent launch): they must be in place
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   if (e == cudaSuccess) {
     ConvTcArgs ta;
     memset(&ta, 0, sizeof(ta));
