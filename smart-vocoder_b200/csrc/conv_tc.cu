@@ -40,6 +40,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "svk_kernels.cuh"
 #include "tc_common.cuh"
 
@@ -457,12 +459,134 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
         for (int e = 0; e < 16; ++e) q[e] = 0.f;
       }
     };
-    if (mode == MODE_STORE && have_cols) {
+    if (mode == MODE_STORE && have_cols && !(kTma && ta.epi_fast)) {
       la_load(r1);
       la_load(r2);
     }
 
-    for (int i = egroup; i < n_my; i += egroups) {
+    // ---- lean STORE epilogue (ta.epi_fast, chosen by launch_conv_tc): the decoder ResBlock convs -- one destination
+    // side, fp16 hi/lo planes, operand image out, optional fp32 residual in / fp32 tensor out, nothing else.  On the
+    // narrow stages the kernel is bound by how many instructions the epilogue warps issue per 16-column job (ncu:
+    // 440-620 in the generic code below, 76 % of all instructions), so this path keeps one address per tile (32-bit
+    // element offsets from the tensor bases), decodes one item per tile, ping-pongs two residual buffers instead of
+    // rotating three, and has no per-element predicates except the row bound.  Same arithmetic, same order.
+    auto store_fast = [&](auto res_tag, auto y_tag) {
+      constexpr bool RES = decltype(res_tag)::value, YOUT = decltype(y_tag)::value;
+      const EpiDesc& d = a.e[0];
+      const float* resb = d.res;  // may alias yb (in-place residual update: each element is read, then written, by one thread)
+      float* yb = d.y;
+      uint16_t* spb = d.split;
+      const uint32_t ystride = (uint32_t)a.y_stride;
+      const uint32_t lo_plane = (uint32_t)a.B * (uint32_t)d.C * ystride;  // halves between the hi and lo planes
+      const float slope = d.split_slope;
+      const int J = (n_hi - n_lo) >> 4;                                    // jobs per tile of this warp (even)
+      const uint32_t cgroups = (uint32_t)d.C >> 5;
+      float rA[16], rB[16];
+      // element offset of (first channel of this warp's columns, row) for item i; false when i is past the end
+      auto tile_off = [&](int i, uint32_t& off_clamped, uint32_t& off_row, int& t_out, int& b_out, int& ch_out) -> bool {
+        if (i >= n_my) return false;
+        int nt2, b2, tt2;
+        decode_item((int)blockIdx.x + i * (int)gridDim.x, ta.div_t, ta.div_b, nt2, b2, tt2);
+        const int t2 = tt2 * 128 + row;
+        const int ch = d.ch_off + nt2 * N + n_lo;
+        const uint32_t base = ((uint32_t)b2 * (uint32_t)d.C + (uint32_t)ch) * ystride;
+        off_clamped = base + (uint32_t)min(t2, a.Lout - 1);
+        off_row = base + (uint32_t)t2;
+        t_out = t2, b_out = b2, ch_out = ch;
+        return true;
+      };
+      auto load_res = [&](float (&r)[16], uint32_t off) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) r[e] = resb[off + (uint32_t)e * ystride];
+      };
+      uint32_t offc = 0, offr = 0, n_offc = 0, n_offr = 0;
+      int t = 0, b = 0, ch0 = 0, n_t = 0, n_b = 0, n_ch0 = 0;
+      bool have = tile_off(egroup, offc, offr, t, b, ch0);
+      if (RES && have) {
+        load_res(rA, offc);
+        load_res(rB, offc + 16u * ystride);
+      }
+      for (int i = egroup; have; i += egroups) {
+        const int s = i & (nacc - 1);
+        const bool have_next = tile_off(i + egroups, n_offc, n_offr, n_t, n_b, n_ch0);
+        const bool tin = t < a.Lout;
+        mbar_wait(&hdr->acc_full[s], (uint32_t)(i >> nacc_shift) & 1u);
+        tc_fence_after();
+        const uint32_t tsub = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(s * acc_cols) + (uint32_t)n_lo;
+        const float* bias_t = bias_s + (ch0 - d.ch_off);
+        auto job = [&](int j, float (&r)[16]) {
+          uint32_t m[16], c[16];
+          tmem_ld16(tsub + (uint32_t)(16 * j), m);
+          tmem_ld16(tsub + (uint32_t)(N + 16 * j), c);
+          const float4* b4 = reinterpret_cast<const float4*>(bias_t + 16 * j);
+          tmem_wait_ld();
+          if (j == J - 1) {  // every tcgen05.ld of this stage has completed: hand it back before the stores
+            tc_fence_before();
+            mbar_arrive(&hdr->acc_empty[s]);
+          }
+          float v[16];
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const float4 q = b4[e4];
+            v[4 * e4 + 0] = fmaf(__uint_as_float(m[4 * e4 + 0]) + __uint_as_float(c[4 * e4 + 0]), unscale, q.x);
+            v[4 * e4 + 1] = fmaf(__uint_as_float(m[4 * e4 + 1]) + __uint_as_float(c[4 * e4 + 1]), unscale, q.y);
+            v[4 * e4 + 2] = fmaf(__uint_as_float(m[4 * e4 + 2]) + __uint_as_float(c[4 * e4 + 2]), unscale, q.z);
+            v[4 * e4 + 3] = fmaf(__uint_as_float(m[4 * e4 + 3]) + __uint_as_float(c[4 * e4 + 3]), unscale, q.w);
+          }
+          if (RES) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] += r[e];
+            // refill this buffer with the residual of the job after next (same tile, or the group's next tile)
+            const int jn = j + 2;
+            if (jn < J) {
+              load_res(r, offc + (uint32_t)(16 * jn) * ystride);
+            } else if (have_next) {
+              load_res(r, n_offc + (uint32_t)(16 * (jn - J)) * ystride);
+            }
+          }
+          if (tin) {
+            if (YOUT) {
+              float* yp = yb + offr + (uint32_t)(16 * j) * ystride;
+#pragma unroll
+              for (int e = 0; e < 16; ++e) yp[(uint32_t)e * ystride] = v[e];
+            }
+            // leaky_relu(y) as fp16 hi/lo: 16 channels = two 16 B pieces of the 64 B image row, per plane
+            const uint32_t dch = (uint32_t)(ch0 + 16 * j);
+            uint16_t* sp = spb + (((uint32_t)b * cgroups + (dch >> 5)) * ystride + (uint32_t)t) * 32u + (dch & 31u);
+#pragma unroll
+            for (int g8 = 0; g8 < 2; ++g8) {
+              float w8[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) w8[e] = v[8 * g8 + e] > 0.f ? v[8 * g8 + e] : v[8 * g8 + e] * slope;
+              uint4 h, l;
+              split2(w8[0], w8[1], h.x, l.x);
+              split2(w8[2], w8[3], h.y, l.y);
+              split2(w8[4], w8[5], h.z, l.z);
+              split2(w8[6], w8[7], h.w, l.w);
+              *reinterpret_cast<uint4*>(sp + 8 * g8) = h;
+              *reinterpret_cast<uint4*>(sp + 8 * g8 + lo_plane) = l;
+            }
+          }
+        };
+        for (int j = 0; j < J; j += 2) {
+          job(j, rA);
+          job(j + 1, rB);
+        }
+        have = have_next;
+        offc = n_offc, offr = n_offr, t = n_t, b = n_b, ch0 = n_ch0;
+      }
+    };
+    const bool epi_fast = kTma && ta.epi_fast;  // only image-fed launches qualify: keep the converting variant lean
+    if constexpr (kTma) if (epi_fast) {
+      if (a.e[0].res) {
+        if (a.e[0].y) store_fast(std::true_type{}, std::true_type{});
+        else store_fast(std::true_type{}, std::false_type{});
+      } else {
+        store_fast(std::false_type{}, std::false_type{});
+      }
+    }
+
+    for (int i = egroup; i < n_my && !epi_fast; i += egroups) {
       const int s = i & (nacc - 1);
       int ntile, b, tt;
       decode_item((int)blockIdx.x + i * (int)gridDim.x, ta.div_t, ta.div_b, ntile, b, tt);
@@ -642,8 +766,30 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
           float v[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) v[e] = fmaf(__uint_as_float(m[e]) + __uint_as_float(c[e]), unscale, bv[e]);
+          if (sh == 2 && a.shuf_p == 1 && o0 + 16 <= a.Cout && (a.y_stride & 1) == 0) {
+            // stride-2 upsamplers (k = 4, p = 1): virtual channels (2 co, 2 co + 1) of row t are y[co, 2t - 1] and
+            // y[co, 2t].  Pair y[co, 2t] with the NEXT row's y[co, 2t + 1] (one lane shuffle) -> one aligned 8 B
+            // store per lane and channel, 256 contiguous bytes per warp instruction; the two ends of the warp's span
+            // (2 t_first - 1 and 2 t_last) are single floats.  All lanes take part in the shuffle; stores are predicated.
+            const int tq = 2 * t;
+#pragma unroll
+            for (int kc = 0; kc < 8; ++kc) {
+              const float nxt = __shfl_down_sync(0xffffffffu, v[2 * kc], 1);
+              float* yrow = ybase + (size_t)((o0 >> 1) + kc) * a.y_stride;
+              if (tin) {
+                if (lane == 0 && tq >= 1) yrow[tq - 1] = v[2 * kc];
+                if (lane < 31 && tq + 1 < a.shuf_Lout) {
+                  *reinterpret_cast<float2*>(yrow + tq) = make_float2(v[2 * kc + 1], nxt);
+                } else if (tq < a.shuf_Lout) {
+                  yrow[tq] = v[2 * kc + 1];
+                }
+              }
+            }
+          }
           if (!tin) continue;
-          if (sh == 8 && (a.shuf_p & 3) == 0) {
+          if (sh == 2 && a.shuf_p == 1 && o0 + 16 <= a.Cout && (a.y_stride & 1) == 0) {
+            // stored above
+          } else if (sh == 8 && (a.shuf_p & 3) == 0) {
 #pragma unroll
             for (int gq = 0; gq < 2; ++gq) {
               const int co = (o0 >> 3) + gq;
@@ -877,6 +1023,21 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
     ta.epi_groups = 1;
     for (int g = 2; g <= quarters; ++g)
       if (quarters % g == 0 && ta.nacc >= 2 * g && ta.nacc >= 4) ta.epi_groups = g;
+  }
+  {
+    // lean STORE epilogue: one destination side with an operand image out, optional fp32 residual in / fp32 out,
+    // full 16-column jobs in pairs, 32-bit element offsets
+    const EpiDesc& d = a.e[0];
+    const int quarters = (ta.x_split ? EPI_WARPS_TMA : EPI_WARPS) / 4, esplit = quarters / ta.epi_groups;
+    const int nch = ta.N / 16, hc = (nch + esplit - 1) / esplit;
+    static const bool allow = [] {
+      const char* e = getenv("SVK_EPI_FAST");
+      return !(e && e[0] == '0');
+    }();
+    ta.epi_fast = allow && a.mode == MODE_STORE && ta.planes == 2 && a.split == (1 << 30) && d.split && !d.res_img &&
+                  !d.acc_in && d.ch_sign == 1 && a.post_div == 1.0f && !a.act_tanh && !(d.use_mask && a.out_mask) &&
+                  (d.y == nullptr || d.res != nullptr) && a.Cout % ta.N == 0 && nch % esplit == 0 && hc % 2 == 0 &&
+                  2ull * a.B * d.C * (unsigned long long)a.y_stride < (1ull << 32) && ta.x_split != nullptr;
   }
   int cols = 32;
   while (cols < ta.nacc * ta.planes * ta.N) cols <<= 1;

@@ -89,6 +89,7 @@ struct ConvTcArgs {
                             // leaky_relu / mask were applied when it was written, c.x / pre_slope / in_mask unused
   // filled by launch_conv_tc:
   int rows, tmem_cols, na, nw, resident, items, ntiles_t, bias_bytes, bias_count, nacc, epi_groups, a_off;
+  int epi_fast;  // lean STORE epilogue (conv_tc.cu: the decoder ResBlock convs take it)
   FastDiv div_t, div_b;  // by ntiles_t and by B (work-item decoding)
 };
 int conv_tc_rows(int K, int dil);
