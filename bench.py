@@ -179,8 +179,10 @@ class ClockSampler:
         except OSError:
             pass
         if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm),
-                       power_w_max=max(power))
+            # median SM clock UNDER LOAD: the sampler also sees the idle stretch before the warm-up
+            load = [c for c, w in zip(sm, power) if w >= 0.5 * max(power)] or sm
+            out.update(sm_mhz=statistics.median(load), sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm),
+                       samples_under_load=len(load), power_w_max=max(power))
         return out
 
 
@@ -248,6 +250,13 @@ def run_b200_arm(args):
     samples_per_step_rank = B * dims.hop * T
 
     with torch.no_grad():
+        # The clock sampler starts BEFORE the warm-up: nvidia-smi's cold start takes seconds on a fresh box, and a GPU
+        # left idle that long drops its SM / memory clocks -- the warm-up steps must be the last thing before the timed
+        # region, not the sampler's start-up.
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            sampler.wait_started()
+        barrier()
         for i in range(Wm):  # identical to a timed step (the L2 flush too: its first use loads a torch module)
             flush.fill_(i & 0xFF)
             o = net.infer(mel_d, len_d, noise_scale=NOISE_SCALE)[0]
@@ -271,9 +280,6 @@ def run_b200_arm(args):
             recs = net._handle.profile_end() if profile else None
             return ev0.elapsed_time(ev1), recs, out
 
-        sampler = ClockSampler(local_rank) if rank == 0 else None
-        if sampler:
-            sampler.wait_started()
         elapsed_ms, _, o = timed_pass(False)
         # the same K steps again with a CUDA-event pair around every launch (roofline numbers); kept out of
         # `value` because event pairs serialise the stream at every launch boundary

@@ -341,6 +341,72 @@ static __global__ void __launch_bounds__(C1_THREADS) conv_cout1_kernel(const Con
   }
 }
 
+// Streaming variant for the shape dec.conv_post actually has (k = 7, pad = 3, long rows): no shared-memory staging
+// and no block-wide barriers -- a thread owns 4 consecutive outputs and reads, per input channel, the three aligned
+// float4 covering t-4 .. t+7 (neighbouring threads share them through L1; HBM sees every element once), so the
+// kernel is a pure stream with enough independent loads in flight to approach the HBM rate.
+constexpr int CS_THREADS = 256;
+template <int K, int PAD>
+static __global__ void __launch_bounds__(CS_THREADS) conv_cout1_stream_kernel(const ConvArgs a) {
+  static_assert(PAD <= 4 && K - PAD <= 5, "taps must lie inside t-4 .. t+7");
+  __shared__ float ws[64 * K];
+  const int Cin = a.Cin;
+  for (int i = threadIdx.x; i < Cin * K; i += CS_THREADS) ws[i] = a.wp[(size_t)i * a.CoutPad];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int t = (blockIdx.x * CS_THREADS + threadIdx.x) * 4;
+  if (t >= a.Lout) return;
+  const float slope = a.pre_slope;
+  const float* xb = a.x + ((size_t)b * a.x_C + a.x_ch_off) * a.x_stride;
+  const bool interior = t >= 4 && t + 8 <= a.Lin;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int c = 0; c < Cin; ++c) {
+    const float* xr = xb + (size_t)c * a.x_stride;
+    float v[12];
+    if (interior) {
+      const float4 f0 = __ldg(reinterpret_cast<const float4*>(xr + t - 4));
+      const float4 f1 = __ldg(reinterpret_cast<const float4*>(xr + t));
+      const float4 f2 = __ldg(reinterpret_cast<const float4*>(xr + t + 4));
+      v[0] = f0.x, v[1] = f0.y, v[2] = f0.z, v[3] = f0.w, v[4] = f1.x, v[5] = f1.y, v[6] = f1.z, v[7] = f1.w;
+      v[8] = f2.x, v[9] = f2.y, v[10] = f2.z, v[11] = f2.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        const int tt = t - 4 + i;
+        v[i] = (tt >= 0 && tt < a.Lin) ? __ldg(xr + tt) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * slope;
+    const float* w = ws + c * K;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const float wj = w[j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(wj, v[4 - PAD + i + j], acc[i]);  // x[t + i + j - pad]
+    }
+  }
+  const float bias = a.bias[0];
+  float* y = a.e[0].y + ((size_t)b * a.e[0].C + a.e[0].ch_off) * a.y_stride;
+  const float* om = a.out_mask ? a.out_mask + (size_t)b * a.mask_stride : nullptr;
+  float o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float q = acc[i] + bias;
+    if (a.post_div != 1.0f) q = q / a.post_div;
+    if (om && a.e[0].use_mask && t + i < a.Lout) q *= om[t + i];
+    o[i] = a.act_tanh ? tanhf(q) : q;
+  }
+  if (t + 3 < a.Lout && (a.y_stride & 3) == 0) {
+    *reinterpret_cast<float4*>(y + t) = make_float4(o[0], o[1], o[2], o[3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (t + i < a.Lout) y[t + i] = o[i];
+  }
+}
+
 static bool conv_cout1_applicable(const ConvArgs& a) {
   return a.Cout == 1 && a.mode == MODE_STORE && a.dil == 1 && a.K <= C1_MAXK && a.Cin % C1_CC == 0 && !a.in_mask &&
          !a.e[0].res && !a.e[0].acc_in && a.e[0].ch_sign == 1 && a.split > 0;
@@ -349,6 +415,13 @@ static bool conv_cout1_applicable(const ConvArgs& a) {
 cudaError_t launch_conv_ffma(const ConvArgs& a, cudaStream_t stream) {
   if (conv_cout1_applicable(a)) {
     if (a.B <= 0 || a.Lout <= 0) return cudaSuccess;
+    // taps must lie inside the three float4 a thread reads (t-4 .. t+7), rows must keep float4 loads aligned
+    const bool stream_ok = a.K == 7 && a.pad == 3 && a.Cin <= 64 && (a.x_stride & 3) == 0 && a.Lout == a.Lin &&
+                           (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
+    if (stream_ok) {  // dec.conv_post (models.py:135: Conv1d(ch, 1, 7, 1, padding=3))
+      conv_cout1_stream_kernel<7, 3><<<dim3((a.Lout + 4 * CS_THREADS - 1) / (4 * CS_THREADS), a.B), CS_THREADS, 0, stream>>>(a);
+      return cudaGetLastError();
+    }
     conv_cout1_kernel<<<dim3((a.Lout + C1_TILE - 1) / C1_TILE, a.B), C1_THREADS, 0, stream>>>(a);
     return cudaGetLastError();
   }

@@ -470,10 +470,12 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
     // 440-620 in the generic code below, 76 % of all instructions), so this path keeps one address per tile (32-bit
     // element offsets from the tensor bases), decodes one item per tile, ping-pongs two residual buffers instead of
     // rotating three, and has no per-element predicates except the row bound.  Same arithmetic, same order.
-    auto store_fast = [&](auto res_tag, auto y_tag) {
-      constexpr bool RES = decltype(res_tag)::value, YOUT = decltype(y_tag)::value;
+    auto store_fast = [&](auto res_tag, auto y_tag, auto acc_tag) {
+      constexpr bool RES = decltype(res_tag)::value, YOUT = decltype(y_tag)::value, ACC = decltype(acc_tag)::value;
       const EpiDesc& d = a.e[0];
       const float* resb = d.res;  // may alias yb (in-place residual update: each element is read, then written, by one thread)
+      const float* accb = d.acc_in;  // running sum over the stage's ResBlocks (models.py:150-155), may alias yb too
+      const float post_div = a.post_div;
       float* yb = d.y;
       uint16_t* spb = d.split;
       const uint32_t ystride = (uint32_t)a.y_stride;
@@ -482,6 +484,10 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
       const int J = (n_hi - n_lo) >> 4;                                    // jobs per tile of this warp (even)
       const uint32_t cgroups = (uint32_t)d.C >> 5;
       float rA[16], rB[16];
+      // ACC: the running-sum operand of the job after next is requested together with its residual into `ab` and
+      // folded into that residual buffer one job later (r = res + acc, as the generic path adds them)
+      float ab[16];
+      bool ab_pending = false;
       // element offset of (first channel of this warp's columns, row) for item i; false when i is past the end
       auto tile_off = [&](int i, uint32_t& off_clamped, uint32_t& off_row, int& t_out, int& b_out, int& ch_out) -> bool {
         if (i >= n_my) return false;
@@ -505,6 +511,10 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
       if (RES && have) {
         load_res(rA, offc);
         load_res(rB, offc + 16u * ystride);
+        if (ACC) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) rA[e] += accb[offc + (uint32_t)e * ystride], rB[e] += accb[offc + (uint32_t)(16 + e) * ystride];
+        }
       }
       for (int i = egroup; have; i += egroups) {
         const int s = i & (nacc - 1);
@@ -514,7 +524,12 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
         tc_fence_after();
         const uint32_t tsub = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(s * acc_cols) + (uint32_t)n_lo;
         const float* bias_t = bias_s + (ch0 - d.ch_off);
-        auto job = [&](int j, float (&r)[16]) {
+        auto job = [&](int j, float (&r)[16], float (&r_other)[16]) {
+          if (ACC && ab_pending) {  // the other buffer was refilled during the previous job: complete r = res + acc
+#pragma unroll
+            for (int e = 0; e < 16; ++e) r_other[e] += ab[e];
+            ab_pending = false;
+          }
           uint32_t m[16], c[16];
           tmem_ld16(tsub + (uint32_t)(16 * j), m);
           tmem_ld16(tsub + (uint32_t)(N + 16 * j), c);
@@ -538,11 +553,19 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
             for (int e = 0; e < 16; ++e) v[e] += r[e];
             // refill this buffer with the residual of the job after next (same tile, or the group's next tile)
             const int jn = j + 2;
-            if (jn < J) {
-              load_res(r, offc + (uint32_t)(16 * jn) * ystride);
-            } else if (have_next) {
-              load_res(r, n_offc + (uint32_t)(16 * (jn - J)) * ystride);
+            if (jn < J || have_next) {
+              const uint32_t off = jn < J ? offc + (uint32_t)(16 * jn) * ystride : n_offc + (uint32_t)(16 * (jn - J)) * ystride;
+              load_res(r, off);
+              if (ACC) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) ab[e] = accb[off + (uint32_t)e * ystride];
+                ab_pending = true;
+              }
             }
+          }
+          if (post_div != 1.0f) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = v[e] / post_div;
           }
           if (tin) {
             if (YOUT) {
@@ -569,8 +592,8 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
           }
         };
         for (int j = 0; j < J; j += 2) {
-          job(j, rA);
-          job(j + 1, rB);
+          job(j, rA, rB);
+          job(j + 1, rB, rA);
         }
         have = have_next;
         offc = n_offc, offr = n_offr, t = n_t, b = n_b, ch0 = n_ch0;
@@ -578,11 +601,13 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
     };
     const bool epi_fast = kTma && ta.epi_fast;  // only image-fed launches qualify: keep the converting variant lean
     if constexpr (kTma) if (epi_fast) {
-      if (a.e[0].res) {
-        if (a.e[0].y) store_fast(std::true_type{}, std::true_type{});
-        else store_fast(std::true_type{}, std::false_type{});
+      if (a.e[0].acc_in) {
+        store_fast(std::true_type{}, std::true_type{}, std::true_type{});
+      } else if (a.e[0].res) {
+        if (a.e[0].y) store_fast(std::true_type{}, std::true_type{}, std::false_type{});
+        else store_fast(std::true_type{}, std::false_type{}, std::false_type{});
       } else {
-        store_fast(std::false_type{}, std::false_type{});
+        store_fast(std::false_type{}, std::false_type{}, std::false_type{});
       }
     }
 
@@ -746,7 +771,66 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
         // (ConvTranspose1d polyphase form).
         const int sh = a.shuf_s;
         float* ybase = a.e[0].y + ((size_t)b * a.e[0].C + a.e[0].ch_off) * a.y_stride;
-        for (int n0 = n_lo; n0 < n_hi; n0 += 16) {
+        // Stride-2 upsamplers (k = 4, p = 1) with an operand image out -- the two launches that feed the narrow stages
+        // and are bound by epilogue instruction issue: row predicates and addresses are computed once per tile.
+        // Virtual channels (2 co, 2 co + 1) of row t are y[co, 2t - 1] and y[co, 2t]; y[co, 2t] is paired with the NEXT
+        // row's y[co, 2t + 1] (one lane shuffle) -> one aligned 8 B store per lane and channel, 256 contiguous bytes
+        // per warp instruction; the two ends of the warp's span are single floats.
+        const bool lean2 = sh == 2 && a.shuf_p == 1 && a.Cout % 16 == 0 && (a.y_stride & 1) == 0 && planes == 2 && a.e[0].split;
+        if (lean2) {
+          const int tq = 2 * t;
+          const bool p_first = tin && lane == 0 && tq >= 1;
+          const bool p_pair = tin && lane < 31 && tq + 1 < a.shuf_Lout;
+          const bool p_single = tin && !p_pair && tq < a.shuf_Lout;
+          const bool i0 = tin && tq >= 1 && tq - 1 < a.shuf_Lout, i1 = tin && tq < a.shuf_Lout;
+          const float sl = a.e[0].split_slope;
+          const size_t lo_plane = sp_plane * (size_t)a.e[0].C;
+          for (int n0 = n_lo; n0 < n_hi; n0 += 16) {
+            uint32_t m[16], c[16];
+            tmem_ld16(tsub + (uint32_t)n0, m);
+            tmem_ld16(tsub + (uint32_t)(N + n0), c);
+            const int o0 = o_tile + n0;
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + o0);
+            tmem_wait_ld();
+            float v[16];
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const float4 q = b4[e4];
+              v[4 * e4 + 0] = fmaf(__uint_as_float(m[4 * e4 + 0]) + __uint_as_float(c[4 * e4 + 0]), unscale, q.x);
+              v[4 * e4 + 1] = fmaf(__uint_as_float(m[4 * e4 + 1]) + __uint_as_float(c[4 * e4 + 1]), unscale, q.y);
+              v[4 * e4 + 2] = fmaf(__uint_as_float(m[4 * e4 + 2]) + __uint_as_float(c[4 * e4 + 2]), unscale, q.z);
+              v[4 * e4 + 3] = fmaf(__uint_as_float(m[4 * e4 + 3]) + __uint_as_float(c[4 * e4 + 3]), unscale, q.w);
+            }
+            float* yr = ybase + (size_t)(o0 >> 1) * a.y_stride + tq;
+#pragma unroll
+            for (int kc = 0; kc < 8; ++kc) {
+              const float nxt = __shfl_down_sync(0xffffffffu, v[2 * kc], 1);
+              if (p_pair) *reinterpret_cast<float2*>(yr) = make_float2(v[2 * kc + 1], nxt);
+              if (p_single) yr[0] = v[2 * kc + 1];
+              if (p_first) yr[-1] = v[2 * kc];
+              yr += a.y_stride;
+            }
+            // leaky_relu(y) as the stage's operand image: 8 real channels at two output steps (16 B per step and plane)
+            const int co0 = a.e[0].ch_off + (o0 >> 1);
+            uint16_t* sp = a.e[0].split + (((size_t)b * (a.e[0].C >> 5) + (co0 >> 5)) * a.y_stride + (tq - 1)) * 32 + (co0 & 31);
+#pragma unroll
+            for (int r2 = 0; r2 < 2; ++r2) {
+              if (r2 ? i1 : i0) {
+                float w8[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) w8[e] = v[2 * e + r2] > 0.f ? v[2 * e + r2] : v[2 * e + r2] * sl;
+                uint4 hq, lq;
+                split2(w8[0], w8[1], hq.x, lq.x);
+                split2(w8[2], w8[3], hq.y, lq.y);
+                split2(w8[4], w8[5], hq.z, lq.z);
+                split2(w8[6], w8[7], hq.w, lq.w);
+                *reinterpret_cast<uint4*>(sp + 32 * r2) = hq;
+                *reinterpret_cast<uint4*>(sp + 32 * r2 + lo_plane) = lq;
+              }
+            }
+          }
+        }
+        for (int n0 = n_lo; n0 < n_hi && !lean2; n0 += 16) {
           uint32_t m[16], c[16];
           tmem_ld16(tsub + (uint32_t)n0, m);
           if (planes == 2) {
@@ -766,30 +850,8 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
           float v[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) v[e] = fmaf(__uint_as_float(m[e]) + __uint_as_float(c[e]), unscale, bv[e]);
-          if (sh == 2 && a.shuf_p == 1 && o0 + 16 <= a.Cout && (a.y_stride & 1) == 0) {
-            // stride-2 upsamplers (k = 4, p = 1): virtual channels (2 co, 2 co + 1) of row t are y[co, 2t - 1] and
-            // y[co, 2t].  Pair y[co, 2t] with the NEXT row's y[co, 2t + 1] (one lane shuffle) -> one aligned 8 B
-            // store per lane and channel, 256 contiguous bytes per warp instruction; the two ends of the warp's span
-            // (2 t_first - 1 and 2 t_last) are single floats.  All lanes take part in the shuffle; stores are predicated.
-            const int tq = 2 * t;
-#pragma unroll
-            for (int kc = 0; kc < 8; ++kc) {
-              const float nxt = __shfl_down_sync(0xffffffffu, v[2 * kc], 1);
-              float* yrow = ybase + (size_t)((o0 >> 1) + kc) * a.y_stride;
-              if (tin) {
-                if (lane == 0 && tq >= 1) yrow[tq - 1] = v[2 * kc];
-                if (lane < 31 && tq + 1 < a.shuf_Lout) {
-                  *reinterpret_cast<float2*>(yrow + tq) = make_float2(v[2 * kc + 1], nxt);
-                } else if (tq < a.shuf_Lout) {
-                  yrow[tq] = v[2 * kc + 1];
-                }
-              }
-            }
-          }
           if (!tin) continue;
-          if (sh == 2 && a.shuf_p == 1 && o0 + 16 <= a.Cout && (a.y_stride & 1) == 0) {
-            // stored above
-          } else if (sh == 8 && (a.shuf_p & 3) == 0) {
+          if (sh == 8 && (a.shuf_p & 3) == 0) {
 #pragma unroll
             for (int gq = 0; gq < 2; ++gq) {
               const int co = (o0 >> 3) + gq;
@@ -1035,8 +1097,8 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
       return !(e && e[0] == '0');
     }();
     ta.epi_fast = allow && a.mode == MODE_STORE && ta.planes == 2 && a.split == (1 << 30) && d.split && !d.res_img &&
-                  !d.acc_in && d.ch_sign == 1 && a.post_div == 1.0f && !a.act_tanh && !(d.use_mask && a.out_mask) &&
-                  (d.y == nullptr || d.res != nullptr) && a.Cout % ta.N == 0 && nch % esplit == 0 && hc % 2 == 0 &&
+                  d.ch_sign == 1 && !a.act_tanh && !(d.use_mask && a.out_mask) && (d.y == nullptr || d.res != nullptr) &&
+                  (d.acc_in == nullptr || (d.res != nullptr && d.y != nullptr)) && a.Cout % ta.N == 0 && nch % esplit == 0 && hc % 2 == 0 &&
                   2ull * a.B * d.C * (unsigned long long)a.y_stride < (1ull << 32) && ta.x_split != nullptr;
   }
   int cols = 32;

@@ -259,10 +259,15 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
         tmem_wait_ld();
         float v[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          float q = fmaf(__uint_as_float(m[e]) + __uint_as_float(c[e]), pa.unscale1, bias_s[n0 + e]);
-          q = inside ? q : 0.f;                        // conv2 zero-pads xt outside [0, L)
-          v[e] = q > 0.f ? q : q * pa.xt_slope;        // leaky_relu between the convs (modules.py:216)
+        for (int e4 = 0; e4 < 4; ++e4) {
+          const float4 bq = reinterpret_cast<const float4*>(bias_s + n0)[e4];
+          const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float q = fmaf(__uint_as_float(m[4 * e4 + e]) + __uint_as_float(c[4 * e4 + e]), pa.unscale1, bb[e]);
+            q = inside ? q : 0.f;                              // conv2 zero-pads xt outside [0, L)
+            v[4 * e4 + e] = q > 0.f ? q : q * pa.xt_slope;      // leaky_relu between the convs (modules.py:216)
+          }
         }
         uint8_t* tile = a2_smem + (size_t)s * a2_buf + (size_t)(n0 >> 5) * a2_chunk;
         uint4* hi = reinterpret_cast<uint4*>(tile) + row * KG;
@@ -286,49 +291,95 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
       mbar_arrive(&hdr->acc1_empty[s]);
     };
 
-    // epi2 operands (residual, running sum), requested two chunk-jobs ahead of use
-    float r1[16], r2[16];
-    int la_i = 0, la_n0 = n_lo;
-    auto la_load = [&](float (&q)[16]) {
+    // epi2 operands (residual, running sum) are requested two chunk-jobs ahead of use into two buffers that the
+    // jobs of this warp use alternately (job q = tile * hc + chunk uses buffer q & 1 and refills it for job q + 2):
+    // no rotation moves, no zero fill -- the epilogue warps are instruction-bound on these narrow layers.
+    float rA[16], rB[16];
+    const int hc_shift = hc >> 1;  // hc is 1 or 2
+    auto load_ops = [&](float (&q)[16], int job) {
+      const int i = job >> hc_shift, n0 = n_lo + ((job & (hc - 1)) << 4);
+      if (i >= n_my) return;
+      int b, tt;
+      item_bt(i, b, tt);
+      const int t = min(tt * TO + row, pa.L - 1);  // clamped: always a valid address
+      const size_t off = ((size_t)b * pa.C + n0) * pa.L + t;
+      if (pa.res_img) {
+        const uint16_t* rp = pa.res_img + (((size_t)b * (pa.C >> 5) + (n0 >> 5)) * pa.L + t) * 32 + (n0 & 31);
 #pragma unroll
-      for (int e = 0; e < 16; ++e) q[e] = 0.f;
-      if (la_i < n_my) {
-        int b, tt;
-        item_bt(la_i, b, tt);
-        const int t = min(tt * TO + row, pa.L - 1);  // clamped: always a valid address
-        const size_t off = ((size_t)b * pa.C + la_n0) * pa.L + t;
-        if (pa.res_img) {
-          const uint16_t* rp = pa.res_img + (((size_t)b * (pa.C >> 5) + (la_n0 >> 5)) * pa.L + t) * 32 + (la_n0 & 31);
+        for (int g8 = 0; g8 < 2; ++g8) {
+          const uint4 hq = *reinterpret_cast<const uint4*>(rp + g8 * 8);
+          const uint4 lq = *reinterpret_cast<const uint4*>(rp + g8 * 8 + plane);
+          const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w}, lw[4] = {lq.x, lq.y, lq.z, lq.w};
 #pragma unroll
-          for (int g8 = 0; g8 < 2; ++g8) {
-            const uint4 hq = *reinterpret_cast<const uint4*>(rp + g8 * 8);
-            const uint4 lq = *reinterpret_cast<const uint4*>(rp + g8 * 8 + plane);
-            const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w}, lw[4] = {lq.x, lq.y, lq.z, lq.w};
-#pragma unroll
-            for (int e2 = 0; e2 < 4; ++e2) {
-              const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e2]));
-              const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e2]));
-              const float v0 = hf.x + lf.x, v1 = hf.y + lf.y;
-              q[8 * g8 + 2 * e2] = v0 >= 0.f ? v0 : v0 * r_inv;
-              q[8 * g8 + 2 * e2 + 1] = v1 >= 0.f ? v1 : v1 * r_inv;
-            }
+          for (int e2 = 0; e2 < 4; ++e2) {
+            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e2]));
+            const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e2]));
+            const float v0 = hf.x + lf.x, v1 = hf.y + lf.y;
+            q[8 * g8 + 2 * e2] = v0 >= 0.f ? v0 : v0 * r_inv;
+            q[8 * g8 + 2 * e2 + 1] = v1 >= 0.f ? v1 : v1 * r_inv;
           }
-        } else if (pa.res) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) q[e] = pa.res[off + (size_t)e * pa.L];
         }
-        if (pa.acc_in) {
+      } else if (pa.res) {
+        const float* rp = pa.res + off;
 #pragma unroll
-          for (int e = 0; e < 16; ++e) q[e] += pa.acc_in[off + (size_t)e * pa.L];
-        }
-        la_n0 += 16;
-        if (la_n0 >= n_hi) la_n0 = n_lo, ++la_i;
+        for (int e = 0; e < 16; ++e) q[e] = rp[(size_t)e * pa.L];
+      }
+      if (pa.acc_in) {
+        const float* ap = pa.acc_in + off;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) q[e] += ap[(size_t)e * pa.L];
       }
     };
-    la_load(r1);
-    la_load(r2);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) rA[e] = 0.f, rB[e] = 0.f;  // stays zero when the pair has no residual operand at all
+    load_ops(rA, 0);
+    load_ops(rB, 1);
 
     // epi2: conv2 accumulators -> y = conv2 + bias + x (+ running sum) (/ post_div) -> fp32 and/or image
+    const float4* bias2_4 = reinterpret_cast<const float4*>(bias_s + N);
+    auto epi2_job = [&](float (&r)[16], int job, int b, int t, bool valid, uint32_t tsub, int n0) {
+      uint32_t m[16], c[16];
+      tmem_ld16(tsub + (uint32_t)n0, m);
+      tmem_ld16(tsub + (uint32_t)(N + n0), c);
+      tmem_wait_ld();
+      float v[16];
+#pragma unroll
+      for (int e4 = 0; e4 < 4; ++e4) {
+        const float4 q = bias2_4[(n0 >> 2) + e4];
+        v[4 * e4 + 0] = fmaf(__uint_as_float(m[4 * e4 + 0]) + __uint_as_float(c[4 * e4 + 0]), pa.unscale2, q.x) + r[4 * e4 + 0];
+        v[4 * e4 + 1] = fmaf(__uint_as_float(m[4 * e4 + 1]) + __uint_as_float(c[4 * e4 + 1]), pa.unscale2, q.y) + r[4 * e4 + 1];
+        v[4 * e4 + 2] = fmaf(__uint_as_float(m[4 * e4 + 2]) + __uint_as_float(c[4 * e4 + 2]), pa.unscale2, q.z) + r[4 * e4 + 2];
+        v[4 * e4 + 3] = fmaf(__uint_as_float(m[4 * e4 + 3]) + __uint_as_float(c[4 * e4 + 3]), pa.unscale2, q.w) + r[4 * e4 + 3];
+      }
+      load_ops(r, job + 2);  // refill this buffer for the job after next
+      if (pa.post_div != 1.0f) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = v[e] / pa.post_div;
+      }
+      if (valid) {
+        if (pa.y_img) {
+          uint16_t* sp = pa.y_img + (((size_t)b * (pa.C >> 5) + (n0 >> 5)) * pa.L + t) * 32 + (n0 & 31);
+#pragma unroll
+          for (int g8 = 0; g8 < 2; ++g8) {
+            float w8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) w8[e] = v[8 * g8 + e] > 0.f ? v[8 * g8 + e] : v[8 * g8 + e] * pa.y_slope;
+            uint4 hq, lq;
+            split2(w8[0], w8[1], hq.x, lq.x);
+            split2(w8[2], w8[3], hq.y, lq.y);
+            split2(w8[4], w8[5], hq.z, lq.z);
+            split2(w8[6], w8[7], hq.w, lq.w);
+            *reinterpret_cast<uint4*>(sp + g8 * 8) = hq;
+            *reinterpret_cast<uint4*>(sp + g8 * 8 + plane) = lq;
+          }
+        }
+        if (pa.y) {
+          float* yp = pa.y + ((size_t)b * pa.C + n0) * pa.L + t;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) yp[(size_t)e * pa.L] = v[e];
+        }
+      }
+    };
     auto epi2 = [&](int i) {
       const int s = i & 1;
       int b, tt;
@@ -338,46 +389,13 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
       mbar_wait(&hdr->acc2_full[s], (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
       const uint32_t tsub = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(4 * N + s * 2 * N);
-      for (int n0 = n_lo; n0 < n_hi; n0 += 16) {
-        float p1[16];
-        la_load(p1);
-        uint32_t m[16], c[16];
-        tmem_ld16(tsub + (uint32_t)n0, m);
-        tmem_ld16(tsub + (uint32_t)(N + n0), c);
-        tmem_wait_ld();
-        float v[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e)
-          v[e] = fmaf(__uint_as_float(m[e]) + __uint_as_float(c[e]), pa.unscale2, bias_s[N + n0 + e]) + r1[e];
-        if (pa.post_div != 1.0f) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = v[e] / pa.post_div;
-        }
-        if (valid) {
-          if (pa.y_img) {
-            uint16_t* sp = pa.y_img + (((size_t)b * (pa.C >> 5) + (n0 >> 5)) * pa.L + t) * 32 + (n0 & 31);
-#pragma unroll
-            for (int g8 = 0; g8 < 2; ++g8) {
-              float w8[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) w8[e] = v[8 * g8 + e] > 0.f ? v[8 * g8 + e] : v[8 * g8 + e] * pa.y_slope;
-              uint4 hq, lq;
-              split2(w8[0], w8[1], hq.x, lq.x);
-              split2(w8[2], w8[3], hq.y, lq.y);
-              split2(w8[4], w8[5], hq.z, lq.z);
-              split2(w8[6], w8[7], hq.w, lq.w);
-              *reinterpret_cast<uint4*>(sp + g8 * 8) = hq;
-              *reinterpret_cast<uint4*>(sp + g8 * 8 + plane) = lq;
-            }
-          }
-          if (pa.y) {
-            float* yp = pa.y + ((size_t)b * pa.C + n0) * pa.L + t;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) yp[(size_t)e * pa.L] = v[e];
-          }
-        }
-#pragma unroll
-        for (int e = 0; e < 16; ++e) r1[e] = r2[e], r2[e] = p1[e];
+      if (hc == 2) {
+        epi2_job(rA, 2 * i, b, t, valid, tsub, n_lo);
+        epi2_job(rB, 2 * i + 1, b, t, valid, tsub, n_lo + 16);
+      } else if (i & 1) {
+        epi2_job(rB, i, b, t, valid, tsub, n_lo);
+      } else {
+        epi2_job(rA, i, b, t, valid, tsub, n_lo);
       }
       tc_fence_before();
       mbar_arrive(&hdr->acc2_empty[s]);
