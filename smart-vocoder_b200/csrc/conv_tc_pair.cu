@@ -13,8 +13,9 @@
 //   recomputed per item), its epilogue turns them into conv2's A tile IN SHARED MEMORY (bias, zero outside
 //   [0, L) = conv2's padding, leaky_relu, hi/lo split, swizzled stores, fence.proxy.async), conv2 runs
 //   on that tile, its epilogue is the usual residual / running-sum / image store.
-//   The MMA warp issues conv1(i+1) before conv2(i), the epilogue warps run epi1(i+1) before epi2(i), so
-//   each accumulator set is drained while the other one is being filled.
+//   The MMA warp issues conv1(i+1) before conv2(i); two role-specialised groups of four epilogue warps run epi1
+//   (conv1's accumulators -> xt tile) and epi2 (conv2's accumulators -> output) over all items independently, so
+//   two items are in flight: epi1(i+1) under conv2(i)'s MMAs, epi2(i) under conv1(i+2)'s.
 #include <string.h>
 
 #include "svk_kernels.cuh"
@@ -28,6 +29,7 @@ constexpr int P_NA_MAX = 8, P_MAXNW = 32;
 constexpr int P_EPI_WARPS = 8;
 constexpr int P_THREADS = 128 + 32 * P_EPI_WARPS;
 constexpr int P_EPI_THREADS = 32 * P_EPI_WARPS;
+constexpr int P_EPI_GROUP = P_EPI_THREADS / 2;  // warps 4..7 run epi1 (xt tile), warps 8..11 run epi2 (output)
 
 struct __align__(8) PairHeader {
   uint64_t a_full[P_NA_MAX], a_empty[P_NA_MAX];
@@ -62,9 +64,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
     for (int i = 0; i < na; ++i) mbar_init(&hdr->a_full[i], 1), mbar_init(&hdr->a_empty[i], 1);
     for (int i = 0; i < P_MAXNW; ++i) mbar_init(&hdr->w_full[i], 1), mbar_init(&hdr->w_empty[i], 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&hdr->acc1_full[i], 1), mbar_init(&hdr->acc1_empty[i], P_EPI_THREADS);
-      mbar_init(&hdr->a2_full[i], P_EPI_THREADS), mbar_init(&hdr->a2_empty[i], 1);
-      mbar_init(&hdr->acc2_full[i], 1), mbar_init(&hdr->acc2_empty[i], P_EPI_THREADS);
+      mbar_init(&hdr->acc1_full[i], 1), mbar_init(&hdr->acc1_empty[i], P_EPI_GROUP);
+      mbar_init(&hdr->a2_full[i], P_EPI_GROUP), mbar_init(&hdr->a2_empty[i], 1);
+      mbar_init(&hdr->acc2_full[i], 1), mbar_init(&hdr->acc2_empty[i], P_EPI_GROUP);
     }
     fence_barrier_init();
   }
@@ -166,6 +168,27 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
         mbar_wait_u32(bar_a_full + 8u * ast, aph);
         tc_fence_after();
         uint32_t ah = a1_lo0 + (uint32_t)ast * a1_stage16;
+        if (resident && i > 0) {
+          // resident weights, already seen: nothing to wait for or release per tap.  These narrow MMAs take ~46 cycles,
+          // so the issuing lane is the bottleneck: bare loop, 4 MMAs + 2 adds per tap (as in conv_tc.cu)
+          if (leader) {
+            uint32_t bw = w_lo0 + (uint32_t)(ch * K) * w_stage16;
+            const uint32_t dstep = (uint32_t)pa.dil1 * 4u;
+#pragma unroll 1
+            for (int j = 0; j < K; ++j) {
+              umma_f16_lo(dmain, ah, bw, a_hi, b_hi, idesc2, acc);
+              umma_f16_lo(dmain + (uint32_t)N, ah + lo1_16, bw, a_hi, b_hi, idesc1, 1u);
+              umma_f16_lo(dmain, ah + ks_a16, bw + ks_b16, a_hi, b_hi, idesc2, 1u);
+              umma_f16_lo(dmain + (uint32_t)N, ah + ks_a16 + lo1_16, bw + ks_b16, a_hi, b_hi, idesc1, 1u);
+              acc = 1u;
+              ah += dstep, bw += w_stage16;
+            }
+            umma_commit_u32(bar_a_empty + 8u * ast);
+          }
+          acc = 1u;
+          if (++ast == na) ast = 0, aph ^= 1;
+          continue;
+        }
         for (int j = 0; j < K; ++j) {
           const int slot = w_acquire(0, ch * K + j, i == 0);
           if (leader) tap(dmain, ah, lo1_16, slot, acc);
@@ -187,6 +210,22 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
       uint32_t acc = 0;
       for (int ch = 0; ch < nchunks; ++ch) {
         uint32_t ah = a2_lo0 + (uint32_t)s * a2_buf16 + (uint32_t)ch * a2_chunk16;
+        if (resident && i > 0) {
+          if (leader) {
+            uint32_t bw = w_lo0 + (uint32_t)(per + ch * K) * w_stage16;
+#pragma unroll 1
+            for (int j = 0; j < K; ++j) {
+              umma_f16_lo(dmain, ah, bw, a_hi, b_hi, idesc2, acc);
+              umma_f16_lo(dmain + (uint32_t)N, ah + lo2_16, bw, a_hi, b_hi, idesc1, 1u);
+              umma_f16_lo(dmain, ah + ks_a16, bw + ks_b16, a_hi, b_hi, idesc2, 1u);
+              umma_f16_lo(dmain + (uint32_t)N, ah + ks_a16 + lo2_16, bw + ks_b16, a_hi, b_hi, idesc1, 1u);
+              acc = 1u;
+              ah += 4u, bw += w_stage16;
+            }
+          }
+          acc = 1u;
+          continue;
+        }
         for (int j = 0; j < K; ++j) {
           const int slot = w_acquire(1, ch * K + j, i == 0);
           if (leader) tap(dmain, ah, lo2_16, slot, acc);
@@ -229,10 +268,14 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
   } else {
     // ------------------------------------------------ epilogue warps
     griddep_wait();
-    const int q4 = warp & 3, part = (warp - 4) >> 2;  // TMEM lane quarter; which half of the 16-column chunks
+    // Two role-specialised groups of four warps (one per TMEM lane quarter), each walking ALL items: group 0 turns
+    // conv1's accumulators into conv2's A tile (epi1), group 1 stores conv2's result (epi2).  Alternating both jobs on
+    // the same warps kept only one item in flight (conv1 -> epi1 -> conv2 -> epi2 is a serial chain of ~4000 cycles per
+    // item); split, epi1(i+1) runs under conv2(i)'s MMAs and epi2(i) under conv1(i+2)'s.
+    const int q4 = warp & 3, role2 = (warp - 4) >> 2;
     const int row = q4 * 32 + lane;
-    const int nch = N >> 4, hc = nch >> 1;  // N = 32: one chunk per warp, N = 64: two
-    const int n_lo = part * hc * 16, n_hi = n_lo + hc * 16;
+    const int hc = N >> 4;  // 16-column jobs per item and warp: 2 (N = 32) or 4 (N = 64)
+    const int n_lo = 0, n_hi = N;
     const size_t plane = (size_t)pa.B * pa.C * pa.L;  // halves between the hi and lo planes of an image
     const float r_inv = pa.res_img ? 1.0f / pa.res_slope : 1.0f;
 
@@ -295,7 +338,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
     // jobs of this warp use alternately (job q = tile * hc + chunk uses buffer q & 1 and refills it for job q + 2):
     // no rotation moves, no zero fill -- the epilogue warps are instruction-bound on these narrow layers.
     float rA[16], rB[16];
-    const int hc_shift = hc >> 1;  // hc is 1 or 2
+    const int hc_shift = hc >> 1;  // log2(hc): hc is 2 or 4
     auto load_ops = [&](float (&q)[16], int job) {
       const int i = job >> hc_shift, n0 = n_lo + ((job & (hc - 1)) << 4);
       if (i >= n_my) return;
@@ -332,8 +375,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
     };
 #pragma unroll
     for (int e = 0; e < 16; ++e) rA[e] = 0.f, rB[e] = 0.f;  // stays zero when the pair has no residual operand at all
-    load_ops(rA, 0);
-    load_ops(rB, 1);
+    if (role2 == 1) {
+      load_ops(rA, 0);
+      load_ops(rB, 1);
+    }
 
     // epi2: conv2 accumulators -> y = conv2 + bias + x (+ running sum) (/ post_div) -> fp32 and/or image
     const float4* bias2_4 = reinterpret_cast<const float4*>(bias_s + N);
@@ -389,22 +434,18 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
       mbar_wait(&hdr->acc2_full[s], (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
       const uint32_t tsub = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(4 * N + s * 2 * N);
-      if (hc == 2) {
-        epi2_job(rA, 2 * i, b, t, valid, tsub, n_lo);
-        epi2_job(rB, 2 * i + 1, b, t, valid, tsub, n_lo + 16);
-      } else if (i & 1) {
-        epi2_job(rB, i, b, t, valid, tsub, n_lo);
-      } else {
-        epi2_job(rA, i, b, t, valid, tsub, n_lo);
+      for (int k = 0; k < hc; k += 2) {  // jobs of an item alternate between the two operand buffers
+        epi2_job(rA, hc * i + k, b, t, valid, tsub, 16 * k);
+        epi2_job(rB, hc * i + k + 1, b, t, valid, tsub, 16 * k + 16);
       }
       tc_fence_before();
       mbar_arrive(&hdr->acc2_empty[s]);
     };
 
-    if (n_my > 0) epi1(0);
-    for (int i = 0; i < n_my; ++i) {
-      if (i + 1 < n_my) epi1(i + 1);
-      epi2(i);
+    if (role2 == 0) {
+      for (int i = 0; i < n_my; ++i) epi1(i);
+    } else {
+      for (int i = 0; i < n_my; ++i) epi2(i);
     }
   }
 

@@ -119,6 +119,7 @@ struct svk_handle {
   int64_t launches = 0;
   bool fuse_pairs = true;  // fused ResBlock conv pairs on the narrow stages ($SVK_FUSE_PAIRS=0 disables: A/B measurements)
   bool fuse_pairs_all = false;
+  bool fuse_pairs_c32 = false;  // every kernel size of the C = 32 stage too (its weights stay resident in the pair kernel)
 
   // svk_profile_begin/end state
   bool profiling = false;
@@ -423,7 +424,8 @@ extern "C" int svk_create(const svk_config* cfg, int device, svk_handle** out) {
   svk_handle* h = new svk_handle();
   h->cfg = c;
   h->device = device;
-  if (const char* e = getenv("SVK_FUSE_PAIRS")) h->fuse_pairs = atoi(e) != 0, h->fuse_pairs_all = atoi(e) == 2;
+  if (const char* e = getenv("SVK_FUSE_PAIRS"))
+    h->fuse_pairs = atoi(e) != 0, h->fuse_pairs_all = atoi(e) == 2, h->fuse_pairs_c32 = atoi(e) == 3;
   build_key_spec(h);
   *out = h;
   return SVK_OK;
@@ -701,7 +703,7 @@ struct Runner {
     // Fusing removes HBM traffic but not MMA work (and recomputes a (K-1)-row halo per item).  Measured at
     // 16 x 1024 frames: k = 3 pairs are HBM-bound and gain 25 %, k >= 7 pairs are bound by the per-MMA floor of
     // narrow tiles and lose 0-25 %  ->  only the 3-tap blocks are fused ($SVK_FUSE_PAIRS=2 fuses every block).
-    if (h->fuse_pairs_all == false && rb.k > 3) return false;
+    if (h->fuse_pairs_all == false && rb.k > 3 && !(h->fuse_pairs_c32 && rb.C == 32)) return false;
     return conv_tc_pair_supported(rb.C, rb.k, rb.dil[l]) && rb.c1[l].tc && rb.c2[l].tc && rb.c1[l].tc_N == rb.C &&
            rb.c2[l].tc_N == rb.C;
   }
