@@ -576,19 +576,19 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
             // leaky_relu(y) as fp16 hi/lo: 16 channels = two 16 B pieces of the 64 B image row, per plane
             const uint32_t dch = (uint32_t)(ch0 + 16 * j);
             uint16_t* sp = spb + (((uint32_t)b * cgroups + (dch >> 5)) * ystride + (uint32_t)t) * 32u + (dch & 31u);
+            uint4 h[2], l[2];
 #pragma unroll
             for (int g8 = 0; g8 < 2; ++g8) {
               float w8[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) w8[e] = v[8 * g8 + e] > 0.f ? v[8 * g8 + e] : v[8 * g8 + e] * slope;
-              uint4 h, l;
-              split2(w8[0], w8[1], h.x, l.x);
-              split2(w8[2], w8[3], h.y, l.y);
-              split2(w8[4], w8[5], h.z, l.z);
-              split2(w8[6], w8[7], h.w, l.w);
-              *reinterpret_cast<uint4*>(sp + 8 * g8) = h;
-              *reinterpret_cast<uint4*>(sp + 8 * g8 + lo_plane) = l;
+              split2(w8[0], w8[1], h[g8].x, l[g8].x);
+              split2(w8[2], w8[3], h[g8].y, l[g8].y);
+              split2(w8[4], w8[5], h[g8].z, l[g8].z);
+              split2(w8[6], w8[7], h[g8].w, l[g8].w);
             }
+            st_global_v8(sp, h[0], h[1]);  // 16 channels = one 32 B sector per plane, one request each
+            st_global_v8(sp + lo_plane, l[0], l[1]);
           }
         };
         for (int j = 0; j < J; j += 2) {
@@ -668,24 +668,24 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
           if (io_c.sp && tin) {
             // second output: leaky_relu(y) as fp16 hi/lo, 8 channels = one 16 B row of the operand image
             uint16_t* sp = io_c.sp;
+            uint4 h[2], l[2];
 #pragma unroll
             for (int g8 = 0; g8 < 2; ++g8) {
               float w8[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) w8[e] = v[8 * g8 + e] > 0.f ? v[8 * g8 + e] : v[8 * g8 + e] * io_c.sp_slope;
               if (planes == 2) {
-                uint4 h, l;
-                split2(w8[0], w8[1], h.x, l.x);
-                split2(w8[2], w8[3], h.y, l.y);
-                split2(w8[4], w8[5], h.z, l.z);
-                split2(w8[6], w8[7], h.w, l.w);
-                *reinterpret_cast<uint4*>(sp) = h;
-                *reinterpret_cast<uint4*>(sp + sp_plane * (size_t)a.e[o_tile + n0 >= a.split ? 1 : 0].C) = l;
+                split2(w8[0], w8[1], h[g8].x, l[g8].x);
+                split2(w8[2], w8[3], h[g8].y, l[g8].y);
+                split2(w8[4], w8[5], h[g8].z, l[g8].z);
+                split2(w8[6], w8[7], h[g8].w, l[g8].w);
               } else {
-                *reinterpret_cast<uint4*>(sp) = pack_bf16x8(w8);
+                h[g8] = pack_bf16x8(w8);
               }
-              sp += 8;  // next 8 channels of the same 64 B image row
             }
+            // 16 channels = one 32 B sector of the 64 B image row, written as one request per plane
+            st_global_v8(sp, h[0], h[1]);
+            if (planes == 2) st_global_v8(sp + sp_plane * (size_t)a.e[o_tile + n0 >= a.split ? 1 : 0].C, l[0], l[1]);
           }
           if (!io_c.y) {
             // operand image only
@@ -744,21 +744,20 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
             // acts as the operand image of the res_skip conv (modules.py:169): no fp32 copy needed
             const int gch0 = a.e[0].ch_off + ntile * hN + n0;
             uint16_t* sp = a.e[0].split + (((size_t)b * (a.e[0].C >> 5) + (gch0 >> 5)) * a.y_stride + t) * 32 + (gch0 & 31);
+            uint4 h[2], l[2];
 #pragma unroll
             for (int g8 = 0; g8 < 2; ++g8) {
               if (planes == 2) {
-                uint4 h, l;
-                split2(g[8 * g8 + 0], g[8 * g8 + 1], h.x, l.x);
-                split2(g[8 * g8 + 2], g[8 * g8 + 3], h.y, l.y);
-                split2(g[8 * g8 + 4], g[8 * g8 + 5], h.z, l.z);
-                split2(g[8 * g8 + 6], g[8 * g8 + 7], h.w, l.w);
-                *reinterpret_cast<uint4*>(sp) = h;
-                *reinterpret_cast<uint4*>(sp + sp_plane * (size_t)a.e[0].C) = l;
+                split2(g[8 * g8 + 0], g[8 * g8 + 1], h[g8].x, l[g8].x);
+                split2(g[8 * g8 + 2], g[8 * g8 + 3], h[g8].y, l[g8].y);
+                split2(g[8 * g8 + 4], g[8 * g8 + 5], h[g8].z, l[g8].z);
+                split2(g[8 * g8 + 6], g[8 * g8 + 7], h[g8].w, l[g8].w);
               } else {
-                *reinterpret_cast<uint4*>(sp) = pack_bf16x8(&g[8 * g8]);
+                h[g8] = pack_bf16x8(&g[8 * g8]);
               }
-              sp += 8;
             }
+            st_global_v8(sp, h[0], h[1]);
+            if (planes == 2) st_global_v8(sp + sp_plane * (size_t)a.e[0].C, l[0], l[1]);
           }
           if (ybase) {
 #pragma unroll
@@ -838,10 +837,8 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
               for (int r2 = 0; r2 < 2; ++r2) {
                 if (r2 ? i1 : i0) {
                   if (paired) {
-                    *reinterpret_cast<uint4*>(sp + 32 * r2) = keep_h[r2];
-                    *reinterpret_cast<uint4*>(sp + 32 * r2 + 8) = hq[r2];
-                    *reinterpret_cast<uint4*>(sp + 32 * r2 + lo_plane) = keep_l[r2];
-                    *reinterpret_cast<uint4*>(sp + 32 * r2 + 8 + lo_plane) = lq[r2];
+                    st_global_v8(sp + 32 * r2, keep_h[r2], hq[r2]);
+                    st_global_v8(sp + 32 * r2 + lo_plane, keep_l[r2], lq[r2]);
                   } else {
                     *reinterpret_cast<uint4*>(sp + 32 * r2) = hq[r2];
                     *reinterpret_cast<uint4*>(sp + 32 * r2 + lo_plane) = lq[r2];
@@ -957,19 +954,24 @@ __global__ void __launch_bounds__(256) split_image_kernel(const float* __restric
     v[e] = q > 0.f ? q : q * slope;
   }
   uint16_t* cell = img + (((size_t)b * (C >> 5) + cg) * L + t) * 32;
+  uint4 h[4], l[4];
 #pragma unroll
   for (int g8 = 0; g8 < 4; ++g8) {
     if (planes == 1) {
-      *reinterpret_cast<uint4*>(cell + g8 * 8) = pack_bf16x8(&v[g8 * 8]);
+      h[g8] = pack_bf16x8(&v[g8 * 8]);
     } else {
-      uint4 h, l;
-      split2(v[g8 * 8 + 0], v[g8 * 8 + 1], h.x, l.x);
-      split2(v[g8 * 8 + 2], v[g8 * 8 + 3], h.y, l.y);
-      split2(v[g8 * 8 + 4], v[g8 * 8 + 5], h.z, l.z);
-      split2(v[g8 * 8 + 6], v[g8 * 8 + 7], h.w, l.w);
-      *reinterpret_cast<uint4*>(cell + g8 * 8) = h;
-      *reinterpret_cast<uint4*>(cell + (size_t)B * C * L + g8 * 8) = l;
+      split2(v[g8 * 8 + 0], v[g8 * 8 + 1], h[g8].x, l[g8].x);
+      split2(v[g8 * 8 + 2], v[g8 * 8 + 3], h[g8].y, l[g8].y);
+      split2(v[g8 * 8 + 4], v[g8 * 8 + 5], h[g8].z, l[g8].z);
+      split2(v[g8 * 8 + 6], v[g8 * 8 + 7], h[g8].w, l[g8].w);
     }
+  }
+  st_global_v8(cell, h[0], h[1]);  // the 64 B row as two full sectors
+  st_global_v8(cell + 16, h[2], h[3]);
+  if (planes == 2) {
+    uint16_t* lo = cell + (size_t)B * C * L;
+    st_global_v8(lo, l[0], l[1]);
+    st_global_v8(lo + 16, l[2], l[3]);
   }
 }
 

@@ -404,19 +404,19 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
       if (valid) {
         if (pa.y_img) {
           uint16_t* sp = pa.y_img + (((size_t)b * (pa.C >> 5) + (n0 >> 5)) * pa.L + t) * 32 + (n0 & 31);
+          uint4 hq[2], lq[2];
 #pragma unroll
           for (int g8 = 0; g8 < 2; ++g8) {
             float w8[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) w8[e] = v[8 * g8 + e] > 0.f ? v[8 * g8 + e] : v[8 * g8 + e] * pa.y_slope;
-            uint4 hq, lq;
-            split2(w8[0], w8[1], hq.x, lq.x);
-            split2(w8[2], w8[3], hq.y, lq.y);
-            split2(w8[4], w8[5], hq.z, lq.z);
-            split2(w8[6], w8[7], hq.w, lq.w);
-            *reinterpret_cast<uint4*>(sp + g8 * 8) = hq;
-            *reinterpret_cast<uint4*>(sp + g8 * 8 + plane) = lq;
+            split2(w8[0], w8[1], hq[g8].x, lq[g8].x);
+            split2(w8[2], w8[3], hq[g8].y, lq[g8].y);
+            split2(w8[4], w8[5], hq[g8].z, lq[g8].z);
+            split2(w8[6], w8[7], hq[g8].w, lq[g8].w);
           }
+          st_global_v8(sp, hq[0], hq[1]);  // one full 32 B sector per plane and row
+          st_global_v8(sp + plane, lq[0], lq[1]);
         }
         if (pa.y) {
           float* yp = pa.y + ((size_t)b * pa.C + n0) * pa.L + t;

@@ -169,6 +169,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
 
+// One 32 B global store (STG.256, sm_100): a whole sector in one request.  Two 16 B stores to the halves of a sector
+// reach L2 as two partial-sector writes; on the operand-image rows (32 B per thread and plane) that costs 1.5-2x the
+// time of the same bytes written as full sectors.  `p` must be 32 B-aligned.
+__device__ __forceinline__ void st_global_v8(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 // fp32 -> (hi, lo) fp16 pair for two values; returns packed half2 words.
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(a, b);
