@@ -868,8 +868,37 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
           float v[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) v[e] = fmaf(__uint_as_float(m[e]) + __uint_as_float(c[e]), unscale, bv[e]);
+          // Stride-8 upsamplers (k = 16, p = 4): row t holds y[co, 8t-4 .. 8t+3] for two real channels.  Its upper four
+          // floats are the lower half of the 32 B sector y[co, 8t .. 8t+7]; the upper half comes from the NEXT row's lower
+          // four (lane shuffles), so a lane stores one whole sector with one 32 B store.  Lane 0 also stores its own lower
+          // four (the previous warp's lane 31 could not), lane 31 stores only its half.
+          const bool sect8 = sh == 8 && a.shuf_p == 4 && o0 + 16 <= a.Cout && (a.y_stride & 7) == 0;
+          if (sect8) {
+#pragma unroll
+            for (int gq = 0; gq < 2; ++gq) {
+              float nl[4];
+#pragma unroll
+              for (int k2 = 0; k2 < 4; ++k2) nl[k2] = __shfl_down_sync(0xffffffffu, v[8 * gq + k2], 1);
+              if (tin) {
+                float* yrow = ybase + (size_t)((o0 >> 3) + gq) * a.y_stride;
+                const int t8 = 8 * t;
+                if (lane == 0 && t8 >= 4)
+                  *reinterpret_cast<float4*>(yrow + t8 - 4) = make_float4(v[8 * gq], v[8 * gq + 1], v[8 * gq + 2], v[8 * gq + 3]);
+                if (lane < 31 && t8 + 7 < a.shuf_Lout) {
+                  const uint4 lo4 = make_uint4(__float_as_uint(v[8 * gq + 4]), __float_as_uint(v[8 * gq + 5]),
+                                               __float_as_uint(v[8 * gq + 6]), __float_as_uint(v[8 * gq + 7]));
+                  const uint4 hi4 = make_uint4(__float_as_uint(nl[0]), __float_as_uint(nl[1]), __float_as_uint(nl[2]), __float_as_uint(nl[3]));
+                  st_global_v8(yrow + t8, lo4, hi4);
+                } else if (t8 + 3 < a.shuf_Lout) {
+                  *reinterpret_cast<float4*>(yrow + t8) = make_float4(v[8 * gq + 4], v[8 * gq + 5], v[8 * gq + 6], v[8 * gq + 7]);
+                }
+              }
+            }
+          }
           if (!tin) continue;
-          if (sh == 8 && (a.shuf_p & 3) == 0) {
+          if (sect8) {
+            // stored above
+          } else if (sh == 8 && (a.shuf_p & 3) == 0) {
 #pragma unroll
             for (int gq = 0; gq < 2; ++gq) {
               const int co = (o0 >> 3) + gq;
