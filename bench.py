@@ -443,7 +443,10 @@ def run_b200_arm(args):
         "e2e": {"value": N_total * dims.hop * T * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke,
                 "path": "pinned host -> H2D" + (" -> NCCL scatter" if world > 1 else "") + " -> SynthesizerTrn.infer (libsvk) -> "
-                        + ("NCCL gather -> " if world > 1 else "") + "D2H pinned host, eps drawn on device (models.py:336)"},
+                        + ("NCCL gather -> " if world > 1 else "") + "D2H pinned host, eps drawn on device (models.py:336)",
+                "note": "timed with a host clock around whole steps (copies + infer + sync).  It can exceed `value`: the K "
+                        "device-resident steps run back to back into the board's power cap, while the per-step copies and "
+                        "synchronisation of this leg leave the GPU short pauses in which it clocks higher"},
         "gpu_launches": int(launches_per_step * K * world),
         "clocks": clocks,
         "device": prop.name,
