@@ -1,3 +1,7 @@
+#!/bin/bash
+# A/B of the lean STORE epilogue on the decoder ResBlock shapes (conv1 = image -> image, conv2 = image + residual -> fp32 + image):
+#   tools/build_probe.sh && tools/probe_fast.sh      ($SVK_EPI_FAST=0 runs the generic epilogue)
+cd "$(dirname "$0")/.."
 P=tools/bin/tc_probe
 run() { timeout 60 $P "$@" 2>&1 | grep -o "B=.*K=[0-9]* \|res=[01]\|maxabs [0-9.e+-]*\|bad [0-9]*\|[0-9.]* ms [0-9.]* TFLOP" | paste -sd' '; }
 for f in 0 1; do echo "== SVK_EPI_FAST=$f"; export SVK_EPI_FAST=$f
