@@ -135,3 +135,25 @@ def time_sharded_infer(window_fn: Callable[[torch.Tensor, torch.Tensor, torch.Te
         return torch.cat(parts, dim=2)
     _gather(pcm, None, root, group)
     return None
+
+
+def length_buckets(lengths: Sequence[int], boundaries: Sequence[int], batch_size: int) -> List[List[int]]:
+    """Serving-side counterpart of the reference's DistributedBucketSampler (data_utils.py:130-226): batches of at most
+    `batch_size` utterance indices whose lengths fall into the same (boundaries[i], boundaries[i+1]] group, so that a padded
+    batch wastes little decoder work (the decoder runs over the padded length).  Unlike the training sampler
+    nothing is dropped, duplicated or shuffled: every utterance appears exactly once (lengths outside the boundaries go
+    to an extra first / last group), longest first inside a group so a batch's padding is set by its first item."""
+    if batch_size < 1:
+        raise ValueError("batch_size must be positive")
+    b = sorted(int(x) for x in boundaries)
+    groups: List[List[int]] = [[] for _ in range(len(b) + 1)]
+    for i, n in enumerate(lengths):
+        g = 0
+        while g < len(b) and int(n) > b[g]:
+            g += 1
+        groups[g].append(i)
+    out: List[List[int]] = []
+    for g in groups:
+        g.sort(key=lambda i: (-int(lengths[i]), i))
+        out += [g[k:k + batch_size] for k in range(0, len(g), batch_size)]
+    return out

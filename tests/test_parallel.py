@@ -138,3 +138,20 @@ def test_time_shard_bounds():
             b = P.time_shard_bounds(T, w, 110)
             assert b[0][0] == 0 and b[-1][1] == T
             assert all(x[2] <= x[0] and x[1] <= x[3] and x[2] >= 0 and x[3] <= T for x in b)
+
+
+def test_length_buckets_cover_every_utterance_once():
+    import svk_parallel as P
+    lengths = [300, 32, 999, 301, 500, 1, 300, 700, 1001, 64]
+    batches = P.length_buckets(lengths, [32, 300, 400, 500, 1000], batch_size=2)
+    flat = [i for b in batches for i in b]
+    assert sorted(flat) == list(range(len(lengths)))          # nothing dropped or duplicated (inference, not training)
+    assert all(1 <= len(b) <= 2 for b in batches)
+    bounds = [32, 300, 400, 500, 1000]
+    grp = lambda n: sum(n > x for x in bounds)                # noqa: E731
+    for b in batches:
+        assert len({grp(lengths[i]) for i in b}) == 1         # one length group per batch (data_utils.py:133-135)
+        assert [lengths[i] for i in b] == sorted((lengths[i] for i in b), reverse=True)
+    assert P.length_buckets([], [10], 4) == []
+    with pytest.raises(ValueError):
+        P.length_buckets([1], [10], 0)
