@@ -99,6 +99,14 @@ def main():
               "mel", float(np.abs(out[f"{tag}_mel_f32"] - out[f"{tag}_mel_f64"]).max()))
     out.update(bases)
     print("basis: torchaudio vs transformers max-abs", float(np.abs(out["basis_torchaudio"] - out["basis_transformers"]).max()))
+    # the drop-in boundary: names, parameter order and defaults of the functions the callers use
+    import inspect
+    import json
+    sigs = {n: str(inspect.signature(getattr(ref, n))) for n in
+            ("spectrogram_torch", "spec_to_mel_torch", "mel_spectrogram_torch", "dynamic_range_compression_torch",
+             "dynamic_range_decompression_torch", "spectral_normalize_torch", "spectral_de_normalize_torch")}
+    sigs["MAX_WAV_VALUE"] = ref.MAX_WAV_VALUE
+    json.dump(sigs, open(os.path.join(HERE, "mel_processing_signatures.json"), "w"), indent=1)
     np.savez_compressed(os.path.join(HERE, "mel_frontend.npz"), **out)
     print("wrote", os.path.join(HERE, "mel_frontend.npz"), os.path.getsize(os.path.join(HERE, "mel_frontend.npz")), "bytes")
 

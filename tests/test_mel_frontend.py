@@ -199,3 +199,17 @@ def test_gpu_wave_to_wave_through_frontend(base_cfg, base_sd):
         o, mask, _ = net.infer(mel, torch.tensor([40], device="cuda"), noise_scale=0.667)
     torch.cuda.synchronize()
     assert tuple(o.shape) == (1, 1, n) and torch.isfinite(o).all() and float(o.abs().max()) <= 1.0
+
+
+def test_shim_signatures_match_the_reference():
+    """Drop-in boundary: same names, parameter order and defaults as the reference's mel_processing.py
+    (signatures recorded by tests/golden/make_golden_mel.py from the reference itself)."""
+    import inspect
+    import json
+    import os
+    import mel_processing as mp
+    from conftest import GOLDEN
+    ref = json.load(open(os.path.join(GOLDEN, "mel_processing_signatures.json")))
+    assert mp.MAX_WAV_VALUE == ref.pop("MAX_WAV_VALUE")
+    for name, sig in ref.items():
+        assert str(inspect.signature(getattr(mp, name))) == sig, name
