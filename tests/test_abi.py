@@ -130,3 +130,17 @@ def test_clip_len_matches_python_slicing():
     for T in (1, 5, 12):
         for ml in (None, 0, 1, 4, 12, 100, -1, -3, -50):
             assert SynthesizerTrn._clip_len(T, ml) == len(list(range(T))[:ml])
+
+
+def test_shim_signatures_match_the_reference_modules():
+    """the nn.Module surface the callers use -- constructor, infer, and the sub-module calls -- has the
+    reference's parameter names, order and defaults (recorded from the reference by make_golden_signatures.py)."""
+    import inspect
+    from models import SynthesizerTrn
+    ref = json.load(open(os.path.join(GOLDEN, "models_signatures.json")))
+    for name in ("__init__", "infer", "forward", "voice_conversion"):
+        assert str(inspect.signature(getattr(SynthesizerTrn, name))) == ref["SynthesizerTrn." + name], name
+    sub = {"Generator.forward": "_dec_forward", "MelEncoder.forward": "_enc_p_forward",
+           "PosteriorEncoder.forward": "_enc_q_forward", "ResidualCouplingBlock.forward": "_flow_forward"}
+    for ref_name, ours in sub.items():
+        assert str(inspect.signature(getattr(SynthesizerTrn, ours))) == ref[ref_name], ref_name
