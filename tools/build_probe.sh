@@ -16,3 +16,4 @@ for v in ${PROBE_VARIANTS:-}; do
   nvcc $F $D -c $C/conv_tc.cu -o tools/bin/conv_tc_$v.o
   nvcc $F tools/tc_probe.cu tools/bin/conv_tc_$v.o tools/bin/conv_ffma.o -o tools/bin/tc_probe_$v
 done
+nvcc $F tools/store_bench.cu -o tools/bin/store_bench
