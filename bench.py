@@ -241,6 +241,7 @@ def run_b200_arm(args):
                          engine=args.engine, **cfg["model"])
     net.load_state_dict({k: torch.from_numpy(v) for k, v in W.make_state_dict(dims, seed=1234).items()})
     net = net.cuda().eval()
+    net.range_check = False  # device-resident legs: keep infer() asynchronous, check once after the timed region
 
     B, T, K, Wm = args.batch_per_gpu, args.frames, args.steps, max(args.warmup, 3)
     mel_h, len_h = synth_inputs(B, T, seed=rank)
@@ -285,7 +286,9 @@ def run_b200_arm(args):
         # `value` because event pairs serialise the stream at every launch boundary
         profiled_ms, records, _ = timed_pass(True)
         clocks = sampler.stop() if sampler else None
+        net.check_range()  # raises if any step produced a non-finite sample (svk_check_range)
         assert torch.isfinite(o).all()
+        net.range_check = True  # the end-to-end leg is the call a user makes: check included
 
         t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
         if world > 1:

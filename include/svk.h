@@ -38,6 +38,9 @@ extern "C" {
 #define SVK_ERR_UNKNOWN_KEY (-3) /* svk_load_tensor: key is not part of the checkpoint surface      */
 #define SVK_ERR_STATE (-4)       /* call order (e.g. infer before svk_finalize_weights)             */
 #define SVK_ERR_WORKSPACE (-5)   /* workspace too small                                             */
+#define SVK_ERR_RANGE (-6)       /* a non-finite waveform sample was produced: an activation left the
+                                    fp16 operand range of the tensor-core engine (|x| > 65504), or the
+                                    inputs / weights were not finite (svk_check_range)              */
 
 #define SVK_MAX_UPSAMPLES 8
 #define SVK_MAX_RESBLOCK_KERNELS 8
@@ -128,6 +131,13 @@ int svk_infer(svk_handle *h, const float *mel_dev, const int64_t *lengths_dev, c
 int svk_infer_host(svk_handle *h, const float *mel, const int64_t *lengths, const float *eps,
                    float noise_scale, int B, int T, int max_len, float *o, float *x_mask, float *z,
                    float *z_p, float *m_p, float *logs_p);
+/* Range guard.  The default engine stores activations as fp16 hi/lo pairs: an activation above 65504
+ * becomes inf and reaches the waveform as NaN.  The final tanh epilogue (models.py:158) raises a device
+ * flag for every output sample outside [-1, 1] (only a NaN can be).  svk_check_range synchronises
+ * `stream`, reads and clears the flag: SVK_OK, or SVK_ERR_RANGE if any svk_infer / svk_generator call
+ * on this handle since the last check produced one.  svk_infer_host checks before it returns.
+ * No reference counterpart: fp32 PyTorch would print the same NaN audio silently. */
+int svk_check_range(svk_handle *h, void *stream);
 /* ---- windowed / chunked synthesis (streaming and T >> 1024) ----------------
  * svk_infer_window computes the PCM of frames [t0, t1) of the utterance batch EXACTLY as the whole-
  * utterance svk_infer would: the window is widened by svk_halo_frames() frames of context per side

@@ -231,7 +231,10 @@ __global__ void __launch_bounds__(WO* WT * 32, 2) conv_ffma_kernel(const ConvArg
       if (arow) v += arow[t];
       if (a.post_div != 1.0f) v = v / a.post_div;
       if (use_mask) v *= omask[t];
-      if (a.act_tanh) v = tanhf(v);
+      if (a.act_tanh) {
+        v = tanhf(v);
+        if (a.range_flag && !(fabsf(v) <= 1.0f)) *a.range_flag = 1;
+      }
       yrow[t] = v;
     }
   }
@@ -332,6 +335,12 @@ static __global__ void __launch_bounds__(C1_THREADS) conv_cout1_kernel(const Con
     if (om && a.e[0].use_mask && t + i < a.Lout) v *= om[t + i];
     o[i] = a.act_tanh ? tanhf(v) : v;
   }
+  if (a.act_tanh && a.range_flag) {
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bad = bad || (t + i < a.Lout && !(fabsf(o[i]) <= 1.0f));
+    if (bad) *a.range_flag = 1;
+  }
   if (t + 3 < a.Lout && (a.y_stride & 3) == 0) {
     *reinterpret_cast<float4*>(y + t) = make_float4(o[0], o[1], o[2], o[3]);
   } else {
@@ -397,6 +406,12 @@ static __global__ void __launch_bounds__(CS_THREADS) conv_cout1_stream_kernel(co
     if (a.post_div != 1.0f) q = q / a.post_div;
     if (om && a.e[0].use_mask && t + i < a.Lout) q *= om[t + i];
     o[i] = a.act_tanh ? tanhf(q) : q;
+  }
+  if (a.act_tanh && a.range_flag) {
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bad = bad || (t + i < a.Lout && !(fabsf(o[i]) <= 1.0f));
+    if (bad) *a.range_flag = 1;
   }
   if (t + 3 < a.Lout && (a.y_stride & 3) == 0) {
     *reinterpret_cast<float4*>(y + t) = make_float4(o[0], o[1], o[2], o[3]);

@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
             for (int e2 = 0; e2 < 4; ++e2) {
               const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e2]));
               const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e2]));
-              const float v0 = hf.x + lf.x, v1 = hf.y + lf.y;
+              const float v0 = fmaf(lf.x, LO_INV, hf.x), v1 = fmaf(lf.y, LO_INV, hf.y);
               q[8 * g8 + 2 * e2] = v0 >= 0.f ? v0 : v0 * io.r_inv;
               q[8 * g8 + 2 * e2 + 1] = v1 >= 0.f ? v1 : v1 * io.r_inv;
             }
@@ -543,10 +543,10 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
 #pragma unroll
           for (int e4 = 0; e4 < 4; ++e4) {
             const float4 q = b4[e4];
-            v[4 * e4 + 0] = fmaf(__uint_as_float(m[4 * e4 + 0]) + __uint_as_float(c[4 * e4 + 0]), unscale, q.x);
-            v[4 * e4 + 1] = fmaf(__uint_as_float(m[4 * e4 + 1]) + __uint_as_float(c[4 * e4 + 1]), unscale, q.y);
-            v[4 * e4 + 2] = fmaf(__uint_as_float(m[4 * e4 + 2]) + __uint_as_float(c[4 * e4 + 2]), unscale, q.z);
-            v[4 * e4 + 3] = fmaf(__uint_as_float(m[4 * e4 + 3]) + __uint_as_float(c[4 * e4 + 3]), unscale, q.w);
+            v[4 * e4 + 0] = fmaf(fmaf(__uint_as_float(c[4 * e4 + 0]), LO_INV, __uint_as_float(m[4 * e4 + 0])), unscale, q.x);
+            v[4 * e4 + 1] = fmaf(fmaf(__uint_as_float(c[4 * e4 + 1]), LO_INV, __uint_as_float(m[4 * e4 + 1])), unscale, q.y);
+            v[4 * e4 + 2] = fmaf(fmaf(__uint_as_float(c[4 * e4 + 2]), LO_INV, __uint_as_float(m[4 * e4 + 2])), unscale, q.z);
+            v[4 * e4 + 3] = fmaf(fmaf(__uint_as_float(c[4 * e4 + 3]), LO_INV, __uint_as_float(m[4 * e4 + 3])), unscale, q.w);
           }
           if (RES) {
 #pragma unroll
@@ -648,10 +648,10 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
 #pragma unroll
           for (int e4 = 0; e4 < 4; ++e4) {
             const float4 q = b4[e4];
-            v[4 * e4 + 0] = fmaf(__uint_as_float(m[4 * e4 + 0]) + __uint_as_float(c[4 * e4 + 0]), unscale, q.x) + r1[4 * e4 + 0];
-            v[4 * e4 + 1] = fmaf(__uint_as_float(m[4 * e4 + 1]) + __uint_as_float(c[4 * e4 + 1]), unscale, q.y) + r1[4 * e4 + 1];
-            v[4 * e4 + 2] = fmaf(__uint_as_float(m[4 * e4 + 2]) + __uint_as_float(c[4 * e4 + 2]), unscale, q.z) + r1[4 * e4 + 2];
-            v[4 * e4 + 3] = fmaf(__uint_as_float(m[4 * e4 + 3]) + __uint_as_float(c[4 * e4 + 3]), unscale, q.w) + r1[4 * e4 + 3];
+            v[4 * e4 + 0] = fmaf(fmaf(__uint_as_float(c[4 * e4 + 0]), LO_INV, __uint_as_float(m[4 * e4 + 0])), unscale, q.x) + r1[4 * e4 + 0];
+            v[4 * e4 + 1] = fmaf(fmaf(__uint_as_float(c[4 * e4 + 1]), LO_INV, __uint_as_float(m[4 * e4 + 1])), unscale, q.y) + r1[4 * e4 + 1];
+            v[4 * e4 + 2] = fmaf(fmaf(__uint_as_float(c[4 * e4 + 2]), LO_INV, __uint_as_float(m[4 * e4 + 2])), unscale, q.z) + r1[4 * e4 + 2];
+            v[4 * e4 + 3] = fmaf(fmaf(__uint_as_float(c[4 * e4 + 3]), LO_INV, __uint_as_float(m[4 * e4 + 3])), unscale, q.w) + r1[4 * e4 + 3];
           }
           if (a.post_div != 1.0f) {
 #pragma unroll
@@ -662,8 +662,10 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
             for (int e = 0; e < 16; ++e) v[e] *= mv;
           }
           if (a.act_tanh) {
+            bool bad = false;
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = tanhf(v[e]);
+            for (int e = 0; e < 16; ++e) v[e] = tanhf(v[e]), bad = bad || !(fabsf(v[e]) <= 1.0f);
+            if (bad && tin && a.range_flag) *a.range_flag = 1;
           }
           if (io_c.sp && tin) {
             // second output: leaky_relu(y) as fp16 hi/lo, 8 channels = one 16 B row of the operand image
@@ -723,10 +725,10 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
 #pragma unroll
           for (int e4 = 0; e4 < 4; ++e4) {
             const float4 q = reinterpret_cast<const float4*>(bptr + n0)[e4];
-            g[4 * e4 + 0] = tanhf(fmaf(__uint_as_float(m[4 * e4 + 0]) + __uint_as_float(c[4 * e4 + 0]), unscale, q.x));
-            g[4 * e4 + 1] = tanhf(fmaf(__uint_as_float(m[4 * e4 + 1]) + __uint_as_float(c[4 * e4 + 1]), unscale, q.y));
-            g[4 * e4 + 2] = tanhf(fmaf(__uint_as_float(m[4 * e4 + 2]) + __uint_as_float(c[4 * e4 + 2]), unscale, q.z));
-            g[4 * e4 + 3] = tanhf(fmaf(__uint_as_float(m[4 * e4 + 3]) + __uint_as_float(c[4 * e4 + 3]), unscale, q.w));
+            g[4 * e4 + 0] = tanhf(fmaf(fmaf(__uint_as_float(c[4 * e4 + 0]), LO_INV, __uint_as_float(m[4 * e4 + 0])), unscale, q.x));
+            g[4 * e4 + 1] = tanhf(fmaf(fmaf(__uint_as_float(c[4 * e4 + 1]), LO_INV, __uint_as_float(m[4 * e4 + 1])), unscale, q.y));
+            g[4 * e4 + 2] = tanhf(fmaf(fmaf(__uint_as_float(c[4 * e4 + 2]), LO_INV, __uint_as_float(m[4 * e4 + 2])), unscale, q.z));
+            g[4 * e4 + 3] = tanhf(fmaf(fmaf(__uint_as_float(c[4 * e4 + 3]), LO_INV, __uint_as_float(m[4 * e4 + 3])), unscale, q.w));
           }
           tmem_ld16(tsub + (uint32_t)(hN + n0), m);
           if (planes == 2) tmem_ld16(tsub + (uint32_t)(N + hN + n0), c);
@@ -734,10 +736,10 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
 #pragma unroll
           for (int e4 = 0; e4 < 4; ++e4) {
             const float4 q = reinterpret_cast<const float4*>(bptr + hN + n0)[e4];
-            g[4 * e4 + 0] *= sigmoidf_(fmaf(__uint_as_float(m[4 * e4 + 0]) + __uint_as_float(c[4 * e4 + 0]), unscale, q.x));
-            g[4 * e4 + 1] *= sigmoidf_(fmaf(__uint_as_float(m[4 * e4 + 1]) + __uint_as_float(c[4 * e4 + 1]), unscale, q.y));
-            g[4 * e4 + 2] *= sigmoidf_(fmaf(__uint_as_float(m[4 * e4 + 2]) + __uint_as_float(c[4 * e4 + 2]), unscale, q.z));
-            g[4 * e4 + 3] *= sigmoidf_(fmaf(__uint_as_float(m[4 * e4 + 3]) + __uint_as_float(c[4 * e4 + 3]), unscale, q.w));
+            g[4 * e4 + 0] *= sigmoidf_(fmaf(fmaf(__uint_as_float(c[4 * e4 + 0]), LO_INV, __uint_as_float(m[4 * e4 + 0])), unscale, q.x));
+            g[4 * e4 + 1] *= sigmoidf_(fmaf(fmaf(__uint_as_float(c[4 * e4 + 1]), LO_INV, __uint_as_float(m[4 * e4 + 1])), unscale, q.y));
+            g[4 * e4 + 2] *= sigmoidf_(fmaf(fmaf(__uint_as_float(c[4 * e4 + 2]), LO_INV, __uint_as_float(m[4 * e4 + 2])), unscale, q.z));
+            g[4 * e4 + 3] *= sigmoidf_(fmaf(fmaf(__uint_as_float(c[4 * e4 + 3]), LO_INV, __uint_as_float(m[4 * e4 + 3])), unscale, q.w));
           }
           const int nval = max(0, min(16, (a.Cout >> 1) - (ntile * hN + n0)));
           if (a.e[0].split && tin && nval == 16) {
@@ -801,10 +803,10 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
 #pragma unroll
             for (int e4 = 0; e4 < 4; ++e4) {
               const float4 q = b4[e4];
-              v[4 * e4 + 0] = fmaf(__uint_as_float(m[4 * e4 + 0]) + __uint_as_float(c[4 * e4 + 0]), unscale, q.x);
-              v[4 * e4 + 1] = fmaf(__uint_as_float(m[4 * e4 + 1]) + __uint_as_float(c[4 * e4 + 1]), unscale, q.y);
-              v[4 * e4 + 2] = fmaf(__uint_as_float(m[4 * e4 + 2]) + __uint_as_float(c[4 * e4 + 2]), unscale, q.z);
-              v[4 * e4 + 3] = fmaf(__uint_as_float(m[4 * e4 + 3]) + __uint_as_float(c[4 * e4 + 3]), unscale, q.w);
+              v[4 * e4 + 0] = fmaf(fmaf(__uint_as_float(c[4 * e4 + 0]), LO_INV, __uint_as_float(m[4 * e4 + 0])), unscale, q.x);
+              v[4 * e4 + 1] = fmaf(fmaf(__uint_as_float(c[4 * e4 + 1]), LO_INV, __uint_as_float(m[4 * e4 + 1])), unscale, q.y);
+              v[4 * e4 + 2] = fmaf(fmaf(__uint_as_float(c[4 * e4 + 2]), LO_INV, __uint_as_float(m[4 * e4 + 2])), unscale, q.z);
+              v[4 * e4 + 3] = fmaf(fmaf(__uint_as_float(c[4 * e4 + 3]), LO_INV, __uint_as_float(m[4 * e4 + 3])), unscale, q.w);
             }
             float* yr = ybase + (size_t)(o0 >> 1) * a.y_stride + tq;
 #pragma unroll
@@ -867,7 +869,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
           tmem_wait_ld();
           float v[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = fmaf(__uint_as_float(m[e]) + __uint_as_float(c[e]), unscale, bv[e]);
+          for (int e = 0; e < 16; ++e) v[e] = fmaf(fmaf(__uint_as_float(c[e]), LO_INV, __uint_as_float(m[e])), unscale, bv[e]);
           // Stride-8 upsamplers (k = 16, p = 4): row t holds y[co, 8t-4 .. 8t+3] for two real channels.  Its upper four
           // floats are the lower half of the 32 B sector y[co, 8t .. 8t+7]; the upper half comes from the NEXT row's lower
           // four (lane shuffles), so a lane stores one whole sector with one 32 B store.  Lane 0 also stores its own lower
@@ -1047,7 +1049,7 @@ void conv_tc_pack(const float* w_ock, int Cout, int Cin, int K, int N, float sca
                   out[idx++] = *reinterpret_cast<const uint16_t*>(&bv);
                 } else {
                   const __half h = __float2half_rn(v);
-                  const __half l = __float2half_rn(v - __half2float(h));
+                  const __half l = __float2half_rn((v - __half2float(h)) * LO_SCALE);
                   const __half pick = part ? l : h;
                   out[idx++] = *reinterpret_cast<const uint16_t*>(&pick);
                 }

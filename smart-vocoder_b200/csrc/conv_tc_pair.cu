@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
           const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float q = fmaf(__uint_as_float(m[4 * e4 + e]) + __uint_as_float(c[4 * e4 + e]), pa.unscale1, bb[e]);
+            float q = fmaf(fmaf(__uint_as_float(c[4 * e4 + e]), LO_INV, __uint_as_float(m[4 * e4 + e])), pa.unscale1, bb[e]);
             q = inside ? q : 0.f;                              // conv2 zero-pads xt outside [0, L)
             v[4 * e4 + e] = q > 0.f ? q : q * pa.xt_slope;      // leaky_relu between the convs (modules.py:216)
           }
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
           for (int e2 = 0; e2 < 4; ++e2) {
             const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e2]));
             const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e2]));
-            const float v0 = hf.x + lf.x, v1 = hf.y + lf.y;
+            const float v0 = fmaf(lf.x, LO_INV, hf.x), v1 = fmaf(lf.y, LO_INV, hf.y);
             q[8 * g8 + 2 * e2] = v0 >= 0.f ? v0 : v0 * r_inv;
             q[8 * g8 + 2 * e2 + 1] = v1 >= 0.f ? v1 : v1 * r_inv;
           }
@@ -391,10 +391,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
 #pragma unroll
       for (int e4 = 0; e4 < 4; ++e4) {
         const float4 q = bias2_4[(n0 >> 2) + e4];
-        v[4 * e4 + 0] = fmaf(__uint_as_float(m[4 * e4 + 0]) + __uint_as_float(c[4 * e4 + 0]), pa.unscale2, q.x) + r[4 * e4 + 0];
-        v[4 * e4 + 1] = fmaf(__uint_as_float(m[4 * e4 + 1]) + __uint_as_float(c[4 * e4 + 1]), pa.unscale2, q.y) + r[4 * e4 + 1];
-        v[4 * e4 + 2] = fmaf(__uint_as_float(m[4 * e4 + 2]) + __uint_as_float(c[4 * e4 + 2]), pa.unscale2, q.z) + r[4 * e4 + 2];
-        v[4 * e4 + 3] = fmaf(__uint_as_float(m[4 * e4 + 3]) + __uint_as_float(c[4 * e4 + 3]), pa.unscale2, q.w) + r[4 * e4 + 3];
+        v[4 * e4 + 0] = fmaf(fmaf(__uint_as_float(c[4 * e4 + 0]), LO_INV, __uint_as_float(m[4 * e4 + 0])), pa.unscale2, q.x) + r[4 * e4 + 0];
+        v[4 * e4 + 1] = fmaf(fmaf(__uint_as_float(c[4 * e4 + 1]), LO_INV, __uint_as_float(m[4 * e4 + 1])), pa.unscale2, q.y) + r[4 * e4 + 1];
+        v[4 * e4 + 2] = fmaf(fmaf(__uint_as_float(c[4 * e4 + 2]), LO_INV, __uint_as_float(m[4 * e4 + 2])), pa.unscale2, q.z) + r[4 * e4 + 2];
+        v[4 * e4 + 3] = fmaf(fmaf(__uint_as_float(c[4 * e4 + 3]), LO_INV, __uint_as_float(m[4 * e4 + 3])), pa.unscale2, q.w) + r[4 * e4 + 3];
       }
       load_ops(r, job + 2);  // refill this buffer for the job after next
       if (pa.post_div != 1.0f) {

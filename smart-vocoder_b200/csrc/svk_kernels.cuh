@@ -64,6 +64,7 @@ struct ConvArgs {
   const float* out_mask;  // [B, mask_stride] or null
   int shuf_s, shuf_p, shuf_Lout;  // MODE_SHUFFLE: t = s*q + r - p, valid in [0, shuf_Lout)
   int B;
+  int* range_flag;  // act_tanh launches: set to 1 when an output is outside [-1, 1] (NaN), may be null (svk_check_range)
 };
 
 // Channel tile (in output channels) the FFMA kernel will use for a layer with `cout` outputs.

@@ -127,6 +127,8 @@ struct svk_handle {
   std::vector<svk_launch_record> prof_records;
   size_t prof_cap = 0;
 
+  int* d_range_flag = nullptr;  // raised by the final tanh epilogue on a non-finite sample (svk_check_range)
+
   // svk_infer_host state
   cudaStream_t host_stream = nullptr;
   void* host_dev = nullptr;
@@ -427,6 +429,11 @@ extern "C" int svk_create(const svk_config* cfg, int device, svk_handle** out) {
   if (const char* e = getenv("SVK_FUSE_PAIRS"))
     h->fuse_pairs = atoi(e) != 0, h->fuse_pairs_all = atoi(e) == 2, h->fuse_pairs_c32 = atoi(e) == 3;
   build_key_spec(h);
+  if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&h->d_range_flag, sizeof(int)) != cudaSuccess ||
+      cudaMemset(h->d_range_flag, 0, sizeof(int)) != cudaSuccess) {
+    delete h;
+    return fail(SVK_ERR_CUDA, "svk_create: device allocation failed");
+  }
   *out = h;
   return SVK_OK;
 }
@@ -437,6 +444,7 @@ extern "C" void svk_destroy(svk_handle* h) {
   if (h->d_blob) cudaFree(h->d_blob);
   if (h->d_tcblob) cudaFree(h->d_tcblob);
   if (h->host_dev) cudaFree(h->host_dev);
+  if (h->d_range_flag) cudaFree(h->d_range_flag);
   if (h->host_stream) cudaStreamDestroy(h->host_stream);
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   delete h;
@@ -953,6 +961,7 @@ void run_decoder(Runner& R, const float* z, int z_stride, const float* in_mask, 
     ConvArgs a = R.base(h->conv_post, prev, prevC, 0, len, len, 1, 3, len, len);
     a.pre_slope = 0.01f;
     a.act_tanh = 1;
+    a.range_flag = h->d_range_flag;
     a.e[0].y = o, a.e[0].C = 1;
     R.run(a, SVK_LAYER_CONV_POST);
   }
@@ -1183,6 +1192,24 @@ extern "C" int svk_infer(svk_handle* h, const float* mel, const int64_t* lengths
   return SVK_OK;
 }
 
+static const char* kRangeMessage =
+    "non-finite waveform sample: an activation left the fp16 operand range of the tensor-core engine (|x| > 65504) or the "
+    "inputs / weights are not finite; rescale the checkpoint or use engine=\"fp32\"";
+
+extern "C" int svk_check_range(svk_handle* h, void* stream) {
+  if (!h) return fail(SVK_ERR_INVALID, "svk_check_range: null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  int flag = 0;
+  CUDA_TRY(cudaMemcpyAsync(&flag, h->d_range_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (flag) {
+    CUDA_TRY(cudaMemsetAsync(h->d_range_flag, 0, sizeof(int), s));
+    return fail(SVK_ERR_RANGE, "%s", kRangeMessage);
+  }
+  return SVK_OK;
+}
+
 extern "C" int svk_infer_host(svk_handle* h, const float* mel, const int64_t* lengths, const float* eps,
                               float noise_scale, int B, int T, int max_len, float* o, float* x_mask, float* z,
                               float* z_p, float* m_p, float* logs_p) {
@@ -1227,8 +1254,7 @@ extern "C" int svk_infer_host(svk_handle* h, const float* mel, const int64_t* le
   if (x_mask) CUDA_TRY(cudaMemcpyAsync(x_mask, d + o_mask, (size_t)B * T * 4, cudaMemcpyDeviceToHost, s));
   for (int i = 0; i < 4; ++i)
     if (hl[i]) CUDA_TRY(cudaMemcpyAsync(hl[i], dl[i], n_lat * 4, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
-  return SVK_OK;
+  return svk_check_range(h, s);  // synchronises
 }
 
 // ------------------------------------------------------------- windowed / chunked synthesis (8(f) rank 3)

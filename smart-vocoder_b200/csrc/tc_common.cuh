@@ -178,11 +178,18 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint4& a, const uint
                : "memory");
 }
 
+// The lo half of every fp16 hi/lo pair -- activations and weights alike -- is stored scaled by 2^11: lo = fp16((x - hi) * 2048).
+// Unscaled, x - hi (<= 2^-11 |x|) falls into fp16's subnormals for |x| < 0.125 and the pair keeps fewer than 22 bits;
+// scaled, the pair is exact to 22 bits for every |x| in [6.1e-5, 65504], the range of hi itself.  Both cross products
+// (xh.wl' and xl'.wh) then carry the same factor, their accumulator is folded in as main + cross * 2^-11 (one FFMA in
+// place of the FADD), and nothing else changes: power-of-two scaling is exact.
+constexpr float LO_SCALE = 2048.0f, LO_INV = 1.0f / 2048.0f;
+
 // fp32 -> (hi, lo) fp16 pair for two values; returns packed half2 words.
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(a, b);
   const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  const __half2 l = __floats2half2_rn((a - hf.x) * LO_SCALE, (b - hf.y) * LO_SCALE);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }

@@ -1,8 +1,9 @@
 """Drop-in for the reference's ``models.SynthesizerTrn`` on the inference path (B200, libsvk).
 
 Put this directory ahead of the reference checkout on ``sys.path`` and ``inference.ipynb`` runs
-unchanged: ``from models import SynthesizerTrn`` resolves here, while ``commons``, ``utils``,
-``mel_processing`` ... keep coming from the reference.
+unchanged: ``from models import SynthesizerTrn`` and ``from mel_processing import ...`` resolve here
+(the mel front-end shim accepts the notebook's CPU tensors), while ``commons``, ``utils``,
+``data_utils`` ... keep coming from the reference.
 
 What is mirrored (reference file:line):
   * constructor signature and ignored keys            models.py:266-314   
@@ -125,6 +126,11 @@ class SynthesizerTrn(nn.Module):
         self._handle: Optional[rt.Handle] = None
         self._device: Optional[torch.device] = None
         self._ws = _Workspace()
+        # Range guard (svk_check_range): the fp16 hi/lo engine turns an activation above 65504 into NaN audio.  With
+        # `range_check` True (default) every infer()/dec() call ends with a check (one 4-byte D2H + stream sync, the
+        # sync the reference's callers do anyway with `.cpu()`) and raises SvkError instead of returning NaNs;
+        # set it False to keep calls asynchronous and call check_range() yourself.
+        self.range_check = bool(kwargs.get("range_check", True))
 
         self.dec = _SubModule(self, self._dec_forward)
         self.enc_p = _SubModule(self, self._enc_p_forward)
@@ -133,7 +139,9 @@ class SynthesizerTrn(nn.Module):
 
     # ------------------------------------------------------------------ nn.Module surface
     def _apply(self, fn, *args, **kwargs):
-        probe = fn(torch.empty(0, dtype=torch.float32))
+        # probe on the device the module currently lives on: dtype-only calls (`.float()`, `.to(torch.float32)`,
+        # no-ops in the reference) then keep the binding, and only a real move to the CPU releases the handle
+        probe = fn(torch.empty(0, dtype=torch.float32, device=self._device if self._device is not None else "cpu"))
         if probe.dtype != torch.float32:
             raise TypeError("SynthesizerTrn (B200) computes in fp32; .half()/.double() are not supported")
         if probe.device.type == "cuda":
@@ -254,15 +262,38 @@ class SynthesizerTrn(nn.Module):
             rt.check(rt.lib().svk_infer(self._handle.ptr, _ptr(x), _ptr(lengths), _ptr(eps), float(noise_scale),
                                         B, T, Tp, _ptr(o), _ptr(x_mask), _ptr(z), _ptr(z_p), _ptr(m_p), _ptr(logs_p),
                                         _ptr(ws), nbytes, self._stream()))
+            if self.range_check:
+                self._handle.check_range(self._stream())
         return o, x_mask, (z, z_p, m_p, logs_p)
+
+    def check_range(self):
+        """Raise SvkError(SVK_ERR_RANGE) if any call since the last check produced a non-finite sample (synchronises)."""
+        self._need_cuda()
+        with torch.cuda.device(self._device):
+            self._handle.check_range(self._stream())
 
     def infer_host(self, mel: np.ndarray, lengths: np.ndarray, eps: np.ndarray, noise_scale=1.0, max_len=None,
                    out: Optional[np.ndarray] = None, want_latents: bool = False):
         """Host-buffer entry (svk_infer_host): what inference.ipynb:114-118 does around ``infer``
         (``.cuda()`` ... ``.cpu()``), copies included.  Arrays should live in pinned memory."""
         self._need_cuda()
+        # the C side copies raw bytes: coerce dtype / layout here (no-ops for the arrays a careful caller passes)
+        mel = np.ascontiguousarray(mel, dtype=np.float32)
+        if mel.ndim != 3 or mel.shape[1] != self.dims.n_mel:
+            raise ValueError(f"mel: expected [B, {self.dims.n_mel}, T], got {list(mel.shape)}")
         B, _, T = mel.shape
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64).reshape(-1)
+        eps = np.ascontiguousarray(eps, dtype=np.float32)
+        if lengths.shape[0] != B:
+            raise ValueError(f"lengths: expected [{B}], got {list(lengths.shape)}")
+        if tuple(eps.shape) != (B, self.dims.inter_channels, T):
+            raise ValueError(f"eps: expected [{B}, {self.dims.inter_channels}, {T}], got {list(eps.shape)}")
         Tp = self._clip_len(T, max_len)
+        if B == 0 or T == 0 or Tp == 0:
+            raise ValueError("infer_host: empty batch / zero frames")
+        if out is not None and (out.dtype != np.float32 or not out.flags["C_CONTIGUOUS"] or
+                                out.size != B * self.dims.hop * Tp):
+            raise ValueError(f"out: expected a C-contiguous float32 array of {B * self.dims.hop * Tp} elements")
         if out is None:
             out = np.empty((B, 1, self.dims.hop * Tp), np.float32)
         mask = np.empty((B, 1, T), np.float32)
@@ -365,6 +396,8 @@ class SynthesizerTrn(nn.Module):
         ws = self._ws.get(nbytes, self._device)
         with torch.cuda.device(self._device):
             rt.check(rt.lib().svk_generator(self._handle.ptr, _ptr(x), B, L, _ptr(o), _ptr(ws), nbytes, self._stream()))
+            if self.range_check:
+                self._handle.check_range(self._stream())
         return o
 
     def _enc_p_forward(self, x, x_lengths, g=None):

@@ -20,6 +20,7 @@ SVK_ERR_CUDA = -2
 SVK_ERR_UNKNOWN_KEY = -3
 SVK_ERR_STATE = -4
 SVK_ERR_WORKSPACE = -5
+SVK_ERR_RANGE = -6
 
 SVK_MAX_UPSAMPLES = 8
 SVK_MAX_RESBLOCK_KERNELS = 8
@@ -85,6 +86,7 @@ SIGNATURES = {
     "svk_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "svk_infer": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "svk_infer_host": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "svk_check_range": (_i, [_vp, _vp]),
     "svk_halo_frames": (_i, [_vp]),
     "svk_window_workspace_bytes": (_sz, [_vp, _i, _i]),
     "svk_infer_window": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
@@ -215,6 +217,10 @@ class Handle:
 
     def last_launch_count(self) -> int:
         return int(lib().svk_last_launch_count(self._h))
+
+    def check_range(self, stream=None):
+        """Synchronises `stream`; raises SvkError(SVK_ERR_RANGE) if a non-finite sample was produced since the last check."""
+        check(lib().svk_check_range(self._h, stream))
 
     def profile_begin(self, max_records: int = 8192):
         self._prof_cap = int(max_records)

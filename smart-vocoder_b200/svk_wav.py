@@ -37,6 +37,9 @@ def write_wav_float32(path: str, pcm, sample_rate: int = SAMPLE_RATE) -> int:
     return (len(blob) - 58) // 4
 
 
+write_wav = write_wav_float32  # the name INTEGRATION.md's table uses
+
+
 def wav_header_info(blob: bytes) -> dict:
     """Parse the chunk structure of a WAV file (enough of it to compare with the reference's demo files)."""
     riff, _, wave = struct.unpack("<4sI4s", blob[:12])

@@ -84,20 +84,183 @@ def test_infer_vs_oracle_ragged(net, base_sd, base_dims):
     assert np.abs(_np(z) - rz).max() <= TOL and np.abs(_np(z_p) - rzp).max() <= TOL
 
 
-def test_flow_passthrough_is_bit_exact(net, base_sd, base_dims):
-    """The last coupling (RCL0) leaves its x0 half untouched and Flip/split/cat are pure indexing, so
-    z[:, :96] must equal -- bit for bit -- what the oracle carries there, given the same input to RCL0."""
+def _sd_with_live_couplings(base_dims, live):
+    """The seeded recipe with `post` (weight and bias) of every coupling NOT in `live` zero, as the reference initialises
+    it (modules.py:321-322): such a coupling is the identity on x1 apart from the mask."""
+    import svk_weights as W
+    sd = W.make_state_dict(base_dims, seed=1234)
+    for f in range(base_dims.n_flows):
+        if f not in live:
+            for leaf in ("weight", "bias"):
+                sd[f"flow.flows.{2 * f}.post.{leaf}"] = np.zeros_like(sd[f"flow.flows.{2 * f}.post.{leaf}"])
+    return sd
+
+
+def _flow_inputs(B=2, T=150, lengths=(150, 97), seed=31):
+    rng = np.random.Generator(np.random.Philox(key=[seed, T]))
+    z_p = rng.standard_normal((B, 192, T)).astype(np.float32)
+    mask = Oracle.sequence_mask(np.asarray(lengths, np.int64), T).astype(np.float32)
+    return z_p, mask
+
+
+@pytest.mark.parametrize("engine", ["tc", "fp32"])
+def test_identity_flow_is_bit_exact_on_gpu(engine, base_cfg, base_dims):
+    """north_star: 'bit-identical on the flow's permutation/indexing ops'.  In the product path the four Flips are folded
+    into weight-index permutations and a reversed-channel store, and split/cat into channel offsets -- so the standalone
+    svk_flip test says nothing about them.  With zero-initialised `post` (the reference's own init) every coupling is
+    x1 -> x1 * mask, the whole reverse flow is z_p * mask, and the GPU must reproduce that BIT FOR BIT through all four
+    folded Flips, on two time tiles with a ragged row."""
+    from gpu_util import build_net, dev, inject_eps
+    net0 = build_net(base_cfg["model"], _sd_with_live_couplings(base_dims, live=()), engine=engine)
+    z_p, mask = _flow_inputs()
+    want = z_p * mask
+    live_rows = np.broadcast_to(mask != 0, z_p.shape)
+    for reverse in (True, False):
+        z = _np(net0.flow(dev(z_p), dev(mask), reverse=reverse))
+        assert np.array_equal(z, want)  # torch.equal semantics (a masked zero may differ in sign: -0 + 0 = +0)
+        assert z[live_rows].tobytes() == z_p[live_rows].tobytes()  # every unmasked element bit for bit
+    # and through infer: the returned z equals the returned z_p * x_mask
+    rng = np.random.Generator(np.random.Philox(key=[32, 1]))
+    mel = (rng.standard_normal((2, 80, 150)) * 2 - 5).astype(np.float32)
+    eps = rng.standard_normal((2, 192, 150)).astype(np.float32)
+    with inject_eps(eps), torch.no_grad():
+        _, xm, (z2, zp2, _, _) = net0.infer(dev(mel), dev(np.array([150, 97]), torch.int64), noise_scale=0.667)
+    assert torch.equal(z2, zp2 * xm)
+
+
+@pytest.mark.parametrize("live", [0, 1, 2, 3])
+def test_single_live_coupling_pass_through_half_bit_exact(net, live, base_cfg, base_dims):
+    """One coupling alive, the other three identities: its x0 half must come out as z_p * mask bit for bit, in the
+    channel positions the Flips put it (coupling f sees the input after n_flows - f Flips, models.py:77-79: odd ->
+    x0 is the reversed upper half), while its x1 half carries x1 - m within 1e-4 of the fp64 oracle."""
+    from gpu_util import build_net, dev
+    sd = _sd_with_live_couplings(base_dims, live=(live,))
+    net1 = build_net(base_cfg["model"], sd, engine=net.engine)
+    z_p, mask = _flow_inputs(seed=40 + live)
+    z = _np(net1.flow(dev(z_p), dev(mask), reverse=True))
+    ref = Oracle(np.float64).flow_reverse(sd, base_dims, z_p.astype(np.float64), mask.astype(np.float64))
+    x0 = slice(0, 96) if (base_dims.n_flows - live) % 2 == 0 else slice(96, 192)
+    x1 = slice(96, 192) if x0.start == 0 else slice(0, 96)
+    # value equality like torch.equal: under the mask a zero may be +0 where z_p * 0 is -0 (the identity couplings add
+    # post(h) = +0 to x1 = -0); every unmasked element is compared bit for bit
+    assert np.array_equal(z[:, x0], (z_p * mask)[:, x0])
+    live_rows = np.broadcast_to(mask != 0, z.shape)[:, x0]
+    assert z[:, x0][live_rows].tobytes() == z_p[:, x0][live_rows].tobytes()
+    assert np.abs(z[:, x1] - ref[:, x1]).max() <= TOL
+    assert np.abs(ref[:, x1] - (z_p * mask)[:, x1]).max() > 1e-2  # the live half really moved
+
+
+def test_flow_tail_against_reference_trace(net, base_sd, base_dims):
+    """All couplings alive (reference trace of infer_base_b1_t12_maxlen9): the GPU's reverse flow from the reference's
+    z_p agrees with the reference's state after the last coupling on BOTH halves within 1e-4.  (Bit-exactness of the
+    pass-through half is pinned by the two tests above, where the GPU's own input to that half is known.)"""
     from gpu_util import dev
     g = load_golden("infer_base_b1_t12_maxlen9")
-    mask = g["ref32_x_mask"]
-    z_in = g["trace_flow2"]  # fp32 copy of the state after RCL1
-    # run only the tail [Flip, RCL0] through the oracle in fp32
-    orc = Oracle(np.float32)
-    ref = orc.coupling_reverse(base_sd, "flow.flows.0", base_dims, orc.flip(z_in), mask)
-    # and the full reverse flow on the GPU from z_p; compare the untouched half of the final result
-    z = _np(net.flow(dev(g["ref64_z_p"]), dev(mask), reverse=True))
-    assert ref[:, :96].tobytes() == orc.flip(z_in)[:, :96].tobytes()  # oracle: x0 passes through
-    assert np.abs(z[:, 96:] - ref[:, 96:]).max() <= TOL
+    z = _np(net.flow(dev(g["ref64_z_p"]), dev(g["ref32_x_mask"]), reverse=True))
+    assert np.abs(z - g["trace_flow3"]).max() <= TOL
+    assert np.abs(z - g["ref64_z"]).max() <= TOL
+
+
+def test_infer_matches_reference_golden_multitile(net):
+    """B=3, T=300, lengths (300, 257, 129): tile borders inside every utterance, ragged rows (F10), generated by the
+    unmodified reference (tests/golden/make_golden_multitile.py)."""
+    g = load_golden("infer_base_b3_t300_ragged")
+    o, mask, (z, z_p, m_p, logs_p) = _run_infer(net, g)
+    assert np.array_equal(_np(mask), g["ref32_x_mask"])
+    e_o = np.abs(_np(o) - g["ref64_o"]).max()
+    print("multi-tile golden: GPU vs ref64 on o %.2e (reference fp32 vs fp64 %.2e); z %.2e" %
+          (e_o, float(g["ref32_vs_ref64_o"]), np.abs(_np(z) - g["ref64_z"]).max()))
+    assert e_o <= TOL
+    assert np.abs(_np(z) - g["ref64_z"]).max() <= TOL and np.abs(_np(m_p) - g["ref64_m_p"]).max() <= TOL
+
+
+# ------------------------------------------------------------------------ operand range of the fp16 hi/lo engine
+def _rel_err(y, ref):
+    return float(np.abs(y - ref).max() / np.sqrt((ref ** 2).mean()))
+
+
+def test_cold_recipe_relative_error(net, base_cfg, base_dims):
+    """Reference random init (zero `post`, unit decoder gains): |o| ~ 0.02, activations down to 1e-3.  The
+    absolute 1e-4 bar is vacuous there, so the error is stated RELATIVE to the signal's rms: the lo halves of the
+    fp16 pairs are stored scaled by 2^11 (tc_common.cuh), which keeps the pairs exact to 22 bits down to |x| = 6e-5."""
+    import svk_weights as W
+    from gpu_util import build_net, dev, inject_eps
+    sd = W.make_state_dict(base_dims, seed=1234, alive=False)
+    netc = build_net(base_cfg["model"], sd, engine=net.engine)
+    rng = np.random.Generator(np.random.Philox(key=[51, 2]))
+    B, T = 2, 40
+    mel = (rng.standard_normal((B, 80, T)) * 2 - 5).astype(np.float32)
+    eps = rng.standard_normal((B, 192, T)).astype(np.float32)
+    lengths = np.array([40, 31], np.int64)
+    with inject_eps(eps), torch.no_grad():
+        o = _np(netc.infer(dev(mel), dev(lengths, torch.int64), noise_scale=0.667)[0])
+    ro = Oracle(np.float64).infer(sd, base_dims, mel, lengths, eps, 0.667, None)[0]
+    ro32 = Oracle(np.float32).infer(sd, base_dims, mel, lengths, eps, 0.667, None)[0]
+    print("cold recipe (%s): |o| max %.4f rms %.4f; GPU rel err %.2e (abs %.2e); fp32 CPU oracle rel err %.2e" %
+          (net.engine, np.abs(ro).max(), np.sqrt((ro ** 2).mean()), _rel_err(o, ro), np.abs(o - ro).max(), _rel_err(ro32, ro)))
+    assert np.abs(o - ro).max() <= TOL
+    assert _rel_err(o, ro) <= 2e-4  # of the signal's rms
+
+
+@pytest.mark.parametrize("scale", [1e-3, 1.0, 1e3])
+@pytest.mark.parametrize("idx", [4, 11])
+def test_resblock_relative_error_over_operand_range(net, base_sd, base_dims, idx, scale):
+    """A ResBlock1 is positively homogeneous up to its biases, so feeding x * scale sweeps the magnitude of every operand
+    image: small (lo halves would be fp16 subnormals unscaled), nominal, large (|activations| ~ 1e4, near the top of the
+    fp16 range).  Error is reported relative to the output's rms and must stay at fp32 class on all three."""
+    import svk_runtime as rt
+    from gpu_util import dev
+    C = {4: 128, 11: 32}[idx]
+    L = 700
+    rng = np.random.Generator(np.random.Philox(key=[61, idx]))
+    x = (rng.standard_normal((1, C, L)) * scale).astype(np.float32)
+    k = base_dims.resblock_kernel_sizes[idx % 3]
+    ref = Oracle(np.float64).resblock1(base_sd, f"dec.resblocks.{idx}", x, k, (1, 3, 5))
+    xd, y = dev(x), torch.empty(1, C, L, device="cuda")
+    ws = torch.empty(rt.lib().svk_resblock1_workspace_bytes(net._handle.ptr, idx, 1, L), dtype=torch.uint8, device="cuda")
+    rt.check(rt.lib().svk_resblock1(net._handle.ptr, idx, xd.data_ptr(), 1, L, y.data_ptr(), ws.data_ptr(), ws.numel(),
+                                    torch.cuda.current_stream().cuda_stream))
+    rel = _rel_err(_np(y), ref)
+    print("resblock %d (%s) at input scale %g: |y| max %.3g, rel err %.2e" % (idx, net.engine, scale, np.abs(ref).max(), rel))
+    assert rel <= 2e-5
+
+
+def test_hot_recipe_fails_loudly(base_cfg, base_dims):
+    """Decoder gains x2 on top of the alive recipe: the reference's own fp32 activations reach 3e7 (measured with forward
+    hooks), far above fp16's 65504.  The tensor-core engine must not hand back NaN audio silently: infer raises
+    SVK_ERR_RANGE (svk_check_range); with range_check off the NaNs are there and check_range() reports them; the fp32
+    FFMA engine computes the (saturated) waveform."""
+    import svk_runtime as rt
+    import svk_weights as W
+    from gpu_util import build_net, dev, inject_eps
+    sd = W.make_state_dict(base_dims, seed=1234)
+    for k in sd:
+        if k.startswith("dec.") and k.endswith("weight_g"):
+            sd[k] = sd[k] * np.float32(2.0)
+    rng = np.random.Generator(np.random.Philox(key=[5, 5]))
+    mel = (rng.standard_normal((1, 80, 24)) * 2 - 5).astype(np.float32)
+    eps = rng.standard_normal((1, 192, 24)).astype(np.float32)
+    ln = np.array([24], np.int64)
+    hot = build_net(base_cfg["model"], sd, engine="tc")
+    with inject_eps(eps), torch.no_grad():
+        with pytest.raises(rt.SvkError) as ei:
+            hot.infer(dev(mel), dev(ln, torch.int64), noise_scale=0.667)
+    assert ei.value.code == rt.SVK_ERR_RANGE
+    hot.range_check = False
+    with inject_eps(eps), torch.no_grad():
+        o = hot.infer(dev(mel), dev(ln, torch.int64), noise_scale=0.667)[0]
+    assert not torch.isfinite(o).all()
+    with pytest.raises(rt.SvkError):
+        hot.check_range()
+    hot.check_range()  # the flag is cleared by the failing check
+    with pytest.raises(rt.SvkError):  # host entry point checks before it returns
+        hot.infer_host(mel, ln, eps, 0.667)
+    ok = build_net(base_cfg["model"], sd, engine="fp32")
+    with inject_eps(eps), torch.no_grad():
+        o32 = ok.infer(dev(mel), dev(ln, torch.int64), noise_scale=0.667)[0]
+    ro = Oracle(np.float32).infer(sd, base_dims, mel, ln, eps, 0.667, None)[0]
+    # a saturated square wave: only samples whose pre-tanh value happens to be O(1) among values of 1e6 can differ
+    assert torch.isfinite(o32).all() and (np.abs(_np(o32) - ro) > 1e-3).mean() <= 1e-3
 
 
 def test_determinism(net):
@@ -367,3 +530,32 @@ def test_config4_bf16_at_b64_t512(base_cfg, base_sd):
     snr = 10 * np.log10((outs["tc"] ** 2).sum(axis=(1, 2)) / (err ** 2).sum(axis=(1, 2)))
     print("bf16 vs tc at 64x512: SNR min %.1f dB, median %.1f dB" % (snr.min(), np.median(snr)))
     assert snr.min() >= 30.0
+
+
+def test_config5_shard_at_b64_t1024(net, base_sd, base_dims):
+    """BASELINE configs[4] per-GPU shape: 64 utterances x 1024 frames (16 GB workspace; 2^31-element tensors in the
+    narrow stages).  Oracle on cropped windows: the interior of a full-length utterance late in the batch, and a window
+    straddling the end of a shorter (padded) one, where the unmasked decoder runs on into the padding."""
+    from gpu_util import dev, inject_eps
+    if net.engine != "tc":
+        pytest.skip("full-size shape: default engine only (the FFMA engine takes 9x longer)")
+    B, T = 64, 1024
+    rng = np.random.Generator(np.random.Philox(key=[1024, 64]))
+    mel = (rng.standard_normal((B, 80, T)) * 2 - 5).astype(np.float32)
+    eps = rng.standard_normal((B, 192, T)).astype(np.float32)
+    lengths = np.full(B, T, np.int64)
+    lengths[9] = 700
+    with inject_eps(eps), torch.no_grad():
+        o_d, mask_d, _ = net.infer(dev(mel), dev(lengths, torch.int64), noise_scale=0.667)
+    assert tuple(o_d.shape) == (B, 1, 256 * T) and bool(torch.isfinite(o_d).all())
+    assert np.array_equal(_np(mask_d), Oracle.sequence_mask(lengths, T).astype(np.float32))
+    for b, lo, hi, a0, a1 in ((61, 400, 640, 512, 528), (9, 580, 830, 690, 706)):
+        ln = np.array([min(max(int(lengths[b]) - lo, 0), hi - lo)], np.int64)
+        ro, _, _ = Oracle(np.float32).infer(base_sd, base_dims, mel[b:b + 1, :, lo:hi], ln, eps[b:b + 1, :, lo:hi], 0.667, None)
+        ref = ro[0, 0, (a0 - lo) * 256:(a1 - lo) * 256]
+        got = _np(o_d[b, 0, a0 * 256:a1 * 256])
+        assert np.abs(got - ref).max() <= TOL, b
+    # last utterance alone == inside the batch, bit for bit (no cross-utterance term, no 32-bit offset wrap)
+    with inject_eps(eps[63:64]), torch.no_grad():
+        o1 = net.infer(dev(mel[63:64]), dev(lengths[63:64], torch.int64), noise_scale=0.667)[0]
+    assert torch.equal(o1[0], o_d[63])

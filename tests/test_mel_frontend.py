@@ -172,8 +172,6 @@ def test_gpu_frontend_errors():
     with pytest.raises(rt.SvkError):
         mp.spectrogram_torch(torch.zeros(1, 384, device="cuda"), 1024, 22050, 256, 1024)   # n <= pad: reflect impossible
     with pytest.raises(rt.SvkError):
-        mp.spectrogram_torch(torch.zeros(1, 4096), 1024, 22050, 256, 1024)                  # CPU tensor
-    with pytest.raises(rt.SvkError):
         mp.spectrogram_torch(torch.zeros(1, 4096, device="cuda"), 1000, 22050, 250, 1000)   # n_fft not a power of two
     with pytest.raises(NotImplementedError):
         mp.spectrogram_torch(torch.zeros(1, 4096, device="cuda"), 1024, 22050, 256, 1024, center=True)
@@ -199,6 +197,40 @@ def test_gpu_wave_to_wave_through_frontend(base_cfg, base_sd):
         o, mask, _ = net.infer(mel, torch.tensor([40], device="cuda"), noise_scale=0.667)
     torch.cuda.synchronize()
     assert tuple(o.shape) == (1, 1, n) and torch.isfinite(o).all() and float(o.abs().max()) <= 1.0
+
+
+@pytest.mark.gpu
+def test_gpu_notebook_cell4_replay_with_cpu_waveform(base_cfg, base_sd):
+    """inference.ipynb cell 4, line for line: the waveform and the spectrogram are CPU tensors
+    (`spectrogram_torch(audio_norm, ...)`, `spec_to_mel_torch(spec, ...)`), `mel.cuda()` comes afterwards.  The shim
+    must take them and give back CPU tensors equal to what the CUDA-tensor path produces."""
+    torch, mp = _gpu_mods()
+    from models import SynthesizerTrn
+    d = base_cfg["data"]
+    net_g = SynthesizerTrn(d["filter_length"] // 2 + 1, base_cfg["train"]["segment_size"] // d["hop_length"],
+                           n_speakers=d["n_speakers"], **base_cfg["model"]).cuda()
+    _ = net_g.eval()
+    net_g.load_state_dict({k: torch.from_numpy(v) for k, v in base_sd.items()})
+    n = 30 * d["hop_length"]
+    audio = (0.3 * 32768.0 * torch.sin(2 * np.pi * 330.0 * torch.arange(n) / d["sampling_rate"]))  # load_wav_to_torch: CPU float
+    audio_norm = audio / 32768.0
+    audio_norm = audio_norm.unsqueeze(0)
+    spec = mp.spectrogram_torch(audio_norm, 1024, 22050, 256, 1024, center=False)
+    mel = mp.spec_to_mel_torch(spec, d["filter_length"], d["n_mel_channels"], d["sampling_rate"], d["mel_fmin"], d["mel_fmax"])
+    assert spec.device.type == "cpu" and mel.device.type == "cpu" and tuple(mel.shape) == (1, 80, 30)
+    spec_d = mp.spectrogram_torch(audio_norm.cuda(), 1024, 22050, 256, 1024, center=False)
+    assert torch.equal(spec, spec_d.cpu())
+    with torch.no_grad():
+        mel = mel.cuda()
+        spec_lengths = torch.LongTensor([mel.size(2)]).cuda()
+        audio_ = net_g.infer(mel, spec_lengths, sid=None, noise_scale=.667, noise_scale_w=0.8, length_scale=1)[0][0, 0].data.cpu().float().numpy()
+    assert audio_.shape == (n,) and np.isfinite(audio_).all()
+    # `.float()` is a no-op in the reference and must not unbind the uploaded weights (ADVICE r1)
+    net_g = net_g.float()
+    net_g.to(torch.float32)
+    with torch.no_grad():
+        net_g.infer(mel, spec_lengths, noise_scale=.667)
+    assert net_g.cpu()._handle is None
 
 
 def test_shim_signatures_match_the_reference():

@@ -74,6 +74,16 @@ def test_oracle_fp32_matches_reference_base_padded_batch(base_sd, base_dims):
     assert np.abs(o - g["ref32_o"]).max() <= 5e-5
 
 
+def test_oracle_fp32_matches_reference_multitile_ragged(base_sd, base_dims):
+    """B=3, T=300, lengths (300, 257, 129): several 128-frame tiles per utterance, ragged (make_golden_multitile.py)."""
+    g = load_golden("infer_base_b3_t300_ragged")
+    orc = Oracle(np.float32)
+    o, mask, (z, z_p, m_p, logs_p) = orc.infer(base_sd, base_dims, g["mel"], g["lengths"], g["eps"], float(g["noise_scale"]), None)
+    assert np.array_equal(mask.astype(np.float32), g["ref32_x_mask"])
+    assert np.abs(o - g["ref64_o"]).max() <= 5e-5
+    assert np.abs(z - g["ref64_z"]).max() <= 5e-5 and np.abs(m_p - g["ref64_m_p"]).max() <= 5e-5
+
+
 def test_flip_and_mask_bit_exact():
     x = np.arange(2 * 6 * 5, dtype=np.float32).reshape(2, 6, 5)
     assert np.array_equal(Oracle.flip(x), x[:, ::-1])
