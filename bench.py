@@ -3,6 +3,8 @@
 
     python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N>1)
     python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU PyTorch path (rank 0 only)
+    python bench.py --impl torch-gpu --steps K ...            # the reference's modules on the same B200 through
+                                                              # PyTorch eager + cuDNN, TF32 off and on
 
 One "step" = one pass of SynthesizerTrn.infer (MelEncoder + inverse flow + HiFi-GAN decoder) over one
 batch of synthetic 80 x T mels per GPU.  Workload at N=1: BASELINE.json configs[2] -- iitp_base.json,
@@ -13,8 +15,11 @@ plumbing case; both are parity tests, not bench lines).  For N>1 every rank runs
 Prints ONE JSON line (rank 0).  `value` = whole-job audio samples/s with inputs resident in HBM;
 `e2e` = the same through the reference-facing `SynthesizerTrn.infer` call from pinned HOST buffers
 (H2D of mel+lengths and D2H of the PCM inside the timed region; NCCL scatter/gather for N>1);
-`roofline` = the dominant kernel against the pipe it runs on; `cpu_baseline` = oracle/torch_port.py
-(the reference's torch-CPU operators restated) on the box's host cores.
+`roofline` = the dominant kernel against the pipe it runs on; `cpu_baseline` = the UNMODIFIED reference
+(oracle/_ref, vendored by oracle/vendor_ref.py; oracle/torch_port.py only if that is absent) on the box's host
+cores.  Extra objects in the same line: `gpu_eager_baseline` (the reference on this GPU through PyTorch eager),
+`latency_b1` (BASELINE configs[1] shape, one utterance), `c4_bf16` (configs[3]), `c5_shard` (configs[4]'s
+64x1024 per GPU).
 """
 from __future__ import annotations
 
@@ -68,26 +73,52 @@ def synth_inputs(B, T, seed=0):
     return mel, lengths
 
 
-# ----------------------------------------------------------------------------------- CPU side
-def cpu_reference_run(B, T, steps, warmup, threads=None):
-    """Time oracle/torch_port.infer (reference operators on torch CPU) -> list of seconds per step."""
-    from oracle import torch_port
-    if threads:
-        torch.set_num_threads(threads)
+# ----------------------------------------------------------------------------------- CPU / eager side
+def seeded_state_dict(dims):
+    return W.make_state_dict(dims, seed=1234)
+
+
+def make_reference_runner(device="cpu"):
+    """-> (fn(mel, lengths) -> o, kind, description).  The unmodified reference (oracle/_ref, vendored by
+    oracle/vendor_ref.py) when present, else oracle/torch_port.py (its torch operators restated)."""
+    from oracle import ref_loader
     cfg = load_cfg()
     dims = W.dims_from_model_kwargs(513, **cfg["model"])
-    sd = {k: torch.from_numpy(v) for k, v in W.make_state_dict(dims, seed=1234).items()}
+    sd = seeded_state_dict(dims)
+    net = ref_loader.build_reference_net(cfg["model"], sd, 513, cfg["train"]["segment_size"] // cfg["data"]["hop_length"],
+                                         cfg["data"]["n_speakers"])
+    if net is not None:
+        net = net.to(device)
+
+        def fn(mel, lengths):
+            return net.infer(mel, lengths, noise_scale=NOISE_SCALE)[0]
+        return fn, "reference", ("unmodified reference SynthesizerTrn.infer (models.py:331-339) imported from oracle/_ref "
+                                 "(weight_norm recomputed per call, as the reference does)")
+    from oracle import torch_port
+    sdt = {k: torch.from_numpy(v).to(device) for k, v in sd.items()}
+
+    def fn2(mel, lengths):
+        return torch_port.infer(sdt, dims, mel, lengths, None, NOISE_SCALE, None)[0]
+    return fn2, "port", "oracle/torch_port.py (the reference's torch operators restated; oracle/_ref not vendored)"
+
+
+def cpu_reference_run(B, T, steps, warmup, threads=None):
+    """Time the reference path on the host cores -> (seconds per step, kind, description)."""
+    if threads:
+        torch.set_num_threads(threads)
+    fn, kind, desc = make_reference_runner("cpu")
     mel, lengths = synth_inputs(B, T)
     torch.manual_seed(1)
     times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        o = torch_port.infer(sd, dims, mel, lengths, None, NOISE_SCALE, None)[0]
-        dt = time.perf_counter() - t0
-        assert o.shape == (B, 1, 256 * T)
-        if i >= warmup:
-            times.append(dt)
-    return times
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            o = fn(mel, lengths)
+            dt = time.perf_counter() - t0
+            assert o.shape == (B, 1, 256 * T)
+            if i >= warmup:
+                times.append(dt)
+    return times, kind, desc
 
 
 def run_reference_arm(args):
@@ -97,25 +128,100 @@ def run_reference_arm(args):
         return 0
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    B, T = 1, args.frames  # bounded sample: one utterance of the per-GPU batch (utterances are independent)
-    times = cpu_reference_run(B, T, args.steps, max(args.warmup, 1), cores)
+    T, Bfull = args.frames, args.batch_per_gpu
+    fn, kind, desc = make_reference_runner("cpu")
+    W_, K = max(args.warmup, 1), args.steps
+    # bounded sample: as many utterances of the per-GPU batch as keep the whole run near `--ref-budget-s` seconds
+    # (utterances are independent; the reference is FASTER per sample at small batch -- SURVEY 6 -- so a sample flatters it)
+    torch.manual_seed(1)
+    mel1, len1 = synth_inputs(1, T)
+    with torch.no_grad():
+        fn(mel1, len1)  # first call: thread pool / primitive-cache start-up, not a step
+        t0 = time.perf_counter()
+        fn(mel1, len1)
+        t1 = time.perf_counter() - t0
+    Bs = int(max(1, min(Bfull, args.ref_budget_s / max(t1 * (K + W_), 1e-6))))
+    mel, lengths = synth_inputs(Bs, T)
+    times = []
+    with torch.no_grad():
+        for i in range(W_ + K):
+            t0 = time.perf_counter()
+            o = fn(mel, lengths)
+            dt = time.perf_counter() - t0
+            if i >= W_:
+                times.append(dt)
+    assert o.shape == (Bs, 1, 256 * T)
     total = sum(times)
-    value = B * 256 * T * len(times) / total
+    value = Bs * 256 * T * len(times) / total
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "warmup": W_, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "rtf": (total / len(times)) / (B * 256 * T / SAMPLE_RATE),
-        "config": {"workload": f"iitp_base.json full path, {args.batch_per_gpu}x80x{T} mel per GPU, fp32 "
-                               f"(BASELINE configs[2]); reference arm times a 1x80x{T} sample of it per step",
-                   "frames": T, "batch_per_gpu": args.batch_per_gpu},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"oracle/torch_port.py (reference torch-CPU operators, weight_norm recomputed per "
-                                   f"call) on 1x80x{T} mel, mean of {len(times)} steps"},
+        "rtf": (total / len(times)) / (Bs * 256 * T / SAMPLE_RATE),
+        "config": {"workload": f"iitp_base.json full path, {Bfull}x80x{T} mel per GPU, fp32 (BASELINE configs[2]); the "
+                               f"reference arm times {Bs} of the {Bfull} utterances per step (independent units, throughput "
+                               f"scales linearly; the reference is faster per sample at small batch)",
+                   "frames": T, "batch_per_gpu": Bfull, "sample_batch": Bs},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                         "sample": f"{desc}; {Bs}x80x{T} mel per step ({Bs}/{Bfull} of the step), mean of {len(times)} steps"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+    return 0
+
+
+def gpu_eager_baseline(B, T, dev, steps=5, warmup=3):
+    """The reference's modules on the SAME GPU through PyTorch eager + cuDNN (the kernel-level bar), TF32
+    off (an fp32 result) and on (torch's default).  Device-resident inputs, CUDA events, L2 flushed."""
+    fn, kind, desc = make_reference_runner(dev)
+    mel, lengths = synth_inputs(B, T)
+    mel, lengths = mel.to(dev), lengths.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = {"kind": kind, "what": desc + f", .cuda(), {B}x80x{T}, PyTorch {torch.__version__} eager, cuDNN "
+                                      f"{torch.backends.cudnn.version()}, cudnn.benchmark off (stock)", "unit": UNIT}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for tag, tf32 in (("tf32_off", False), ("tf32_on", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            with torch.no_grad():
+                for i in range(warmup):
+                    flush.fill_(i)
+                    o = fn(mel, lengths)
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(steps):
+                    flush.fill_(i)
+                    o = fn(mel, lengths)
+                e1.record()
+                torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / steps
+            out[tag] = {"value": B * 256 * T / (ms / 1e3), "ms_per_step": ms, "finite": bool(torch.isfinite(o).all())}
+            del o
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_torch_gpu_arm(args):
+    """`--impl torch-gpu`: one JSON line for the reference on the GPU through PyTorch eager (rank 0, one GPU)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    if not torch.cuda.is_available():
+        emit({"impl": "torch-gpu", "unavailable": "no CUDA device"})
+        return 0
+    dev = torch.device("cuda", 0)
+    B, T = args.batch_per_gpu, args.frames
+    g = gpu_eager_baseline(B, T, dev, steps=args.steps, warmup=max(args.warmup, 3))
+    off = g["tf32_off"]
+    emit({"impl": "torch-gpu", "metric": METRIC, "value": off["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+          "warmup": max(args.warmup, 3), "ms_per_step": off["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+          "config": {"workload": f"iitp_base.json full path, {B}x80x{T} mel, fp32 (TF32 off) through PyTorch eager + cuDNN"},
+          "gpu_eager_baseline": g, "gpu_launches": 0})
     return 0
 
 
@@ -206,6 +312,101 @@ def aggregate_profile(records, steps):
     total_ms = sum(f["ms"] for f in fam.values())
     top_key, top = max(fam.items(), key=lambda kv: kv[1]["ms"])
     return total_ms, top_key, top, by_layer, by_engine
+
+
+def _timed_steps(fn, K, Wm, flush, barrier, dev, world):
+    """Wm warm-up + K timed calls of fn() with the L2 flush in between, CUDA events, max over ranks -> ms per step."""
+    import torch.distributed as dist
+    for i in range(Wm):
+        flush.fill_(i & 0xFF)
+        fn()
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        flush.fill_(i & 0xFF)
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) / K
+
+
+def run_extras(args, net, dims, cfg, dev, world, rank, barrier, flush):
+    """Measurements beside the headline, in the same process on the same box (VERDICT r1 'missing' 3/4, N2, N3)."""
+    from models import SynthesizerTrn
+    out = {}
+    T = args.frames
+    net.range_check = False
+    # ---- BASELINE configs[4]: 64 utterances x 1024 frames per GPU (512 over 8 GPUs), device-resident, weak sharding
+    B5 = args.c5_batch
+    if B5 > 0:
+        mel5, len5 = synth_inputs(B5, T, seed=100 + rank)
+        mel5, len5 = mel5.to(dev), len5.to(dev)
+        K5 = max(2, min(args.steps, 5))
+        ms5 = _timed_steps(lambda: net.infer(mel5, len5, noise_scale=NOISE_SCALE), K5, 1, flush, barrier, dev, world)
+        net.check_range()
+        out["c5_shard"] = {"value": B5 * world * dims.hop * T / (ms5 / 1e3), "unit": UNIT, "ms_per_step": ms5, "steps": K5,
+                           "warmup": 1, "workload": f"BASELINE configs[4] per-GPU shape: {B5}x80x{T} mel per GPU, "
+                           f"{B5 * world} utterances over {world} GPU(s), fp32-class engine, inputs resident in HBM",
+                           "workspace_bytes": int(net._handle.workspace_bytes(B5, T, T))}
+        del mel5, len5
+    if world > 1:
+        net.range_check = True
+        return out
+    # ---- BASELINE configs[1] shape / the notebook's actual use: ONE utterance of 1024 frames, latency
+    mel1, len1 = synth_inputs(1, T, seed=7)
+    mel1, len1 = mel1.to(dev), len1.to(dev)
+    lat = []
+    for i in range(3 + 20):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        net.infer(mel1, len1, noise_scale=NOISE_SCALE)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            lat.append(e0.elapsed_time(e1))
+    net.check_range()
+    out["latency_b1"] = {"median_ms": statistics.median(lat), "min_ms": min(lat), "max_ms": max(lat), "calls": len(lat),
+                         "launches": int(net.last_launch_count()),
+                         "rtf": statistics.median(lat) / 1e3 / (dims.hop * T / SAMPLE_RATE),
+                         "workload": f"1x80x{T} mel (inference.ipynb:114-118), device-resident, one infer per measurement, "
+                                     f"CUDA events around the call, L2 warm"}
+    if hasattr(net, "infer_graph"):
+        try:
+            g_lat = net.infer_graph_latency(mel1, len1, NOISE_SCALE, calls=20)
+            out["latency_b1"]["cuda_graph_median_ms"] = statistics.median(g_lat)
+            out["latency_b1"]["cuda_graph_min_ms"] = min(g_lat)
+        except Exception as e:  # pragma: no cover
+            out["latency_b1"]["cuda_graph_error"] = str(e)[:200]
+    # ---- the reference's modules on this GPU through PyTorch eager + cuDNN (the kernel-level bar, SURVEY 2.2)
+    try:
+        out["gpu_eager_baseline"] = gpu_eager_baseline(args.batch_per_gpu, T, dev, steps=3, warmup=2)
+    except Exception as e:  # pragma: no cover
+        out["gpu_eager_baseline"] = {"error": str(e)[:300]}
+    # ---- BASELINE configs[3]: 64 x 80x512, bf16 operands / fp32 accumulate
+    if args.engine != "bf16" and args.c4_batch > 0:
+        net16 = SynthesizerTrn(513, 32, n_speakers=cfg["data"]["n_speakers"], engine="bf16", range_check=False, **cfg["model"])
+        net16.load_state_dict({k: torch.from_numpy(v) for k, v in seeded_state_dict(dims).items()})
+        net16 = net16.cuda().eval()
+        B4, T4 = args.c4_batch, 512
+        mel4, len4 = synth_inputs(B4, T4, seed=9)
+        mel4, len4 = mel4.to(dev), len4.to(dev)
+        K4 = max(2, min(args.steps, 5))
+        ms4 = _timed_steps(lambda: net16.infer(mel4, len4, noise_scale=NOISE_SCALE), K4, 2, flush, barrier, dev, world)
+        out["c4_bf16"] = {"value": B4 * dims.hop * T4 / (ms4 / 1e3), "unit": UNIT, "ms_per_step": ms4, "steps": K4, "warmup": 2,
+                          "dtype": "bf16", "workload": f"BASELINE configs[3]: {B4}x80x{T4} mel, bf16 operands (activation images "
+                          f"and weights), one tcgen05 pass per conv, fp32 accumulate; tolerance stated in tests/test_gpu_parity.py",
+                          "frac_of_bf16_ceiling": (FLOP_PER_FRAME * B4 * T4 / (ms4 / 1e3) / 1e12) / measured_peaks()["bf16_tflops_sustained"]}
+        del net16, mel4, len4
+        torch.cuda.empty_cache()
+    net.range_check = True
+    return out
 
 
 def run_b200_arm(args):
@@ -334,6 +535,11 @@ def run_b200_arm(args):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te[1].item())  # wall clock bracketed by syncs: includes the host-side copies' latency
 
+        # ---------------- extra measurements (same run, same box) ----------------
+        extras = {}
+        if not args.no_extras:
+            extras = run_extras(args, net, dims, cfg, dev, world, rank, barrier, flush)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -401,6 +607,30 @@ def run_b200_arm(args):
                        "profiled_gap_ms_per_step": sum(r["gap_ms"] for r in records) / K},
     }
 
+    # honest traffic accounting: what the launches move, split into what an fp32-only layer-by-layer
+    # schedule would move too and what exists only because tensors are kept twice (fp32 + fp16 hi/lo operand image)
+    alg_b = sum(r["bytes"] for r in records) / K
+    dup_b = sum(r["dup_bytes"] for r in records) / K
+    yard = 4_282_688 * B * T  # unfused fp32 conv-boundary traffic per frame, measured with hooks on the reference
+    roofline["traffic_accounting"] = {
+        "algorithmic_bytes_per_step": alg_b, "operand_image_duplicate_bytes_per_step": dup_b,
+        "compulsory_bytes_per_step": alg_b - dup_b, "unfused_fp32_yardstick_bytes_per_step": yard,
+        "ratio_to_yardstick": alg_b / yard, "hbm_floor_ms_per_step": alg_b / (peaks["hbm_gbs"] * 1e9) * 1e3,
+        "note": "sum over launches of input + outputs + residual operands + weights; an operand image counts 4 B/element "
+                "(two fp16 planes); `duplicate` = images written beside an fp32 copy of the same values + split_image launches"}
+    # the most HBM-bound family beside the dominant tensor-bound one
+    fam_hbm = {}
+    for r in records:
+        if r["engine"] != "tc" or r["ms"] <= 0:
+            continue
+        f = fam_hbm.setdefault((r["layer"], r["cin"], r["k"]), {"ms": 0.0, "bytes": 0.0, "n": 0})
+        f["ms"] += r["ms"]; f["bytes"] += r["bytes"]; f["n"] += 1
+    if fam_hbm:
+        (hl, hc, hk), hf = max(fam_hbm.items(), key=lambda kv: kv[1]["bytes"] / kv[1]["ms"])
+        hg = hf["bytes"] / hf["ms"] / 1e6
+        roofline["most_hbm_bound_family"] = {"layer": hl, "cin": hc, "k": hk, "avg_launch_ms": hf["ms"] / hf["n"],
+                                             "achieved_gbs": hg, "peak_gbs": peaks["hbm_gbs"], "frac": hg / peaks["hbm_gbs"]}
+
     if args.dump_profile:
         groups = {}
         for r in records:
@@ -418,10 +648,10 @@ def run_b200_arm(args):
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        times = cpu_reference_run(1, T, steps=args.cpu_steps, warmup=1, threads=cores)
+        times, kind, desc = cpu_reference_run(1, T, steps=args.cpu_steps, warmup=1, threads=cores)
         best = min(times)
-        cpu_baseline = {"value": 256 * T / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                        "sample": f"oracle/torch_port.py (reference torch-CPU operators) on 1x80x{T} mel = 1/{B} of the step; "
+        cpu_baseline = {"value": 256 * T / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                        "sample": f"{desc} on 1x80x{T} mel = 1/{B} of the step; "
                                   f"best of {len(times)} after 1 warm-up; mean {statistics.mean(times):.2f}s",
                         "rtf": best / (256 * T / SAMPLE_RATE)}
 
@@ -454,6 +684,7 @@ def run_b200_arm(args):
         "clocks": clocks,
         "device": prop.name,
     }
+    line.update(extras)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -483,7 +714,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch-gpu"])
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="reference arm: wall-clock budget that sizes its per-step sample")
+    ap.add_argument("--no-extras", action="store_true", help="skip gpu_eager_baseline / latency_b1 / c4_bf16 / c5_shard")
     ap.add_argument("--batch-per-gpu", type=int, default=16)
     ap.add_argument("--frames", type=int, default=1024)
     ap.add_argument("--e2e-steps", type=int, default=5)
@@ -492,10 +725,14 @@ def main():
                     help="tc = tcgen05 fp16x3 (fp32-class, the default and the headline), fp32 = FFMA, "
                          "bf16 = BASELINE configs[3] arithmetic (use with --batch-per-gpu 64 --frames 512)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--c5-batch", type=int, default=64, help="utterances per GPU of the c5_shard extra (0 = skip)")
+    ap.add_argument("--c4-batch", type=int, default=64, help="utterances of the c4_bf16 extra (0 = skip)")
     ap.add_argument("--dump-profile", default=None, help="write the per-layer launch table (CUDA-event times) to this file")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.impl == "torch-gpu":
+        return run_torch_gpu_arm(args)
     return run_b200_arm(args)
 
 

@@ -184,6 +184,8 @@ int64_t svk_last_launch_count(const svk_handle *h);
 #define SVK_LAYER_RESBLOCK_CONV2 10
 #define SVK_LAYER_CONV_POST 11
 #define SVK_LAYER_RESBLOCK_PAIR 12 /* fused convs1[l] + convs2[l] + residual of a ResBlock1 (narrow stages) */
+#define SVK_LAYER_SPLIT_IMAGE 13   /* fp32 tensor -> operand image copy (pure duplicate traffic) */
+#define SVK_LAYER_WN_LAYER 14      /* fused WN layer: in_layer k5 + gate + res_skip 1x1 + residual / skip update */
 typedef struct svk_launch_record {
   int32_t layer;      /* SVK_LAYER_* */
   int32_t cin, cout;  /* logical channels */
@@ -196,6 +198,8 @@ typedef struct svk_launch_record {
   int32_t engine;     /* 0 = fp32 FFMA kernel, 1 = tcgen05 kernel */
   float gap_ms;       /* device time between the previous record's end event and this one's start */
   int32_t reserved;
+  double dup_bytes;   /* part of `bytes` that exists only because a tensor is kept twice (fp32 + fp16 hi/lo operand
+                         image of the same values): bytes - dup_bytes is what an fp32-only layer would move */
 } svk_launch_record;
 int svk_profile_begin(svk_handle *h, int max_records);
 int svk_profile_end(svk_handle *h, svk_launch_record *out, int max_records, int *n_records);

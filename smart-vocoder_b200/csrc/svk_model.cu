@@ -642,20 +642,26 @@ struct Runner {
     r.layer = layer, r.cin = a.Cin, r.cout = cout_logical, r.k = a.K, r.dilation = a.dil, r.batch = B;
     r.length = out_len;
     r.flops = 2.0 * macs;
-    // compulsory traffic of this launch: input (fp32 tensor or operand image, 4 B/element either way),
-    // weights, and per destination side the fp32 tensor and/or operand image written plus res / acc_in read
-    double bytes = 4.0 * ((double)B * a.Cin * a.Lin + (double)a.Cin * a.K * a.Cout);
+    // algorithmic traffic of this launch: input (fp32 tensor or operand image, 4 B/element either way with two planes),
+    // weights, and per destination side the fp32 tensor and/or operand image written plus res / acc_in read.
+    // dup = the image when the same values are ALSO written as fp32 (the tensor then lives in HBM twice).
+    const double img = h->planes() * 0.5;  // an operand image is 2 B per plane per element = img * 4 B
+    double bytes = 4.0 * ((double)B * a.Cin * a.Lin + (double)a.Cin * a.K * a.Cout), dup = 0.0;
     if (a.mode != MODE_STORE) {
-      bytes += 4.0 * B * (double)cout_logical * out_len;
+      const double per = 4.0 * B * (double)cout_logical * out_len;
+      const bool y = a.e[0].y != nullptr, sp = a.e[0].split != nullptr;
+      bytes += per * ((y ? 1 : 0) + (sp ? img : 0));
+      if (y && sp) dup += per * img;
     } else {
       for (int s = 0; s < 2; ++s) {
         const double n_s = s == 0 ? (a.split < a.Cout ? a.split : a.Cout) : (a.split < a.Cout ? a.Cout - a.split : 0);
         const double per = 4.0 * B * (double)out_len * n_s;
-        const double img = h->planes() * 0.5;  // an operand image is 2 B per plane per element
         bytes += per * ((a.e[s].y ? 1 : 0) + (a.e[s].split ? img : 0) + (a.e[s].res ? 1 : 0) + (a.e[s].res_img ? img : 0) +
                         (a.e[s].acc_in ? 1 : 0));
+        if (a.e[s].y && a.e[s].split) dup += per * img;
       }
     }
+    r.dup_bytes = dup;
     r.bytes = bytes;
     h->prof_records.push_back(r);
     cudaEventRecord(h->prof_events[2 * (h->prof_records.size() - 1)], stream);
@@ -704,6 +710,24 @@ struct Runner {
     if (err == cudaSuccess) err = e;
     h->launches++;
   }
+  // fp32 tensor -> operand image (split_image_kernel), recorded like a conv launch: all of its traffic is duplicate
+  void split_image(const float* x, int C, int L, float slope, uint16_t* img) {
+    if (err != cudaSuccess) return;
+    bool open = false;
+    if (h->profiling && h->prof_records.size() < h->prof_cap) {
+      svk_launch_record r;
+      memset(&r, 0, sizeof(r));
+      r.layer = SVK_LAYER_SPLIT_IMAGE, r.cin = C, r.cout = C, r.k = 1, r.dilation = 1, r.batch = B, r.length = L, r.engine = 0;
+      r.bytes = (4.0 + 2.0 * h->planes()) * B * (double)C * L;
+      r.dup_bytes = r.bytes;
+      h->prof_records.push_back(r);
+      cudaEventRecord(h->prof_events[2 * (h->prof_records.size() - 1)], stream);
+      open = true;
+    }
+    err = launch_split_image(x, B, C, L, slope, img, h->planes(), stream);
+    prof_close(open);
+    h->launches++;
+  }
 
   // Fused conv pair of a ResBlock1 (conv_tc_pair.cu) with the same per-launch accounting as run().
   bool pair_fusable(const ResBlock& rb, int l) const {
@@ -733,6 +757,7 @@ struct Runner {
       r.flops = 2.0 * 2.0 * E * rb.C * rb.k;  // both convs
       r.bytes = 4.0 * E * (1 + (p.res || p.res_img ? 1 : 0) + (p.acc_in ? 1 : 0) + (p.y ? 1 : 0) + (p.y_img ? 1 : 0)) +
                 2.0 * 4.0 * rb.C * rb.C * rb.k;
+      r.dup_bytes = (p.y && p.y_img) ? 4.0 * E : 0.0;
       h->prof_records.push_back(r);
       cudaEventRecord(h->prof_events[2 * (h->prof_records.size() - 1)], stream);
       open = true;
@@ -942,7 +967,7 @@ void run_decoder(Runner& R, const float* z, int z_stride, const float* in_mask, 
       R.run(a, SVK_LAYER_UPSAMPLE, (up.tc && pi >= 0) ? img[pi] : nullptr);
     }
     // xs = sum_j resblock_j(x); x = xs / num_kernels (models.py:150-155)
-    if (images && !up_writes_img) R.note(launch_split_image(X, R.B, C, Lout, 0.1f, x_img, h->planes(), R.stream));  // shared by the nk blocks
+    if (images && !up_writes_img) R.split_image(X, C, Lout, 0.1f, x_img);  // shared by the nk blocks
     const bool next_wants_img = images && i + 1 < c.n_upsamples && h->ups[i + 1].tc && C % 32 == 0;
     for (int j = 0; j < nk; ++j) {
       const ResBlock& rb = h->resblocks[i * nk + j];
@@ -1013,7 +1038,7 @@ void run_mel_encoder(Runner& R, const float* mel, const float* mask, int T, floa
   a.e[0].y = hbuf, a.e[0].C = H, a.e[0].use_mask = 1;
   R.run(a, SVK_LAYER_PRE_ENC);
   const bool images = x_img && acts_img && R.wn_uses_images(h->enc_in, h->enc_rs);
-  if (images) R.note(launch_split_image(hbuf, R.B, H, T, 1.0f, x_img, h->planes(), R.stream));  // pre_enc runs on the FFMA kernel
+  if (images) R.split_image(hbuf, H, T, 1.0f, x_img);  // pre_enc runs on the FFMA kernel
   R.wn(h->enc_in, h->enc_rs, hbuf, acts, out, mask, T, images ? x_img : nullptr, images ? acts_img : nullptr);
   // stats = proj(x) * x_mask; m, logs = split(stats) (models.py:44-46)
   ConvArgs p = R.base(h->proj, out, H, 0, T, T, 1, 0, T, T);
@@ -1039,7 +1064,7 @@ void run_flow_reverse(Runner& R, float* z, const float* mask, int T, float* hbuf
     const bool images = x_img && acts_img && R.wn_uses_images(L.in, L.rs);
     if (images && L.pre.tc) a.e[0].split = x_img, a.e[0].split_slope = 1.0f;
     R.run(a, SVK_LAYER_FLOW_PRE);
-    if (images && !L.pre.tc) R.note(launch_split_image(hbuf, R.B, H, T, 1.0f, x_img, h->planes(), R.stream));
+    if (images && !L.pre.tc) R.split_image(hbuf, H, T, 1.0f, x_img);
     R.wn(L.in, L.rs, hbuf, acts, out, mask, T, images ? x_img : nullptr, images ? acts_img : nullptr);
     // x1 = (x1 - post(h) * mask) * mask, written over x1's storage channels
     ConvArgs p = R.base(L.post, out, H, 0, T, T, 1, 0, T, T);
@@ -1065,7 +1090,7 @@ void run_posterior_encoder(Runner& R, const float* spec, const float* eps, const
   a.e[0].y = hbuf, a.e[0].C = H, a.e[0].use_mask = 1;
   R.run(a, SVK_LAYER_PRE_ENC);
   const bool images = x_img && acts_img && R.wn_uses_images(h->encq_in, h->encq_rs);
-  if (images) R.note(launch_split_image(hbuf, R.B, H, T, 1.0f, x_img, h->planes(), R.stream));
+  if (images) R.split_image(hbuf, H, T, 1.0f, x_img);
   R.wn(h->encq_in, h->encq_rs, hbuf, acts, out, mask, T, images ? x_img : nullptr, images ? acts_img : nullptr);
   ConvArgs p = R.base(h->encq_proj, out, H, 0, T, T, 1, 0, T, T);  // stats = proj(x) * x_mask
   p.out_mask = mask, p.mask_stride = T;
@@ -1092,7 +1117,7 @@ void run_flow_forward(Runner& R, float* z, const float* mask, int T, float* hbuf
     const bool images = x_img && acts_img && R.wn_uses_images(L.in, L.rs);
     if (images && L.pre.tc) a.e[0].split = x_img, a.e[0].split_slope = 1.0f;
     R.run(a, SVK_LAYER_FLOW_PRE);
-    if (images && !L.pre.tc) R.note(launch_split_image(hbuf, R.B, H, T, 1.0f, x_img, h->planes(), R.stream));
+    if (images && !L.pre.tc) R.split_image(hbuf, H, T, 1.0f, x_img);
     R.wn(L.in, L.rs, hbuf, acts, out, mask, T, images ? x_img : nullptr, images ? acts_img : nullptr);
     // x1 = m + x1 * exp(0) * mask = (post(h) + x1) * mask, written over x1's storage channels
     ConvArgs p = R.base(L.post_fwd, out, H, 0, T, T, 1, 0, T, T);
@@ -1510,7 +1535,7 @@ extern "C" int svk_resblock1(svk_handle* h, int index, const float* x, int B, in
   Runner R{h, (cudaStream_t)stream, B};
   if (R.resblock_uses_images(rb)) {
     uint16_t* x_img = reinterpret_cast<uint16_t*>(ws + n);
-    R.note(launch_split_image(x, B, rb.C, L, 0.1f, x_img, h->planes(), R.stream));
+    R.split_image(x, rb.C, L, 0.1f, x_img);
     R.resblock_images(rb, x, x_img, reinterpret_cast<uint16_t*>(ws + 2 * n), ws, reinterpret_cast<uint16_t*>(ws + 3 * n), y,
                       nullptr, 1.0f, L);
   } else {

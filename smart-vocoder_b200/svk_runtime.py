@@ -64,11 +64,13 @@ class SvkLaunchRecord(ctypes.Structure):
     _fields_ = [("layer", ctypes.c_int32), ("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("k", ctypes.c_int32),
                 ("dilation", ctypes.c_int32), ("batch", ctypes.c_int32), ("length", ctypes.c_int64),
                 ("flops", ctypes.c_double), ("bytes", ctypes.c_double), ("ms", ctypes.c_float),
-                ("engine", ctypes.c_int32), ("gap_ms", ctypes.c_float), ("reserved", ctypes.c_int32)]
+                ("engine", ctypes.c_int32), ("gap_ms", ctypes.c_float), ("reserved", ctypes.c_int32),
+                ("dup_bytes", ctypes.c_double)]
 
 
 LAYER_NAMES = {0: "other", 1: "pre_enc", 2: "wn_in", 3: "wn_res_skip", 4: "proj", 5: "flow_pre", 6: "flow_post",
-               7: "conv_pre", 8: "upsample", 9: "resblock_conv1", 10: "resblock_conv2", 11: "conv_post", 12: "resblock_pair"}
+               7: "conv_pre", 8: "upsample", 9: "resblock_conv1", 10: "resblock_conv2", 11: "conv_post", 12: "resblock_pair",
+               13: "split_image", 14: "wn_layer"}
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -235,5 +237,5 @@ class Handle:
         for r in buf[:min(n.value, self._prof_cap)]:
             out.append(dict(layer=LAYER_NAMES.get(r.layer, str(r.layer)), cin=r.cin, cout=r.cout, k=r.k,
                             dilation=r.dilation, batch=r.batch, length=r.length, flops=r.flops, bytes=r.bytes, ms=r.ms,
-                            engine="tc" if r.engine else "ffma", gap_ms=r.gap_ms))
+                            engine="tc" if r.engine else "ffma", gap_ms=r.gap_ms, dup_bytes=r.dup_bytes))
         return out
