@@ -725,10 +725,10 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
 #pragma unroll
           for (int e4 = 0; e4 < 4; ++e4) {
             const float4 q = reinterpret_cast<const float4*>(bptr + n0)[e4];
-            g[4 * e4 + 0] = tanhf(fmaf(fmaf(__uint_as_float(c[4 * e4 + 0]), LO_INV, __uint_as_float(m[4 * e4 + 0])), unscale, q.x));
-            g[4 * e4 + 1] = tanhf(fmaf(fmaf(__uint_as_float(c[4 * e4 + 1]), LO_INV, __uint_as_float(m[4 * e4 + 1])), unscale, q.y));
-            g[4 * e4 + 2] = tanhf(fmaf(fmaf(__uint_as_float(c[4 * e4 + 2]), LO_INV, __uint_as_float(m[4 * e4 + 2])), unscale, q.z));
-            g[4 * e4 + 3] = tanhf(fmaf(fmaf(__uint_as_float(c[4 * e4 + 3]), LO_INV, __uint_as_float(m[4 * e4 + 3])), unscale, q.w));
+            g[4 * e4 + 0] = fmaf(fmaf(__uint_as_float(c[4 * e4 + 0]), LO_INV, __uint_as_float(m[4 * e4 + 0])), unscale, q.x);  // tanh side, pre-activation
+            g[4 * e4 + 1] = fmaf(fmaf(__uint_as_float(c[4 * e4 + 1]), LO_INV, __uint_as_float(m[4 * e4 + 1])), unscale, q.y);  // tanh side, pre-activation
+            g[4 * e4 + 2] = fmaf(fmaf(__uint_as_float(c[4 * e4 + 2]), LO_INV, __uint_as_float(m[4 * e4 + 2])), unscale, q.z);  // tanh side, pre-activation
+            g[4 * e4 + 3] = fmaf(fmaf(__uint_as_float(c[4 * e4 + 3]), LO_INV, __uint_as_float(m[4 * e4 + 3])), unscale, q.w);  // tanh side, pre-activation
           }
           tmem_ld16(tsub + (uint32_t)(hN + n0), m);
           if (planes == 2) tmem_ld16(tsub + (uint32_t)(N + hN + n0), c);
@@ -736,10 +736,10 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
 #pragma unroll
           for (int e4 = 0; e4 < 4; ++e4) {
             const float4 q = reinterpret_cast<const float4*>(bptr + hN + n0)[e4];
-            g[4 * e4 + 0] *= sigmoidf_(fmaf(fmaf(__uint_as_float(c[4 * e4 + 0]), LO_INV, __uint_as_float(m[4 * e4 + 0])), unscale, q.x));
-            g[4 * e4 + 1] *= sigmoidf_(fmaf(fmaf(__uint_as_float(c[4 * e4 + 1]), LO_INV, __uint_as_float(m[4 * e4 + 1])), unscale, q.y));
-            g[4 * e4 + 2] *= sigmoidf_(fmaf(fmaf(__uint_as_float(c[4 * e4 + 2]), LO_INV, __uint_as_float(m[4 * e4 + 2])), unscale, q.z));
-            g[4 * e4 + 3] *= sigmoidf_(fmaf(fmaf(__uint_as_float(c[4 * e4 + 3]), LO_INV, __uint_as_float(m[4 * e4 + 3])), unscale, q.w));
+            g[4 * e4 + 0] = gate_tanh_sigmoid(g[4 * e4 + 0], fmaf(fmaf(__uint_as_float(c[4 * e4 + 0]), LO_INV, __uint_as_float(m[4 * e4 + 0])), unscale, q.x));
+            g[4 * e4 + 1] = gate_tanh_sigmoid(g[4 * e4 + 1], fmaf(fmaf(__uint_as_float(c[4 * e4 + 1]), LO_INV, __uint_as_float(m[4 * e4 + 1])), unscale, q.y));
+            g[4 * e4 + 2] = gate_tanh_sigmoid(g[4 * e4 + 2], fmaf(fmaf(__uint_as_float(c[4 * e4 + 2]), LO_INV, __uint_as_float(m[4 * e4 + 2])), unscale, q.z));
+            g[4 * e4 + 3] = gate_tanh_sigmoid(g[4 * e4 + 3], fmaf(fmaf(__uint_as_float(c[4 * e4 + 3]), LO_INV, __uint_as_float(m[4 * e4 + 3])), unscale, q.w));
           }
           const int nval = max(0, min(16, (a.Cout >> 1) - (ntile * hN + n0)));
           if (a.e[0].split && tin && nval == 16) {

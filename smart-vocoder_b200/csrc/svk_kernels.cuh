@@ -131,6 +131,32 @@ struct ConvPairArgs {
 bool conv_tc_pair_supported(int C, int K, int dil1);
 cudaError_t launch_conv_tc_pair(const ConvPairArgs& a, cudaStream_t stream);
 
+// ---- fused WN layer (wn_layer.cu): in_layer conv + gate + res_skip 1x1 + residual / skip update in ONE launch
+// (modules.py:156-175).  Weights are the conv_tc_pack images of the two convs (in_layer gate-packed, planes as given).
+struct WnLayerArgs {
+  int B, T, H, K, planes;
+  const uint16_t* x_img_in;  // operand image of the incoming x [B, H, T] (read with a (K-1)/2 halo by TMA)
+  uint16_t* x_img_out;       // operand image of the updated x (another buffer: neighbours still read the old one); null = none
+  float* x;                  // fp32 x, updated in place (unused on the last layer)
+  float* out;                // fp32 skip accumulator [B, H, T]
+  const float* mask;         // [B, T]
+  int first, last;           // first: out = skip (nothing read); last: res_skip has H outputs, out = (out + rs) * mask
+  const uint16_t* w_in;
+  const float* bias_in;      // [nt_in * N_in], virtual (gate-packed) order
+  float unscale_in;
+  int N_in;
+  const uint16_t* w_rs;
+  const float* bias_rs;      // [nt_rs * N_rs]
+  float unscale_rs;
+  int N_rs, Cout_rs;
+  // filled by launch_wn_layer:
+  int rows, ntiles_t, items, nt_in, nt_rs, na, nw, a_off, acts_off, w_off, w_slot, bias_count_in, bias_count_rs, acc_stride,
+      tmem_cols;
+  FastDiv div_t;
+};
+bool wn_layer_supported(int H, int K, int N_in, int N_rs, int Cout_rs, int planes);
+cudaError_t launch_wn_layer(const WnLayerArgs& a, cudaStream_t stream);
+
 // elementwise / small kernels
 cudaError_t launch_sequence_mask(const int64_t* lengths, int B, int T, float* mask, cudaStream_t s);
 cudaError_t launch_window_lengths(const int64_t* lengths, int B, int64_t a, int64_t w, int64_t* out, cudaStream_t s);

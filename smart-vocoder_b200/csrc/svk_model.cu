@@ -120,6 +120,7 @@ struct svk_handle {
   bool fuse_pairs = true;  // fused ResBlock conv pairs on the narrow stages ($SVK_FUSE_PAIRS=0 disables: A/B measurements)
   bool fuse_pairs_all = false;
   bool fuse_pairs_c32 = false;  // every kernel size of the C = 32 stage too (its weights stay resident in the pair kernel)
+  bool fuse_wn = true;          // one launch per WN layer (wn_layer.cu); $SVK_FUSE_WN=0 runs in_layer and res_skip as two launches
 
   // svk_profile_begin/end state
   bool profiling = false;
@@ -428,6 +429,7 @@ extern "C" int svk_create(const svk_config* cfg, int device, svk_handle** out) {
   h->device = device;
   if (const char* e = getenv("SVK_FUSE_PAIRS"))
     h->fuse_pairs = atoi(e) != 0, h->fuse_pairs_all = atoi(e) == 2, h->fuse_pairs_c32 = atoi(e) == 3;
+  if (const char* e = getenv("SVK_FUSE_WN")) h->fuse_wn = atoi(e) != 0;
   build_key_spec(h);
   if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&h->d_range_flag, sizeof(int)) != cudaSuccess ||
       cudaMemset(h->d_range_flag, 0, sizeof(int)) != cudaSuccess) {
@@ -776,6 +778,42 @@ struct Runner {
     const int H = h->cfg.hidden_channels, n = (int)in.size(), k = h->cfg.wn_kernel;
     bool images = x_img && acts_img && h->tensor_engine() && H % 32 == 0;
     for (int i = 0; i < n && images; ++i) images = in[i].tc && rs[i].tc;
+    // One launch per layer (wn_layer.cu): acts stays in shared memory, the x image ping-pongs between the two buffers.
+    bool fused = images && h->fuse_wn;
+    for (int i = 0; i < n && fused; ++i)
+      fused = wn_layer_supported(H, k, in[i].tc_N, rs[i].tc_N, rs[i].Cout, h->planes()) && rs[i].Cout == (i < n - 1 ? 2 * H : H);
+    if (fused) {
+      for (int i = 0; i < n && err == cudaSuccess; ++i) {
+        WnLayerArgs w;
+        memset(&w, 0, sizeof(w));
+        w.B = B, w.T = T, w.H = H, w.K = k, w.planes = h->planes();
+        w.x_img_in = (i & 1) ? acts_img : x_img;
+        w.x_img_out = i < n - 1 ? ((i & 1) ? x_img : acts_img) : nullptr;
+        w.x = x, w.out = out, w.mask = mask;
+        w.first = i == 0, w.last = i == n - 1;
+        w.w_in = h->d_tcblob + in[i].tc_off, w.bias_in = h->d_blob + in[i].tc_b_off, w.unscale_in = in[i].tc_unscale, w.N_in = in[i].tc_N;
+        w.w_rs = h->d_tcblob + rs[i].tc_off, w.bias_rs = h->d_blob + rs[i].tc_b_off, w.unscale_rs = rs[i].tc_unscale, w.N_rs = rs[i].tc_N;
+        w.Cout_rs = rs[i].Cout;
+        bool open = false;
+        if (h->profiling && h->prof_records.size() < h->prof_cap) {
+          svk_launch_record r;
+          memset(&r, 0, sizeof(r));
+          r.layer = SVK_LAYER_WN_LAYER, r.cin = H, r.cout = rs[i].Cout, r.k = k, r.dilation = 1, r.batch = B, r.length = T, r.engine = 1;
+          const double E = (double)B * H * T, img = h->planes() * 0.5;
+          r.flops = 2.0 * B * (double)T * ((double)2 * H * H * k + (double)rs[i].Cout * H);
+          // x image in; fp32 x read + written and its new image (not on the last layer); out read (not on the first) + written; weights
+          r.bytes = 4.0 * E * (img + (w.last ? 0.0 : 2.0 + img) + (w.first ? 1.0 : 2.0)) + 4.0 * ((double)2 * H * H * k + (double)rs[i].Cout * H);
+          r.dup_bytes = w.last ? 0.0 : 4.0 * E * img;
+          h->prof_records.push_back(r);
+          cudaEventRecord(h->prof_events[2 * (h->prof_records.size() - 1)], stream);
+          open = true;
+        }
+        err = launch_wn_layer(w, stream);
+        prof_close(open);
+        h->launches++;
+      }
+      return;
+    }
     for (int i = 0; i < n; ++i) {
       ConvArgs a = base(in[i], x, H, 0, T, T, 1, (k - 1) / 2, T, T);
       a.mode = MODE_GATE;

@@ -169,6 +169,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
 
+// WN gate of the tensor-core engines: tanh(a) * sigmoid(b) (commons.py:100-107) = (1 - 2 / (1 + e^{2a})) / (1 + e^{-b}) on the
+// SFU (ex2.approx / rcp.approx: 13 instructions instead of ~60 for tanhf + expf + an IEEE division).  ncu on the fused WN
+// layer showed the gate epilogue (1700 warp instructions per N-tile at 0.14 IPC per warp) taking longer than the MMAs it
+// should hide under.  Absolute error <= 2e-7 on a value in (-1, 1) (1 - 2/(1 + e^{2a}) rounds twice near 1), limits exact:
+// e^{2a} = inf -> 1, = 0 -> -1; NaN propagates.  The fp32 FFMA engine keeps tanhf / expf.
+__device__ __forceinline__ float gate_tanh_sigmoid(float a, float b) {
+  const float ea = __expf(2.0f * a), eb = __expf(-b);
+  const float th = 1.0f - __fdividef(2.0f, 1.0f + ea);
+  return __fdividef(th, 1.0f + eb);
+}
+
 // One 32 B global store (STG.256, sm_100): a whole sector in one request.  Two 16 B stores to the halves of a sector
 // reach L2 as two partial-sector writes; on the operand-image rows (32 B per thread and plane) that costs 1.5-2x the
 // time of the same bytes written as full sectors.  `p` must be 32 B-aligned.

@@ -263,6 +263,26 @@ def test_hot_recipe_fails_loudly(base_cfg, base_dims):
     assert torch.isfinite(o32).all() and (np.abs(_np(o32) - ro) > 1e-3).mean() <= 1e-3
 
 
+def test_wn_fused_layer_equals_two_launch_form(base_cfg, base_sd, monkeypatch):
+    """wn_layer.cu (in_layer + gate + res_skip + residual/skip in ONE launch, acts in shared memory) performs the same
+    arithmetic in the same order as the two-launch form ($SVK_FUSE_WN=0: conv_tc MODE_GATE + split STORE epilogue), so
+    the encoder and the flow must agree BIT FOR BIT -- on a ragged batch spanning three time tiles."""
+    from gpu_util import build_net, dev
+    g = load_golden("infer_base_b3_t300_ragged")
+    outs = []
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("SVK_FUSE_WN", fuse)
+        n = build_net(base_cfg["model"], base_sd, engine="tc")
+        xo, m, logs, mask = n.enc_p(dev(g["mel"]), dev(g["lengths"], torch.int64))
+        z = n.flow(dev(g["ref64_z"]), mask, reverse=False)
+        torch.cuda.synchronize()
+        outs.append((_np(xo), _np(m), _np(logs), _np(z), n.last_launch_count()))
+    for a, b in zip(outs[0][:4], outs[1][:4]):
+        assert np.array_equal(a, b)
+    assert outs[0][4] < outs[1][4]  # fewer launches
+    assert np.abs(outs[0][1] - g["ref64_m_p"]).max() <= TOL
+
+
 def test_determinism(net):
     g = load_golden("infer_base_b2_t40")
     o1, _, _ = _run_infer(net, g)

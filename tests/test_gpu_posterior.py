@@ -34,7 +34,7 @@ def test_posterior_encoder_matches_reference_golden(net):
         err = np.abs(_np(v) - g["ref64_" + nm]).max()
         print(nm, "GPU vs ref64", err, "ref32 vs ref64", np.abs(g["ref32_" + nm] - g["ref64_" + nm]).max())
         assert err <= TOL, nm
-    assert net.last_launch_count() > 30
+    assert net.last_launch_count() > 15  # mask, pre, image, 16 fused WN layers, proj, sample
 
 
 def test_flow_forward_matches_reference_golden(net):
