@@ -138,6 +138,53 @@ int svk_infer_host(svk_handle *h, const float *mel, const int64_t *lengths, cons
  * on this handle since the last check produced one.  svk_infer_host checks before it returns.
  * No reference counterpart: fp32 PyTorch would print the same NaN audio silently. */
 int svk_check_range(svk_handle *h, void *stream);
+/* The configuration the handle was created with. */
+int svk_get_config(const svk_handle *h, svk_config *out);
+
+/* ---- CUDA-graph replay -----------------------------------------------------------------------
+ * svk_infer issues ~135 kernels; at small batch (inference.ipynb:114-118 runs ONE utterance) the host's launch calls
+ * are a visible part of the latency.  svk_graph_create runs svk_infer once on an internal stream, captures the same
+ * launch sequence (programmatic dependent launch edges kept when the driver accepts them) into a CUDA graph bound
+ * to buffers the graph owns, and svk_graph_launch replays it with one call.  The caller writes mel / lengths / eps
+ * into the buffers svk_graph_buffers reports (stream-ordered before the launch) and reads o / x_mask / latents from
+ * them afterwards.  Shapes, max_len and noise_scale are fixed per graph.  No reference counterpart. */
+typedef struct svk_graph svk_graph;
+typedef struct svk_graph_io {
+  float *mel;        /* [B, n_mel, T]  in  */
+  int64_t *lengths;  /* [B]            in  */
+  float *eps;        /* [B, inter, T]  in  */
+  float *o;          /* [B, 1, hop*T_out] out */
+  float *x_mask;     /* [B, 1, T] */
+  float *z, *z_p, *m_p, *logs_p; /* [B, inter, T] */
+  int32_t B, T, T_out;
+  int32_t programmatic_edges; /* 1: captured with programmatic dependent launch */
+  int64_t kernel_nodes;
+} svk_graph_io;
+int svk_graph_create(svk_handle *h, int B, int T, int max_len, float noise_scale, svk_graph **out);
+int svk_graph_buffers(const svk_graph *g, svk_graph_io *io);
+int svk_graph_launch(svk_graph *g, void *stream);
+void svk_graph_destroy(svk_graph *g);
+
+/* ---- pipelined host entry (pinned D2H overlapped with compute) ---------------
+ * svk_infer_host is serial: H2D, kernels, D2H, sync.  A pipeline keeps `depth` slots of device I/O buffers and
+ * three streams: svk_pipeline_submit enqueues the H2D of this call (overlapping the kernels of the previous one),
+ * its kernels, and its D2H (overlapping the kernels of the next one), and returns a ticket without waiting;
+ * svk_pipeline_wait blocks until that ticket's PCM (and x_mask) are in host memory and returns SVK_ERR_RANGE if it
+ * contains a non-finite sample.  Host buffers must stay valid (and should be pinned) until the wait.  Tickets are
+ * waited in submission order; a ticket not waited for before `depth` further submits is waited for implicitly.
+ * eps_host may be NULL: the N(0,1) draw of models.py:336 is then made on the device by svk_randn from
+ * (seed, a per-pipeline counter).  Shapes and max_len are fixed per pipeline. */
+typedef struct svk_pipeline svk_pipeline;
+int svk_pipeline_create(svk_handle *h, int B, int T, int max_len, int depth, svk_pipeline **out);
+int svk_pipeline_submit(svk_pipeline *p, const float *mel_host, const int64_t *lengths_host, const float *eps_host,
+                        uint64_t seed, float noise_scale, float *o_host, float *x_mask_host, int64_t *ticket);
+int svk_pipeline_wait(svk_pipeline *p, int64_t ticket);
+int svk_pipeline_drain(svk_pipeline *p);
+void svk_pipeline_destroy(svk_pipeline *p);
+/* Counter-based N(0,1) generator (Philox4x32-10 + Box-Muller): element i = f(seed, offset + i/4).  Stands in for
+ * torch.randn_like (models.py:336) where the caller does not bring eps; not torch's element order. */
+int svk_randn(svk_handle *h, uint64_t seed, uint64_t offset, int64_t n, float *out_dev, void *stream);
+
 /* ---- windowed / chunked synthesis (streaming and T >> 1024) ----------------
  * svk_infer_window computes the PCM of frames [t0, t1) of the utterance batch EXACTLY as the whole-
  * utterance svk_infer would: the window is widened by svk_halo_frames() frames of context per side

@@ -120,7 +120,8 @@ struct svk_handle {
   bool fuse_pairs = true;  // fused ResBlock conv pairs on the narrow stages ($SVK_FUSE_PAIRS=0 disables: A/B measurements)
   bool fuse_pairs_all = false;
   bool fuse_pairs_c32 = false;  // every kernel size of the C = 32 stage too (its weights stay resident in the pair kernel)
-  bool fuse_wn = true;          // one launch per WN layer (wn_layer.cu); $SVK_FUSE_WN=0 runs in_layer and res_skip as two launches
+  int fuse_wn = 1;              // one launch per WN layer (wn_layer.cu): 1 = when the batch fills the GPU (see Runner::wn),
+                                // 2 = always, 0 = never ($SVK_FUSE_WN; the two-launch form spreads a layer over 3x more CTAs)
 
   // svk_profile_begin/end state
   bool profiling = false;
@@ -385,6 +386,17 @@ int pack_wn(svk_handle* h, const std::string& prefix, int n_layers, std::vector<
 }  // namespace
 
 // ------------------------------------------------------------------------------------ lifetime
+extern "C" {
+int svk_g_pdl_enabled = 1;
+}
+extern "C" void svk__set_pdl(int enabled) { svk_g_pdl_enabled = enabled ? 1 : 0; }
+extern "C" int svk__device(const svk_handle* h) { return h ? h->device : 0; }
+extern "C" int* svk__range_flag(svk_handle* h) { return h ? h->d_range_flag : nullptr; }
+extern "C" int svk_get_config(const svk_handle* h, svk_config* out) {
+  if (!h || !out) return fail(SVK_ERR_INVALID, "svk_get_config: null argument");
+  *out = h->cfg;
+  return SVK_OK;
+}
 extern "C" int svk_abi_version(void) { return SVK_ABI_VERSION; }
 extern "C" const char* svk_last_error(void) { return g_last_error.c_str(); }
 
@@ -429,7 +441,7 @@ extern "C" int svk_create(const svk_config* cfg, int device, svk_handle** out) {
   h->device = device;
   if (const char* e = getenv("SVK_FUSE_PAIRS"))
     h->fuse_pairs = atoi(e) != 0, h->fuse_pairs_all = atoi(e) == 2, h->fuse_pairs_c32 = atoi(e) == 3;
-  if (const char* e = getenv("SVK_FUSE_WN")) h->fuse_wn = atoi(e) != 0;
+  if (const char* e = getenv("SVK_FUSE_WN")) h->fuse_wn = atoi(e);
   build_key_spec(h);
   if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&h->d_range_flag, sizeof(int)) != cudaSuccess ||
       cudaMemset(h->d_range_flag, 0, sizeof(int)) != cudaSuccess) {
@@ -779,7 +791,11 @@ struct Runner {
     bool images = x_img && acts_img && h->tensor_engine() && H % 32 == 0;
     for (int i = 0; i < n && images; ++i) images = in[i].tc && rs[i].tc;
     // One launch per layer (wn_layer.cu): acts stays in shared memory, the x image ping-pongs between the two buffers.
-    bool fused = images && h->fuse_wn;
+    // The fused kernel gives one CTA a whole 128-frame tile (all N-tiles of both GEMMs); the two-launch form spreads the
+    // same work over 3x as many CTAs.  With fewer than ~48 tiles (B = 1, T = 1024: 8) most SMs would idle in the fused
+    // form and latency is better unfused (measured at 1 x 1024: 3.6 vs 4.1 ms per infer).
+    const int wn_tiles = B * ((T + 127) / 128);
+    bool fused = images && (h->fuse_wn == 2 || (h->fuse_wn == 1 && wn_tiles >= 48));
     for (int i = 0; i < n && fused; ++i)
       fused = wn_layer_supported(H, k, in[i].tc_N, rs[i].tc_N, rs[i].Cout, h->planes()) && rs[i].Cout == (i < n - 1 ? 2 * H : H);
     if (fused) {

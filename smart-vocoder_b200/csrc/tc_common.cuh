@@ -11,6 +11,8 @@
 
 #include "svk_kernels.cuh"
 
+extern "C" int svk_g_pdl_enabled;  // defined in svk_model.cu
+
 namespace svk {
 namespace {
 
@@ -60,7 +62,8 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // for a launch without the programmatic-stream-serialization attribute.
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-// Launch with programmatic stream serialization unless $SVK_PDL=0 (A/B measurements).
+// Launch with programmatic stream serialization unless $SVK_PDL=0 (A/B measurements) or svk__set_pdl(0) (graph capture
+// falls back to plain edges when the driver refuses programmatic ones; svk_pipeline.cu).
 template <class... KArgs, class... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int threads, size_t smem, cudaStream_t stream, Args... args) {
   static const bool pdl = [] {
@@ -73,7 +76,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int threads, s
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr, cfg.numAttrs = pdl ? 1 : 0;
+  cfg.attrs = attr, cfg.numAttrs = (pdl && svk_g_pdl_enabled) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 

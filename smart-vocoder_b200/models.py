@@ -62,6 +62,104 @@ class _SubModule:
     forward = __call__
 
 
+class _DevView:
+    """Zero-copy torch view of a device buffer owned by libsvk (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(int(s) for s in shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def _view(ptr, shape, typestr, device):
+    return torch.as_tensor(_DevView(ptr, shape, typestr), device=device)
+
+
+class InferGraph:
+    """One captured ``infer`` (svk_graph_*): fixed (B, T, max_len, noise_scale); I/O lives in buffers the graph owns."""
+
+    def __init__(self, handle: "rt.Handle", dims, B: int, T: int, Tp: int, noise_scale: float, device):
+        import ctypes
+        self._g = ctypes.c_void_p()
+        rt.check(rt.lib().svk_graph_create(handle.ptr, B, T, Tp, float(noise_scale), ctypes.byref(self._g)))
+        io = rt.SvkGraphIO()
+        rt.check(rt.lib().svk_graph_buffers(self._g, ctypes.byref(io)))
+        C = dims.inter_channels
+        self.mel = _view(io.mel, (B, dims.n_mel, T), "<f4", device)
+        self.lengths = _view(io.lengths, (B,), "<i8", device)
+        self.eps = _view(io.eps, (B, C, T), "<f4", device)
+        self.o = _view(io.o, (B, 1, dims.hop * Tp), "<f4", device)
+        self.x_mask = _view(io.x_mask, (B, 1, T), "<f4", device)
+        self.lat = tuple(_view(p, (B, C, T), "<f4", device) for p in (io.z, io.z_p, io.m_p, io.logs_p))
+        self.kernel_nodes, self.programmatic_edges = int(io.kernel_nodes), bool(io.programmatic_edges)
+
+    def launch(self, stream):
+        rt.check(rt.lib().svk_graph_launch(self._g, stream))
+
+    def close(self):
+        if self._g:
+            rt.lib().svk_graph_destroy(self._g)
+            self._g = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class InferPipeline:
+    """Pipelined host-buffer ``infer`` (svk_pipeline_*): submit() enqueues H2D + kernels + D2H on three streams and
+    returns a ticket; wait() blocks until that call's PCM is in host memory.  The H2D of call i+1 and the D2H of call
+    i-1 overlap the kernels of call i.  Host arrays should be pinned and must outlive the wait."""
+
+    def __init__(self, handle: "rt.Handle", dims, B: int, T: int, Tp: int, depth: int):
+        import ctypes
+        self._p = ctypes.c_void_p()
+        rt.check(rt.lib().svk_pipeline_create(handle.ptr, B, T, Tp, int(depth), ctypes.byref(self._p)))
+        self.B, self.T, self.Tp, self.dims, self.depth = B, T, Tp, dims, int(depth)
+        self._keep = {}
+
+    def submit(self, mel: np.ndarray, lengths: np.ndarray, out: np.ndarray, eps: Optional[np.ndarray] = None, seed: int = 0,
+               noise_scale: float = 1.0, x_mask: Optional[np.ndarray] = None) -> int:
+        import ctypes
+        d = self.dims
+        for a, shape, dt, nm in ((mel, (self.B, d.n_mel, self.T), np.float32, "mel"), (lengths, (self.B,), np.int64, "lengths"),
+                                 (out, (self.B, 1, d.hop * self.Tp), np.float32, "out")):
+            if a.dtype != dt or tuple(a.shape) != shape or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"{nm}: expected a C-contiguous {np.dtype(dt).name} array of shape {shape}")
+        if eps is not None and (eps.dtype != np.float32 or tuple(eps.shape) != (self.B, d.inter_channels, self.T) or
+                                not eps.flags["C_CONTIGUOUS"]):
+            raise ValueError("eps: expected a C-contiguous float32 array [B, inter_channels, T]")
+        if x_mask is not None and (x_mask.dtype != np.float32 or x_mask.size != self.B * self.T or not x_mask.flags["C_CONTIGUOUS"]):
+            raise ValueError("x_mask: expected a C-contiguous float32 array [B, 1, T]")
+        t = ctypes.c_int64()
+        vp = lambda a: None if a is None else a.ctypes.data  # noqa: E731
+        rt.check(rt.lib().svk_pipeline_submit(self._p, vp(mel), vp(lengths), vp(eps), int(seed), float(noise_scale), vp(out),
+                                              vp(x_mask), ctypes.byref(t)))
+        self._keep[t.value] = (mel, lengths, eps, out, x_mask)  # the copies are asynchronous: keep the arrays alive
+        self._keep.pop(t.value - 2 * self.depth, None)
+        return t.value
+
+    def wait(self, ticket: int):
+        rt.check(rt.lib().svk_pipeline_wait(self._p, int(ticket)))
+        self._keep.pop(int(ticket), None)
+
+    def drain(self):
+        rt.check(rt.lib().svk_pipeline_drain(self._p))
+        self._keep.clear()
+
+    def close(self):
+        if self._p:
+            rt.lib().svk_pipeline_destroy(self._p)
+            self._p = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class SynthesizerTrn(nn.Module):
     """
     Synthesizer for Training  (inference path only; see module docstring)
@@ -126,6 +224,7 @@ class SynthesizerTrn(nn.Module):
         self._handle: Optional[rt.Handle] = None
         self._device: Optional[torch.device] = None
         self._ws = _Workspace()
+        self._graphs = {}
         # Range guard (svk_check_range): the fp16 hi/lo engine turns an activation above 65504 into NaN audio.  With
         # `range_check` True (default) every infer()/dec() call ends with a check (one 4-byte D2H + stream sync, the
         # sync the reference's callers do anyway with `.cpu()`) and raises SvkError instead of returning NaNs;
@@ -151,6 +250,9 @@ class SynthesizerTrn(nn.Module):
         return self
 
     def _release(self):
+        for g in self._graphs.values():
+            g.close()
+        self._graphs = {}
         if self._handle is not None:
             self._handle.close()
         self._handle, self._device = None, None
@@ -265,6 +367,39 @@ class SynthesizerTrn(nn.Module):
             if self.range_check:
                 self._handle.check_range(self._stream())
         return o, x_mask, (z, z_p, m_p, logs_p)
+
+    def infer_graph(self, x, x_lengths, sid=None, noise_scale=1, length_scale=1, noise_scale_w=1., max_len=None):
+        """``infer`` replayed from a CUDA graph (svk_graph_*): one launch call instead of ~135, for small-batch latency.
+        Same arguments and return value as ``infer`` -- but the returned tensors ALIAS buffers owned by the graph of
+        this (B, T, max_len, noise_scale) and are overwritten by its next replay: clone what you keep.  The first
+        call per shape captures (one eager run + instantiation)."""
+        self._need_cuda(x, x_lengths)
+        x = self._f32(x, "x")
+        if x.dim() != 3 or x.shape[1] != self.dims.n_mel:
+            raise RuntimeError(f"expected input[B, {self.dims.n_mel}, T], got {list(x.shape)}")
+        B, _, T = x.shape
+        Tp = self._clip_len(T, max_len)
+        if B == 0 or T == 0 or Tp == 0:
+            raise ValueError("infer_graph: empty batch / zero frames")
+        key = (B, T, Tp, float(noise_scale))
+        with torch.cuda.device(self._device):
+            g = self._graphs.get(key)
+            if g is None:
+                if len(self._graphs) >= 8:  # bounded cache: a graph owns a full workspace
+                    self._graphs.pop(next(iter(self._graphs))).close()
+                g = self._graphs[key] = InferGraph(self._handle, self.dims, B, T, Tp, float(noise_scale), self._device)
+            g.mel.copy_(x)
+            g.lengths.copy_(x_lengths.to(torch.int64))
+            g.eps.copy_(torch.randn_like(g.lat[2]))  # the draw of models.py:336, through torch like infer()
+            g.launch(self._stream())
+            if self.range_check:
+                self._handle.check_range(self._stream())
+        return g.o, g.x_mask, g.lat
+
+    def pipeline(self, B, T, depth=2, max_len=None) -> InferPipeline:
+        """Pipelined host-buffer entry for a fixed batch shape (svk_pipeline_*); see InferPipeline."""
+        self._need_cuda()
+        return InferPipeline(self._handle, self.dims, int(B), int(T), self._clip_len(int(T), max_len), depth)
 
     def check_range(self):
         """Raise SvkError(SVK_ERR_RANGE) if any call since the last check produced a non-finite sample (synchronises)."""

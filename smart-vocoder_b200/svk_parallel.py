@@ -68,28 +68,167 @@ def _gather(local: torch.Tensor, outs: Optional[Sequence[torch.Tensor]], dst: in
 
 def sharded_infer(infer_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tensor], mel: Optional[torch.Tensor],
                   lengths: Optional[torch.Tensor], n_utterances: int, n_mel: int, T: int, samples_per_frame: int,
-                  device, root: int = 0, group=None) -> Optional[torch.Tensor]:
-    """Scatter `mel [N, n_mel, T]` / `lengths [N]` (present on `root` only, already on `device`),
-    run `infer_fn(mel_shard, lengths_shard) -> pcm [n, 1, samples_per_frame*T]` on every rank, gather
-    PCM on `root`.  Returns the full `[N, 1, samples_per_frame*T]` tensor on root, None elsewhere."""
+                  device, root: int = 0, group=None, micro_batches: int = 1,
+                  out_host: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """Scatter `mel [N, n_mel, T]` / `lengths [N]` (present on `root` only), run
+    `infer_fn(mel_shard, lengths_shard) -> pcm [n, 1, samples_per_frame*T]` on every rank, gather PCM on `root`.
+    Returns the full `[N, 1, samples_per_frame*T]` tensor on root, None elsewhere.
+
+    `mel` / `lengths` may live on `device` or (root, CUDA) in pinned host memory; with `out_host` (root: a pinned CPU
+    tensor `[N, 1, spf*T]`) the PCM is also copied to the host and `out_host` is returned after synchronising.
+
+    `micro_batches` > 1 splits every rank's shard into that many contiguous pieces and pipelines them on CUDA: the
+    H2D + NCCL scatter of piece m+1 and the NCCL gather + D2H of piece m-1 run on side streams under the kernels of
+    piece m, so the root's serial PCIe / gather leg (all PCM of the box funnels through rank 0) hides behind compute
+    instead of following it.  Every rank issues the same sequence of NCCL group calls.  On CPU (gloo) the pieces
+    simply run one after another -- same result."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     bounds = shard_bounds(n_utterances, world)
-    s, e = bounds[rank]
-    mel_local = torch.empty(e - s, n_mel, T, device=device, dtype=torch.float32)
-    len_local = torch.empty(e - s, device=device, dtype=torch.int64)
-    if rank == root:
-        _scatter(mel_local, [mel[a:b] for a, b in bounds], root, group)
-        _scatter(len_local, [lengths[a:b] for a, b in bounds], root, group)
-    else:
-        _scatter(mel_local, None, root, group)
-        _scatter(len_local, None, root, group)
-    pcm_local = infer_fn(mel_local, len_local) if e > s else torch.empty(0, 1, samples_per_frame * T, device=device)
-    if rank == root:
-        full = torch.empty(n_utterances, 1, samples_per_frame * T, device=device, dtype=torch.float32)
-        _gather(pcm_local, [full[a:b] for a, b in bounds], root, group)
-        return full
-    _gather(pcm_local, None, root, group)
-    return None
+    M = max(1, int(micro_batches))
+    L = samples_per_frame * T
+    cuda = torch.device(device).type == "cuda"
+    # piece m of rank r = utterances pieces[r][m]
+    pieces = [[(a + x, a + y) for x, y in shard_bounds(b - a, M)] for a, b in bounds]
+    if cuda:
+        cur = torch.cuda.current_stream(device)
+        comm, copy = torch.cuda.Stream(device), torch.cuda.Stream(device)
+        comm.wait_stream(cur), copy.wait_stream(cur)
+    full = torch.empty(n_utterances, 1, L, device=device, dtype=torch.float32) if rank == root else None
+    mel_loc, len_loc, ev_sc = [], [], []
+    # ---- stage the inputs: (root) H2D of piece m on the copy stream, then the scatter of piece m on the comm stream
+    for m in range(M):
+        a, b = pieces[rank][m]
+        ml = torch.empty(b - a, n_mel, T, device=device, dtype=torch.float32)
+        ll = torch.empty(b - a, device=device, dtype=torch.int64)
+        chunks_m = chunks_l = None
+        if rank == root:
+            if cuda and not mel.is_cuda:
+                with torch.cuda.stream(copy):
+                    chunks_m = [mel[x:y].to(device, non_blocking=True) for x, y in (pieces[r][m] for r in range(world))]
+                    chunks_l = [lengths[x:y].to(device, non_blocking=True) for x, y in (pieces[r][m] for r in range(world))]
+                comm.wait_stream(copy)
+            else:
+                chunks_m = [mel[x:y] for x, y in (pieces[r][m] for r in range(world))]
+                chunks_l = [lengths[x:y] for x, y in (pieces[r][m] for r in range(world))]
+        if cuda:
+            with torch.cuda.stream(comm):
+                _scatter(ml, chunks_m, root, group)
+                _scatter(ll, chunks_l, root, group)
+                ev = torch.cuda.Event()
+                ev.record(comm)
+            for t_ in (chunks_m or []) + (chunks_l or []) + [ml, ll]:
+                t_.record_stream(comm)
+            ev_sc.append(ev)
+        else:
+            _scatter(ml, chunks_m, root, group)
+            _scatter(ll, chunks_l, root, group)
+        mel_loc.append(ml), len_loc.append(ll)
+    # ---- compute piece m while piece m-1 is gathered (and copied to the host)
+    for m in range(M):
+        a, b = pieces[rank][m]
+        if cuda:
+            cur.wait_event(ev_sc[m])
+        pcm = infer_fn(mel_loc[m], len_loc[m]) if b > a else torch.empty(0, 1, L, device=device)
+        outs = [full[x:y] for x, y in (pieces[r][m] for r in range(world))] if rank == root else None
+        if cuda:
+            comm.wait_stream(cur)
+            with torch.cuda.stream(comm):
+                _gather(pcm, outs, root, group)
+            pcm.record_stream(comm)
+            if rank == root and out_host is not None:
+                copy.wait_stream(comm)
+                with torch.cuda.stream(copy):
+                    for x, y in (pieces[r][m] for r in range(world)):
+                        if y > x:
+                            out_host[x:y].copy_(full[x:y], non_blocking=True)
+        else:
+            _gather(pcm, outs, root, group)
+            if rank == root and out_host is not None:
+                out_host.copy_(full) if m == M - 1 else None
+    if cuda:
+        cur.wait_stream(comm), cur.wait_stream(copy)
+        if full is not None:
+            full.record_stream(comm), full.record_stream(copy)
+    if rank == root and out_host is not None:
+        if cuda:
+            torch.cuda.current_stream(device).synchronize()
+        return out_host
+    return full
+
+
+class SharedHostBuffer:
+    """A host array that every rank process of the box maps (POSIX shared memory) and registers with CUDA as pinned
+    memory, so each GPU can DMA its own shard of a batch in or out over ITS OWN PCIe link -- instead of the whole batch
+    funnelling through rank 0's link and an NCCL gather.  Rank `root` creates it, the others attach by name."""
+
+    def __init__(self, name: str, shape, dtype: torch.dtype, create: bool, register: bool = True):
+        from multiprocessing import shared_memory
+        import numpy as np
+        self._np_dtype = {torch.float32: np.float32, torch.int64: np.int64, torch.int16: np.int16}[dtype]
+        nbytes = int(np.prod(shape)) * np.dtype(self._np_dtype).itemsize
+        self._shm = shared_memory.SharedMemory(name=name, create=create, size=max(nbytes, 1))
+        if not create:
+            # Python < 3.13 registers attached segments with this process's resource tracker too, which then unlinks
+            # them at exit under the owner's feet (and warns); only the creating rank owns the name
+            try:
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self._shm._name, "shared_memory")
+            except Exception:  # pragma: no cover
+                pass
+        self.array = np.ndarray(tuple(shape), dtype=self._np_dtype, buffer=self._shm.buf)
+        self.tensor = torch.from_numpy(self.array)
+        self._registered, self._owner = False, create
+        if register and torch.cuda.is_available() and nbytes:
+            rc = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), nbytes, 0)
+            self._registered = int(rc) == 0
+        self.name = name
+
+    def close(self):
+        if self._registered:
+            torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
+            self._registered = False
+        self.tensor = self.array = None
+        try:
+            self._shm.close()
+            if self._owner:
+                self._shm.unlink()
+        except Exception:  # pragma: no cover
+            pass
+
+
+def sharded_infer_direct(infer_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tensor], mel_host: torch.Tensor,
+                         lengths_host: torch.Tensor, out_host: torch.Tensor, n_utterances: int, device, group=None,
+                         micro_batches: int = 1) -> None:
+    """The same sharding with NO NCCL on the data path: `mel_host [N, n_mel, T]`, `lengths_host [N]` and
+    `out_host [N, 1, L]` are SharedHostBuffer tensors visible to every rank; rank r copies its own utterances in
+    (H2D), runs `infer_fn`, and copies its PCM out (D2H) -- N PCIe links in parallel.  With `micro_batches` > 1 the D2H
+    of piece m runs on a side stream under the kernels of piece m+1.  Ends with a barrier: afterwards `out_host` is
+    complete on every rank.  For callers that can hand the library shared host buffers; `sharded_infer` is the form
+    that needs nothing but rank 0's tensors."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    a, b = shard_bounds(n_utterances, world)[rank]
+    cuda = torch.device(device).type == "cuda"
+    if cuda:
+        cur = torch.cuda.current_stream(device)
+        copy = torch.cuda.Stream(device)
+        copy.wait_stream(cur)
+    for x, y in shard_bounds(b - a, max(1, int(micro_batches))):
+        if y <= x:
+            continue
+        m = mel_host[a + x:a + y].to(device, non_blocking=True)
+        l = lengths_host[a + x:a + y].to(device, non_blocking=True)
+        pcm = infer_fn(m, l)
+        if cuda:
+            copy.wait_stream(cur)
+            with torch.cuda.stream(copy):
+                out_host[a + x:a + y].copy_(pcm, non_blocking=True)
+            pcm.record_stream(copy)
+        else:
+            out_host[a + x:a + y].copy_(pcm)
+    if cuda:
+        copy.synchronize()
+        cur.synchronize()
+    dist.barrier(group)
 
 
 def time_shard_bounds(T: int, world_size: int, halo: int) -> List[Tuple[int, int, int, int]]:

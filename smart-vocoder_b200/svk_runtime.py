@@ -68,6 +68,13 @@ class SvkLaunchRecord(ctypes.Structure):
                 ("dup_bytes", ctypes.c_double)]
 
 
+class SvkGraphIO(ctypes.Structure):
+    _fields_ = [("mel", ctypes.c_void_p), ("lengths", ctypes.c_void_p), ("eps", ctypes.c_void_p), ("o", ctypes.c_void_p),
+                ("x_mask", ctypes.c_void_p), ("z", ctypes.c_void_p), ("z_p", ctypes.c_void_p), ("m_p", ctypes.c_void_p),
+                ("logs_p", ctypes.c_void_p), ("B", ctypes.c_int32), ("T", ctypes.c_int32), ("T_out", ctypes.c_int32),
+                ("programmatic_edges", ctypes.c_int32), ("kernel_nodes", ctypes.c_int64)]
+
+
 LAYER_NAMES = {0: "other", 1: "pre_enc", 2: "wn_in", 3: "wn_res_skip", 4: "proj", 5: "flow_pre", 6: "flow_post",
                7: "conv_pre", 8: "upsample", 9: "resblock_conv1", 10: "resblock_conv2", 11: "conv_post", 12: "resblock_pair",
                13: "split_image", 14: "wn_layer"}
@@ -89,6 +96,17 @@ SIGNATURES = {
     "svk_infer": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "svk_infer_host": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "svk_check_range": (_i, [_vp, _vp]),
+    "svk_get_config": (_i, [_vp, ctypes.POINTER(SvkConfig)]),
+    "svk_graph_create": (_i, [_vp, _i, _i, _i, _f, ctypes.POINTER(_vp)]),
+    "svk_graph_buffers": (_i, [_vp, _vp]),
+    "svk_graph_launch": (_i, [_vp, _vp]),
+    "svk_graph_destroy": (None, [_vp]),
+    "svk_pipeline_create": (_i, [_vp, _i, _i, _i, _i, ctypes.POINTER(_vp)]),
+    "svk_pipeline_submit": (_i, [_vp, _vp, _vp, _vp, ctypes.c_uint64, _f, _vp, _vp, ctypes.POINTER(_i64)]),
+    "svk_pipeline_wait": (_i, [_vp, _i64]),
+    "svk_pipeline_drain": (_i, [_vp]),
+    "svk_pipeline_destroy": (None, [_vp]),
+    "svk_randn": (_i, [_vp, ctypes.c_uint64, ctypes.c_uint64, _i64, _vp, _vp]),
     "svk_halo_frames": (_i, [_vp]),
     "svk_window_workspace_bytes": (_sz, [_vp, _i, _i]),
     "svk_infer_window": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),

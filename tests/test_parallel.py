@@ -39,10 +39,31 @@ def _worker(rank, world, port, n_utt, q):
         lengths = torch.arange(n_utt, dtype=torch.int64) + 1
         out = P.sharded_infer(_fake_infer, mel if rank == 0 else None, lengths if rank == 0 else None, n_utt, C, T, 4,
                               torch.device("cpu"))
+        # pipelined form (micro-batches + host egress): same result, same NCCL-call sequence on every rank
+        host = torch.zeros(n_utt, 1, 4 * T) if rank == 0 else None
+        out2 = P.sharded_infer(_fake_infer, mel if rank == 0 else None, lengths if rank == 0 else None, n_utt, C, T, 4,
+                               torch.device("cpu"), micro_batches=3, out_host=host)
+        # direct form: every rank reads / writes its own rows of buffers shared between the rank processes
+        name = f"svk_test_{port}"
+        shapes = ((n_utt, C, T), torch.float32), ((n_utt,), torch.int64), ((n_utt, 1, 4 * T), torch.float32)
         if rank == 0:
-            q.put(bool(torch.equal(out, _fake_infer(mel, lengths))))
+            bufs = [P.SharedHostBuffer(f"{name}_{i}", sh, dt, create=True) for i, (sh, dt) in enumerate(shapes)]
+            bufs[0].tensor.copy_(mel), bufs[1].tensor.copy_(lengths), bufs[2].tensor.zero_()
+        dist.barrier()
+        if rank != 0:
+            bufs = [P.SharedHostBuffer(f"{name}_{i}", sh, dt, create=False) for i, (sh, dt) in enumerate(shapes)]
+        P.sharded_infer_direct(_fake_infer, bufs[0].tensor, bufs[1].tensor, bufs[2].tensor, n_utt, torch.device("cpu"),
+                               micro_batches=2)
+        out3 = bufs[2].tensor.clone()
+        dist.barrier()
+        for bf in bufs:
+            bf.close()
+        if rank == 0:
+            want = _fake_infer(mel, lengths)
+            q.put(bool(torch.equal(out, want)) and bool(torch.equal(out2, want)) and out2 is host and bool(torch.equal(out3, want)))
         else:
-            assert out is None
+            assert out is None and out2 is None
+            assert torch.equal(out3, _fake_infer(mel, lengths))
     finally:
         dist.destroy_process_group()
 
