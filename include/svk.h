@@ -301,6 +301,10 @@ int svk_conv_transpose1d_tc(const float *x_dev, int B, int Cin, int L, const flo
                             float pre_slope, float *y_dev, void *stream);
 /* commons.sequence_mask(...).to(float) (commons.py:121-125, models.py:40): mask [B,T]. */
 int svk_sequence_mask(const int64_t *lengths_dev, int B, int T, float *mask_dev, void *stream);
+/* PCM egress: float waveform -> int16 samples, y = saturate(round_to_nearest_even(x * max_wav_value))
+ * with max_wav_value = 32768 (configs/iitp_base.json:23), the inverse of `audio / 32768.0` (inference.ipynb cell 4); halves
+ * the D2H bytes of a serving path that ships int16.  Both buffers 16 B-aligned. */
+int svk_pcm_to_int16(const float *pcm_dev, int64_t n, float max_wav_value, int16_t *out_dev, void *stream);
 /* modules.Flip (modules.py:270-277): y[b,c,t] = x[b,C-1-c,t]. Bit-exact copy. */
 int svk_flip(const float *x_dev, int B, int C, int T, float *y_dev, void *stream);
 /* torch.nn.utils.weight_norm fold: v [dim0, inner], g [dim0] -> w. */
@@ -313,6 +317,28 @@ int svk_rq_spline(const float *x_dev, const float *uw_dev, const float *uh_dev, 
                   int64_t n, int num_bins, int inverse, float tail_bound, float min_bin_width,
                   float min_bin_height, float min_derivative, float *y_dev, float *logabsdet_dev,
                   int32_t *bin_dev, void *stream);
+
+/* modules.ConvFlow.forward(x, x_mask, g=None, reverse) (modules.py:346-390) with its DDSConv (modules.py:70-108) and
+ * LayerNorm (modules.py:20-32): the spline coupling flow.  The reference never instantiates it, so this is a
+ * stateless operator with explicit weights in the reference's layouts, the per-layer tensors stacked along a leading
+ * n_layers axis (device pointers):
+ *   pre    Conv1d(C/2 -> F, 1)            convs_sep[i] Conv1d(F, F, k, groups=F, dilation k^i)    convs_1x1[i] Conv1d(F -> F, 1)
+ *   norms_1[i], norms_2[i]  LayerNorm(F), eps 1e-5      proj   Conv1d(F -> C/2 * (3*num_bins - 1), 1)
+ *   x [B, C, T], mask [B, T] -> y [B, C, T] = cat(x0, spline(x1)) * mask; logdet [B] = sum(logabsdet * mask) (may be NULL;
+ *   the reference returns it for reverse = 0 only); bins [B, C/2, T] (may be NULL) = the searchsorted bin of every
+ *   element (-1 in the linear tails) -- integer work, compared bit for bit by the tests. */
+typedef struct svk_convflow_weights {
+  const float *pre_w, *pre_b;       /* [F, C/2, 1], [F] */
+  const float *sep_w, *sep_b;       /* [n_layers, F, 1, k], [n_layers, F] */
+  const float *pw_w, *pw_b;         /* [n_layers, F, F, 1], [n_layers, F] */
+  const float *norm1_g, *norm1_b;   /* [n_layers, F] gamma / beta of norms_1 */
+  const float *norm2_g, *norm2_b;   /* [n_layers, F] */
+  const float *proj_w, *proj_b;     /* [C/2 * (3*num_bins - 1), F, 1], [C/2 * (3*num_bins - 1)] */
+} svk_convflow_weights;
+size_t svk_convflow_workspace_bytes(int B, int C, int T, int filter_channels, int num_bins);
+int svk_convflow(const float *x_dev, const float *mask_dev, int B, int C, int T, int filter_channels, int kernel_size,
+                 int n_layers, int num_bins, float tail_bound, const svk_convflow_weights *w, int reverse, float *y_dev,
+                 float *logdet_dev, int32_t *bins_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
 
 /* ---- mel front-end (the step before infer in both callers) -----------------
  * Replaces mel_processing.spectrogram_torch (mel_processing.py:51-69), spec_to_mel_torch (:72-81) and

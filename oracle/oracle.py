@@ -11,6 +11,7 @@ call stack of ``SynthesizerTrn.infer`` (reference models.py:331-339; SURVEY 3.1 
   Generator.forward           models.py:141-160
   ResBlock1.forward           modules.py:210-223
   spline operator             transforms.py:12-193
+  ConvFlow / DDSConv / LayerNorm   modules.py:363-390, 70-108, 20-32  (standalone operator)
 
 Pinning: the reference ships no golden vectors; this oracle is pinned against outputs of the
 reference itself (tests/golden/*.npz, produced by tests/golden/make_golden.py in the build
@@ -158,6 +159,62 @@ class Oracle:
                               r(min_bin_width), r(min_bin_height), r(min_derivative), _ptr(out),
                               _ptr(lad), _ptr(bins))
         return out, lad, bins
+
+    # ---- ConvFlow (standalone operator; never instantiated by the reference model) ----
+    def layer_norm(self, x, gamma, beta, eps: float = 1e-5) -> np.ndarray:
+        """modules.LayerNorm.forward (modules.py:20-32): F.layer_norm over the channel axis of [B, C, T]."""
+        x = self.arr(x)
+        mean = x.mean(axis=1, keepdims=True)
+        var = ((x - mean) ** 2).mean(axis=1, keepdims=True)
+        y = (x - mean) / np.sqrt(var + self.dtype.type(eps))
+        return (y * self.arr(gamma)[None, :, None] + self.arr(beta)[None, :, None]).astype(self.dtype)
+
+    def gelu(self, x) -> np.ndarray:
+        """F.gelu (erf form, torch's default)."""
+        from math import erf, sqrt
+        x = self.arr(x)
+        e = np.vectorize(erf, otypes=[np.float64])(x.astype(np.float64) / sqrt(2.0))
+        return (0.5 * x * (1.0 + e)).astype(self.dtype)
+
+    def dds_conv(self, w: Dict[str, np.ndarray], prefix: str, x, mask, channels: int, kernel: int, n_layers: int) -> np.ndarray:
+        """modules.DDSConv.forward, g=None (modules.py:96-108): depthwise dilated conv (dilation kernel**i) of x * mask,
+        LayerNorm, GELU, 1x1 conv, LayerNorm, GELU, residual; result * mask."""
+        x, mask = self.arr(x), self.arr(mask)
+        for i in range(n_layers):
+            dil = kernel ** i
+            pad = (kernel * dil - dil) // 2
+            sw, sb = self.arr(w[f"{prefix}.convs_sep.{i}.weight"]), self.arr(w[f"{prefix}.convs_sep.{i}.bias"])
+            xm = x * mask
+            y = np.empty_like(x)
+            for c in range(channels):  # groups = channels: one single-channel conv per channel
+                y[:, c:c + 1] = self.conv1d(xm[:, c:c + 1], sw[c:c + 1], sb[c:c + 1], dilation=dil, padding=pad)
+            y = self.gelu(self.layer_norm(y, w[f"{prefix}.norms_1.{i}.gamma"], w[f"{prefix}.norms_1.{i}.beta"]))
+            y = self.conv1d(y, self.arr(w[f"{prefix}.convs_1x1.{i}.weight"]), self.arr(w[f"{prefix}.convs_1x1.{i}.bias"]))
+            y = self.gelu(self.layer_norm(y, w[f"{prefix}.norms_2.{i}.gamma"], w[f"{prefix}.norms_2.{i}.beta"]))
+            x = x + y
+        return x * mask
+
+    def convflow(self, w: Dict[str, np.ndarray], x, mask, filter_channels: int, kernel: int, n_layers: int, num_bins: int = 10,
+                 tail_bound: float = 5.0, reverse: bool = False):
+        """modules.ConvFlow.forward (modules.py:363-390).  `w` holds the module's state_dict.  Returns (y, logdet, bins);
+        logdet is None for reverse=True, like the reference."""
+        x, mask = self.arr(x), self.arr(mask)
+        B, C, T = x.shape
+        half = C // 2
+        x0, x1 = x[:, :half], x[:, half:]
+        h = self.conv1d(x0, self.arr(w["pre.weight"]), self.arr(w["pre.bias"]))
+        h = self.dds_conv(w, "convs", h, mask, filter_channels, kernel, n_layers)
+        h = self.conv1d(h, self.arr(w["proj.weight"]), self.arr(w["proj.bias"])) * mask
+        h = h.reshape(B, half, -1, T).transpose(0, 1, 3, 2)  # [b, c, t, 3nb-1]
+        sf = self.dtype.type(np.sqrt(float(filter_channels)))
+        uw = h[..., :num_bins] / sf
+        uh = h[..., num_bins:2 * num_bins] / sf
+        ud = h[..., 2 * num_bins:]
+        y1, lad, bins = self.rq_spline(np.ascontiguousarray(x1), np.ascontiguousarray(uw), np.ascontiguousarray(uh),
+                                       np.ascontiguousarray(ud), reverse, tail_bound)
+        y = np.concatenate([x0, y1], axis=1) * mask
+        logdet = None if reverse else (lad * mask).sum(axis=(1, 2))
+        return y, logdet, bins
 
     # ---- weights --------------------------------------------------------------------
     def conv_w(self, sd: Dict[str, np.ndarray], prefix: str) -> Tuple[np.ndarray, Optional[np.ndarray]]:

@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "spline.cuh"
 #include "svk_kernels.cuh"
 
 namespace svk {
@@ -97,94 +98,58 @@ __global__ void weight_norm_kernel(const float* __restrict__ v, const float* __r
   for (int64_t j = threadIdx.x; j < inner; j += blockDim.x) w[i * inner + j] = vr[j] * scale;
 }
 
-// transforms.py:12-193, one thread per element; parameters are read once (29 floats / element).
-constexpr int MAX_BINS = 32;
-
+// transforms.py:12-193, one thread per element; parameters are read once (29 floats / element); spline.cuh holds the math.
 __global__ void rq_spline_kernel(const float* __restrict__ x, const float* __restrict__ uw,
                                  const float* __restrict__ uh, const float* __restrict__ ud, int64_t n,
                                  int nb, int inverse, float tail_bound, float min_bw, float min_bh,
                                  float min_d, float* __restrict__ y, float* __restrict__ lad,
                                  int32_t* __restrict__ bins) {
-  const float left = -tail_bound, right = tail_bound;
-  // transforms.py:72-75 (computed in double by numpy, then stored into an fp32 tensor)
-  const float cst = (float)log(exp(1.0 - (double)min_d) - 1.0);
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
        e += (int64_t)gridDim.x * blockDim.x) {
-    const float xin = x[e];
-    if (!(xin >= left && xin <= right)) {  // transforms.py:65-78: identity tails
-      y[e] = xin;
-      lad[e] = 0.f;
-      if (bins) bins[e] = -1;
-      continue;
-    }
-    float cw[MAX_BINS + 1], chh[MAX_BINS + 1];
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      const float* pu = (pass == 0 ? uw : uh) + e * nb;
-      float* cum = pass == 0 ? cw : chh;
-      const float minb = pass == 0 ? min_bw : min_bh;
-      float mx = pu[0];
-      for (int i = 1; i < nb; ++i) mx = fmaxf(mx, pu[i]);
-      float sum = 0.f;
-      for (int i = 0; i < nb; ++i) {
-        cum[i + 1] = expf(pu[i] - mx);
-        sum += cum[i + 1];
-      }
-      const float scale = (float)(1.0 - (double)minb * nb);
-      float run = 0.f;
-      for (int i = 0; i < nb; ++i) {
-        const float sm = cum[i + 1] / sum;
-        run = __fadd_rn(run, __fadd_rn(minb, __fmul_rn(scale, sm)));
-        cum[i + 1] = __fadd_rn(__fmul_rn(right - left, run), left);
-      }
-      cum[0] = left;
-      cum[nb] = right;
-    }
-    const float* knots = inverse ? chh : cw;
-    int bin = -1;
-    for (int i = 0; i <= nb; ++i) {
-      float kn = knots[i];
-      if (i == nb) kn = __fadd_rn(kn, 1e-6f);
-      bin += (xin >= kn) ? 1 : 0;
-    }
-    if (bins) bins[e] = bin;
-    const int bi = bin < 0 ? 0 : (bin > nb - 1 ? nb - 1 : bin);
-    const float in_cw = cw[bi], in_w = cw[bi + 1] - cw[bi];
-    const float in_ch = chh[bi], in_h = chh[bi + 1] - chh[bi];
-    const float delta = in_h / in_w;
+    const float* pw = uw + e * nb;
+    const float* ph = uh + e * nb;
     const float* pd = ud + e * (nb - 1);
-    const float u0 = bi == 0 ? cst : pd[bi - 1];
-    const float u1 = bi + 1 == nb ? cst : pd[bi];
-    const float d0 = min_d + (u0 > 20.f ? u0 : log1pf(expf(u0)));
-    const float d1 = min_d + (u1 > 20.f ? u1 : log1pf(expf(u1)));
-    const float s2 = d0 + d1 - 2.f * delta;
-    if (inverse) {  // transforms.py:152-177
-      const float dy = xin - in_ch;
-      const float a = dy * s2 + in_h * (delta - d0);
-      const float b = in_h * d0 - dy * s2;
-      const float c = -delta * dy;
-      const float disc = b * b - 4.f * a * c;
-      const float root = (2.f * c) / (-b - sqrtf(disc));
-      y[e] = root * in_w + in_cw;
-      const float tomt = root * (1.f - root);
-      const float den = delta + s2 * tomt;
-      const float num =
-          delta * delta * (d1 * root * root + 2.f * delta * tomt + d0 * (1.f - root) * (1.f - root));
-      lad[e] = -(logf(num) - 2.f * logf(den));
-    } else {  // transforms.py:178-193
-      const float theta = (xin - in_cw) / in_w;
-      const float tomt = theta * (1.f - theta);
-      const float numr = in_h * (delta * theta * theta + d0 * tomt);
-      const float den = delta + s2 * tomt;
-      y[e] = in_ch + numr / den;
-      const float num =
-          delta * delta * (d1 * theta * theta + 2.f * delta * tomt + d0 * (1.f - theta) * (1.f - theta));
-      lad[e] = logf(num) - 2.f * logf(den);
+    float yo, lo;
+    int bin;
+    rq_spline_element(
+        x[e], [&](int i) { return pw[i]; }, [&](int i) { return ph[i]; }, [&](int i) { return pd[i]; }, nb, inverse,
+        tail_bound, min_bw, min_bh, min_d, yo, lo, bin);
+    y[e] = yo;
+    lad[e] = lo;
+    if (bins) bins[e] = bin;
+  }
+}
+
+// PCM egress: float waveform -> int16 (max_wav_value 32768, configs/iitp_base.json:23; the inverse of the
+// `audio / 32768.0` of inference.ipynb cell 4): round to nearest even, saturate.  8 samples per thread, one 16 B store.
+__global__ void __launch_bounds__(256) pcm_to_int16_kernel(const float* __restrict__ x, int64_t n, float scale, int16_t* __restrict__ y) {
+  const int64_t n8 = n >> 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(x)[2 * i], b = reinterpret_cast<const float4*>(x)[2 * i + 1];
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int lo = max(-32768, min(32767, __float2int_rn(v[2 * e] * scale)));
+      const int hi = max(-32768, min(32767, __float2int_rn(v[2 * e + 1] * scale)));
+      w[e] = ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16);
     }
+    reinterpret_cast<uint4*>(y)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const int64_t i = (n8 << 3) + threadIdx.x;
+    y[i] = (int16_t)max(-32768, min(32767, __float2int_rn(x[i] * scale)));
   }
 }
 
 }  // namespace
+
+cudaError_t launch_pcm_to_int16(const float* x, int64_t n, float scale, int16_t* y, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return cudaErrorInvalidValue;
+  pcm_to_int16_kernel<<<ew_blocks((n + 7) / 8), 256, 0, s>>>(x, n, scale, y);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_sequence_mask(const int64_t* lengths, int B, int T, float* mask, cudaStream_t s) {
   if ((int64_t)B * T == 0) return cudaSuccess;
@@ -232,7 +197,7 @@ cudaError_t launch_rq_spline(const float* x, const float* uw, const float* uh, c
                              float min_bh, float min_d, float* y, float* lad, int32_t* bins,
                              cudaStream_t s) {
   if (n == 0) return cudaSuccess;
-  if (nb < 1 || nb > MAX_BINS) return cudaErrorInvalidValue;
+  if (nb < 1 || nb > SPLINE_MAX_BINS) return cudaErrorInvalidValue;
   rq_spline_kernel<<<ew_blocks(n), 128, 0, s>>>(x, uw, uh, ud, n, nb, inverse, tail_bound, min_bw,
                                                 min_bh, min_d, y, lad, bins);
   return cudaGetLastError();

@@ -160,6 +160,7 @@ cudaError_t launch_wn_layer(const WnLayerArgs& a, cudaStream_t stream);
 // elementwise / small kernels
 cudaError_t launch_sequence_mask(const int64_t* lengths, int B, int T, float* mask, cudaStream_t s);
 cudaError_t launch_window_lengths(const int64_t* lengths, int B, int64_t a, int64_t w, int64_t* out, cudaStream_t s);
+cudaError_t launch_pcm_to_int16(const float* x, int64_t n, float scale, int16_t* y, cudaStream_t s);
 cudaError_t launch_flip(const float* x, int B, int C, int T, float* y, cudaStream_t s);
 cudaError_t launch_sample(const float* m, const float* logs, const float* eps, float noise_scale,
                           float* z_p, float* z, int64_t n, cudaStream_t s);

@@ -240,6 +240,12 @@ extern "C" int svk_sequence_mask(const int64_t* lengths, int B, int T, float* ma
   return e == cudaSuccess ? SVK_OK : cuda_fail(e, "svk_sequence_mask");
 }
 
+extern "C" int svk_pcm_to_int16(const float* pcm, int64_t n, float max_wav_value, int16_t* out, void* stream) {
+  if (!pcm || !out || n < 0 || !(max_wav_value > 0.f)) return op_fail(SVK_ERR_INVALID, "svk_pcm_to_int16: bad argument");
+  cudaError_t e = launch_pcm_to_int16(pcm, n, max_wav_value, out, (cudaStream_t)stream);
+  return e == cudaSuccess ? SVK_OK : cuda_fail(e, "svk_pcm_to_int16 (buffers must be 16 B-aligned)");
+}
+
 extern "C" int svk_flip(const float* x, int B, int C, int T, float* y, void* stream) {
   if (!x || !y || x == y || B < 0 || C < 0 || T < 0) return op_fail(SVK_ERR_INVALID, "svk_flip: bad argument (in-place not supported)");
   cudaError_t e = launch_flip(x, B, C, T, y, (cudaStream_t)stream);

@@ -68,6 +68,11 @@ class SvkLaunchRecord(ctypes.Structure):
                 ("dup_bytes", ctypes.c_double)]
 
 
+class SvkConvFlowWeights(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("pre_w", "pre_b", "sep_w", "sep_b", "pw_w", "pw_b", "norm1_g", "norm1_b",
+                                               "norm2_g", "norm2_b", "proj_w", "proj_b")]
+
+
 class SvkGraphIO(ctypes.Structure):
     _fields_ = [("mel", ctypes.c_void_p), ("lengths", ctypes.c_void_p), ("eps", ctypes.c_void_p), ("o", ctypes.c_void_p),
                 ("x_mask", ctypes.c_void_p), ("z", ctypes.c_void_p), ("z_p", ctypes.c_void_p), ("m_p", ctypes.c_void_p),
@@ -126,9 +131,12 @@ SIGNATURES = {
     "svk_conv1d_tc": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
     "svk_conv_transpose1d_tc": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
     "svk_sequence_mask": (_i, [_vp, _i, _i, _vp, _vp]),
+    "svk_pcm_to_int16": (_i, [_vp, _i64, _f, _vp, _vp]),
     "svk_flip": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "svk_weight_norm": (_i, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "svk_rq_spline": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp]),
+    "svk_convflow_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "svk_convflow": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, ctypes.POINTER(SvkConvFlowWeights), _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "svk_frontend_create": (_i, [_i, _i, _i, _i, _i, _f, _f, _i, ctypes.POINTER(_vp)]),
     "svk_frontend_destroy": (None, [_vp]),
     "svk_frontend_frames": (_i64, [_vp, _i64]),

@@ -64,6 +64,27 @@ def rq_spline(x, uw, uh, ud, inverse, tail_bound=5.0):
     return y, lad, bins
 
 
+def convflow(x, mask, w, filter_channels, kernel, n_layers, num_bins=10, tail_bound=5.0, reverse=False):
+    """svk_convflow with the state_dict of a reference modules.ConvFlow (numpy arrays keyed like the module)."""
+    import ctypes
+    B, C, T = x.shape
+    st = lambda name, leaf: dev(np.stack([w[f"convs.{name}.{i}.{leaf}"] for i in range(n_layers)]))  # noqa: E731
+    t = dict(pre_w=dev(w["pre.weight"]), pre_b=dev(w["pre.bias"]), sep_w=st("convs_sep", "weight"), sep_b=st("convs_sep", "bias"),
+             pw_w=st("convs_1x1", "weight"), pw_b=st("convs_1x1", "bias"), norm1_g=st("norms_1", "gamma"), norm1_b=st("norms_1", "beta"),
+             norm2_g=st("norms_2", "gamma"), norm2_b=st("norms_2", "beta"), proj_w=dev(w["proj.weight"]), proj_b=dev(w["proj.bias"]))
+    ws_ = rt.SvkConvFlowWeights(**{k: v.data_ptr() for k, v in t.items()})
+    y = torch.empty_like(x)
+    logdet = torch.empty(B, device="cuda")
+    bins = torch.empty(B, C // 2, T, device="cuda", dtype=torch.int32)
+    nbytes = rt.lib().svk_convflow_workspace_bytes(B, C, T, filter_channels, num_bins)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    rt.check(rt.lib().svk_convflow(x.data_ptr(), mask.data_ptr(), B, C, T, filter_channels, kernel, n_layers, num_bins, tail_bound,
+                                   ctypes.byref(ws_), int(reverse), y.data_ptr(), logdet.data_ptr(), bins.data_ptr(), ws.data_ptr(),
+                                   nbytes, _s()))
+    torch.cuda.synchronize()
+    return y, logdet, bins
+
+
 @contextlib.contextmanager
 def inject_eps(eps_np):
     """Feed the path's only RNG draw (models.py:336) with a fixed tensor, as make_golden.py does."""

@@ -409,6 +409,85 @@ def test_rq_spline_matches_reference(inverse):
     assert np.array_equal(bins, obins)  # searchsorted index: integer work
 
 
+def test_convflow_matches_reference_golden():
+    """modules.ConvFlow(4, 32, 3, 3) (pre -> 3 x DDSConv layer -> proj -> spline -> cat) against the reference's fp64
+    outputs: forward, its log-determinant, and the reverse pass; the bin indices (integer work) against the fp32 oracle."""
+    from gpu_util import convflow, dev
+    g = load_golden("convflow")
+    w = {k[2:]: v for k, v in g.items() if k.startswith("w_")}
+    mask_np = Oracle.sequence_mask(g["lengths"], g["x"].shape[2]).astype(np.float32)
+    x, mask = dev(g["x"]), dev(mask_np[:, 0])
+    y, logdet, bins = convflow(x, mask, w, 32, 3, 3, reverse=False)
+    assert np.abs(_np(y) - g["fwd64"]).max() <= 2e-5
+    assert np.abs(_np(logdet) - g["logdet64"]).max() <= 2e-4
+    yr, _, bins_r = convflow(x, mask, w, 32, 3, 3, reverse=True)
+    # the inverse solves a quadratic per element and amplifies parameter noise where a bin is nearly flat: fp32 bar (1e-4)
+    assert np.abs(_np(yr) - g["rev64"]).max() <= TOL
+    print("ConvFlow GPU vs ref64: fwd %.2e logdet %.2e rev %.2e (ref32 vs ref64: %.2e / %.2e / %.2e)" % (
+        np.abs(_np(y) - g["fwd64"]).max(), np.abs(_np(logdet) - g["logdet64"]).max(), np.abs(_np(yr) - g["rev64"]).max(),
+        np.abs(g["fwd32"] - g["fwd64"]).max(), np.abs(g["logdet32"] - g["logdet64"]).max(), np.abs(g["rev32"] - g["rev64"]).max()))
+    orc = Oracle(np.float32)
+    _, _, ob = orc.convflow(w, g["x"], mask_np, 32, 3, 3, reverse=False)
+    _, _, obr = orc.convflow(w, g["x"], mask_np, 32, 3, 3, reverse=True)
+    assert np.array_equal(_np(bins), ob) and np.array_equal(_np(bins_r), obr)
+    # x0 passes through untouched apart from the mask: bit for bit
+    assert np.array_equal(_np(y)[:, :2], g["x"][:, :2] * mask_np)
+    # the flow is a bijection where the mask is on: reverse(forward(x)) == x * mask
+    back, _, _ = convflow(y, mask, w, 32, 3, 3, reverse=True)
+    assert np.abs(_np(back) - g["x"] * mask_np).max() <= 1e-4
+
+
+def test_convflow_module_shim_matches_reference_surface():
+    """svk_modules.ConvFlow: the reference's constructor, state_dict key names and forward signature / return values."""
+    from svk_modules import ConvFlow
+    g = load_golden("convflow")
+    w = {k[2:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("w_")}
+    cf = ConvFlow(4, 32, 3, 3)
+    assert list(cf.state_dict().keys()) == list(w.keys())  # same names, same order as modules.ConvFlow(...).state_dict()
+    assert float(cf.state_dict()["proj.weight"].abs().max()) == 0.0  # zero-initialised like modules.py:358-359
+    cf.load_state_dict(w)
+    cf = cf.cuda().eval()
+    mask = torch.from_numpy(Oracle.sequence_mask(g["lengths"], 37).astype(np.float32)).cuda()
+    y, logdet = cf(torch.from_numpy(g["x"]).cuda(), mask)
+    assert np.abs(_np(y) - g["fwd64"]).max() <= 2e-5 and np.abs(_np(logdet) - g["logdet64"]).max() <= 2e-4
+    back = cf(y, mask, reverse=True)
+    assert np.abs(_np(back) - g["x"] * _np(mask)).max() <= TOL
+
+
+def test_convflow_vs_oracle_wide():
+    """VITS-sized instance (in_channels 2, filter_channels 192, 3 layers: the widest tile the kernels stage) on a ragged
+    batch spanning several 64-step tiles, against the fp64 oracle; and with the reference's zero-initialised proj (modules.py:358-359)."""
+    from gpu_util import convflow, dev
+    rng = np.random.Generator(np.random.Philox(key=[192, 3]))
+    B, C, T, F, k, n = 2, 2, 150, 192, 3, 3
+    w = {"pre.weight": rng.standard_normal((F, C // 2, 1)) * 0.5, "pre.bias": rng.standard_normal(F) * 0.1,
+         "proj.weight": rng.standard_normal((C // 2 * 29, F, 1)) * 0.05, "proj.bias": rng.standard_normal(C // 2 * 29) * 0.1}
+    for i in range(n):
+        w[f"convs.convs_sep.{i}.weight"] = rng.standard_normal((F, 1, k)) * 0.5
+        w[f"convs.convs_sep.{i}.bias"] = rng.standard_normal(F) * 0.1
+        w[f"convs.convs_1x1.{i}.weight"] = rng.standard_normal((F, F, 1)) / np.sqrt(F)
+        w[f"convs.convs_1x1.{i}.bias"] = rng.standard_normal(F) * 0.1
+        for nm in ("norms_1", "norms_2"):
+            w[f"convs.{nm}.{i}.gamma"] = 1 + 0.1 * rng.standard_normal(F)
+            w[f"convs.{nm}.{i}.beta"] = 0.1 * rng.standard_normal(F)
+    w = {kk: v.astype(np.float32) for kk, v in w.items()}
+    xx = (rng.standard_normal((B, C, T)) * 2.5).astype(np.float32)
+    mask_np = Oracle.sequence_mask(np.array([150, 70]), T).astype(np.float32)
+    y, logdet, _ = convflow(dev(xx), dev(mask_np[:, 0]), w, F, k, n)
+    ry, rl, _ = Oracle(np.float64).convflow(w, xx, mask_np, F, k, n)
+    assert np.abs(_np(y) - ry).max() <= 1e-4 and np.abs(_np(logdet) - rl).max() <= 2e-3
+    # zero-initialised proj (modules.py:358-359): every element sees the same parameter-free spline (uniform bins, interior
+    # derivative 1e-3 + softplus(0)); the tails beyond +-5 are the identity bit for bit
+    w0 = dict(w)
+    w0["proj.weight"], w0["proj.bias"] = np.zeros_like(w["proj.weight"]), np.zeros_like(w["proj.bias"])
+    y0, l0, _ = convflow(dev(xx), dev(mask_np[:, 0]), w0, F, k, n)
+    ry0, rl0, _ = Oracle(np.float64).convflow(w0, xx, mask_np, F, k, n)
+    assert np.abs(_np(y0) - ry0).max() <= 1e-5 and np.abs(_np(l0) - rl0).max() <= 1e-3
+    outside = np.broadcast_to(np.abs(xx) > 5.0, xx.shape).copy()
+    outside[:, 0] = True  # x0 is never transformed
+    assert np.array_equal(_np(y0)[outside], (xx * mask_np)[outside])
+
+
 def test_rq_spline_round_trip_large():
     """Size-independent property at scale: inverse(forward(x)) == x, logdets cancel."""
     from gpu_util import rq_spline

@@ -111,3 +111,13 @@ def test_device_randn_statistics_and_counter(net):
     w = torch.empty(n, device="cuda")
     rt.check(rt.lib().svk_randn(net._handle.ptr, 1235, 0, n, w.data_ptr(), s))
     assert abs((x * w).double().mean().item()) < 3e-3  # different seeds: uncorrelated streams
+
+
+def test_device_int16_egress_matches_host_conversion():
+    import svk_wav
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = (torch.randn(3, 1, 256 * 37 + 5, device="cuda", generator=g) * 0.6)
+    x[0, 0, :4] = torch.tensor([1.0, -1.0, 0.99999, 3.0517578125e-05 * 0.5])
+    q = svk_wav.to_int16(x)
+    assert q.dtype == torch.int16 and q.is_cuda and q.shape == x.shape
+    assert np.array_equal(q.cpu().numpy(), svk_wav.to_int16(x.cpu().numpy()))

@@ -117,6 +117,25 @@ def test_spline_round_trip():
     assert np.abs(lad + lad2).max() < 1e-8
 
 
+def _convflow_weights(g):
+    return {k[2:]: v for k, v in g.items() if k.startswith("w_")}
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-9), (np.float32, 5e-5)])
+def test_oracle_convflow_matches_reference(dtype, tol):
+    """modules.ConvFlow(4, 32, 3, 3) forward and reverse, ragged batch (tests/golden/make_golden.py::convflow_case)."""
+    g = load_golden("convflow")
+    tag = "64" if dtype is np.float64 else "32"
+    orc = Oracle(dtype)
+    mask = Oracle.sequence_mask(g["lengths"], g["x"].shape[2]).astype(dtype)
+    w = _convflow_weights(g)
+    y, logdet, _ = orc.convflow(w, g["x"], mask, 32, 3, 3, reverse=False)
+    assert np.abs(y - g["fwd" + tag]).max() <= tol
+    assert np.abs(logdet - g["logdet" + tag]).max() <= 20 * tol
+    yr, none, _ = orc.convflow(w, g["x"], mask, 32, 3, 3, reverse=True)
+    assert none is None and np.abs(yr - g["rev" + tag]).max() <= tol
+
+
 def test_spline_argument_checks():
     with pytest.raises(ValueError):
         Oracle().rq_spline(np.zeros((1,)), np.zeros((1, 10)), np.zeros((1, 10)), np.zeros((1, 9)), False,

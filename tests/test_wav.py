@@ -30,3 +30,17 @@ def test_wav_accepts_infer_shaped_output():
     blob = svk_wav.wav_float32_bytes(o[0])
     info = svk_wav.wav_header_info(blob)
     assert info["data_bytes"] == 2048 and info["format_tag"] == 3 and info["sample_rate"] == 22050
+
+
+def test_int16_wav_round_trip(tmp_path):
+    """16-bit egress: saturating round-half-even of x * 32768 and a canonical 44-byte PCM header (readable by scipy)."""
+    from scipy.io import wavfile
+    x = np.array([0.0, 0.5, -0.5, 1.0, -1.0, 1.5, 3.0517578125e-05 * 0.5, 3.0517578125e-05 * 1.5, -2.0], np.float32)
+    q = svk_wav.to_int16(x)
+    assert q.tolist() == [0, 16384, -16384, 32767, -32768, 32767, 0, 2, -32768]
+    path = tmp_path / "i16.wav"
+    assert svk_wav.write_wav_int16(str(path), x) == x.size
+    sr, data = wavfile.read(str(path))
+    assert sr == 22050 and data.dtype == np.int16 and np.array_equal(data, q)
+    info = svk_wav.wav_header_info(path.read_bytes())
+    assert info["format_tag"] == 1 and info["bits"] == 16 and info["data_bytes"] == 2 * x.size
