@@ -470,10 +470,14 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
     // 440-620 in the generic code below, 76 % of all instructions), so this path keeps one address per tile (32-bit
     // element offsets from the tensor bases), decodes one item per tile, ping-pongs two residual buffers instead of
     // rotating three, and has no per-element predicates except the row bound.  Same arithmetic, same order.
-    auto store_fast = [&](auto res_tag, auto y_tag, auto acc_tag) {
-      constexpr bool RES = decltype(res_tag)::value, YOUT = decltype(y_tag)::value, ACC = decltype(acc_tag)::value;
+    auto store_fast = [&](auto res_tag, auto y_tag, auto acc_tag, auto spl_tag) {
+      // RES: 0 = no residual, 1 = fp32 tensor, 2 = operand image (hi + lo * 2^-11, leaky_relu inverted)
+      constexpr int RES = decltype(res_tag)::value;
+      constexpr bool YOUT = decltype(y_tag)::value, ACC = decltype(acc_tag)::value, SPL = decltype(spl_tag)::value;
       const EpiDesc& d = a.e[0];
       const float* resb = d.res;  // may alias yb (in-place residual update: each element is read, then written, by one thread)
+      const uint16_t* rimg = d.res_img;
+      const float r_inv = RES == 2 ? 1.0f / d.res_slope : 1.0f;
       const float* accb = d.acc_in;  // running sum over the stage's ResBlocks (models.py:150-155), may alias yb too
       const float post_div = a.post_div;
       float* yb = d.y;
@@ -501,16 +505,37 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
         t_out = t2, b_out = b2, ch_out = ch;
         return true;
       };
-      auto load_res = [&](float (&r)[16], uint32_t off) {
+      // residual of the 16 channels starting at channel `ch` of utterance `bb`, row min(tt, Lout - 1); `off` = the same
+      // position as an fp32 element offset
+      auto load_res = [&](float (&r)[16], uint32_t off, int bb, int ch, int tt) {
+        if (RES == 2) {
+          const uint32_t tl = (uint32_t)min(tt, a.Lout - 1);
+          const uint16_t* rp = rimg + (((uint32_t)bb * cgroups + ((uint32_t)ch >> 5)) * ystride + tl) * 32u + ((uint32_t)ch & 31u);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) r[e] = resb[off + (uint32_t)e * ystride];
+          for (int g8 = 0; g8 < 2; ++g8) {
+            const uint4 hq = *reinterpret_cast<const uint4*>(rp + g8 * 8);
+            const uint4 lq = *reinterpret_cast<const uint4*>(rp + g8 * 8 + lo_plane);
+            const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w}, lw[4] = {lq.x, lq.y, lq.z, lq.w};
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) {
+              const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e2]));
+              const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e2]));
+              const float v0 = fmaf(lf.x, LO_INV, hf.x), v1 = fmaf(lf.y, LO_INV, hf.y);
+              r[8 * g8 + 2 * e2] = v0 >= 0.f ? v0 : v0 * r_inv;
+              r[8 * g8 + 2 * e2 + 1] = v1 >= 0.f ? v1 : v1 * r_inv;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) r[e] = resb[off + (uint32_t)e * ystride];
+        }
       };
       uint32_t offc = 0, offr = 0, n_offc = 0, n_offr = 0;
       int t = 0, b = 0, ch0 = 0, n_t = 0, n_b = 0, n_ch0 = 0;
       bool have = tile_off(egroup, offc, offr, t, b, ch0);
       if (RES && have) {
-        load_res(rA, offc);
-        load_res(rB, offc + 16u * ystride);
+        load_res(rA, offc, b, ch0, t);
+        load_res(rB, offc + 16u * ystride, b, ch0 + 16, t);
         if (ACC) {
 #pragma unroll
           for (int e = 0; e < 16; ++e) rA[e] += accb[offc + (uint32_t)e * ystride], rB[e] += accb[offc + (uint32_t)(16 + e) * ystride];
@@ -554,8 +579,9 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
             // refill this buffer with the residual of the job after next (same tile, or the group's next tile)
             const int jn = j + 2;
             if (jn < J || have_next) {
-              const uint32_t off = jn < J ? offc + (uint32_t)(16 * jn) * ystride : n_offc + (uint32_t)(16 * (jn - J)) * ystride;
-              load_res(r, off);
+              const bool same = jn < J;
+              const uint32_t off = same ? offc + (uint32_t)(16 * jn) * ystride : n_offc + (uint32_t)(16 * (jn - J)) * ystride;
+              load_res(r, off, same ? b : n_b, same ? ch0 + 16 * jn : n_ch0 + 16 * (jn - J), same ? t : n_t);
               if (ACC) {
 #pragma unroll
                 for (int e = 0; e < 16; ++e) ab[e] = accb[off + (uint32_t)e * ystride];
@@ -573,22 +599,24 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
 #pragma unroll
               for (int e = 0; e < 16; ++e) yp[(uint32_t)e * ystride] = v[e];
             }
-            // leaky_relu(y) as fp16 hi/lo: 16 channels = two 16 B pieces of the 64 B image row, per plane
-            const uint32_t dch = (uint32_t)(ch0 + 16 * j);
-            uint16_t* sp = spb + (((uint32_t)b * cgroups + (dch >> 5)) * ystride + (uint32_t)t) * 32u + (dch & 31u);
-            uint4 h[2], l[2];
+            if (SPL) {
+              // leaky_relu(y) as fp16 hi/lo: 16 channels = two 16 B pieces of the 64 B image row, per plane
+              const uint32_t dch = (uint32_t)(ch0 + 16 * j);
+              uint16_t* sp = spb + (((uint32_t)b * cgroups + (dch >> 5)) * ystride + (uint32_t)t) * 32u + (dch & 31u);
+              uint4 h[2], l[2];
 #pragma unroll
-            for (int g8 = 0; g8 < 2; ++g8) {
-              float w8[8];
+              for (int g8 = 0; g8 < 2; ++g8) {
+                float w8[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) w8[e] = v[8 * g8 + e] > 0.f ? v[8 * g8 + e] : v[8 * g8 + e] * slope;
-              split2(w8[0], w8[1], h[g8].x, l[g8].x);
-              split2(w8[2], w8[3], h[g8].y, l[g8].y);
-              split2(w8[4], w8[5], h[g8].z, l[g8].z);
-              split2(w8[6], w8[7], h[g8].w, l[g8].w);
+                for (int e = 0; e < 8; ++e) w8[e] = v[8 * g8 + e] > 0.f ? v[8 * g8 + e] : v[8 * g8 + e] * slope;
+                split2(w8[0], w8[1], h[g8].x, l[g8].x);
+                split2(w8[2], w8[3], h[g8].y, l[g8].y);
+                split2(w8[4], w8[5], h[g8].z, l[g8].z);
+                split2(w8[6], w8[7], h[g8].w, l[g8].w);
+              }
+              st_global_v8(sp, h[0], h[1]);  // 16 channels = one 32 B sector per plane, one request each
+              st_global_v8(sp + lo_plane, l[0], l[1]);
             }
-            st_global_v8(sp, h[0], h[1]);  // 16 channels = one 32 B sector per plane, one request each
-            st_global_v8(sp + lo_plane, l[0], l[1]);
           }
         };
         for (int j = 0; j < J; j += 2) {
@@ -601,13 +629,32 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
     };
     const bool epi_fast = kTma && ta.epi_fast;  // only image-fed launches qualify: keep the converting variant lean
     if constexpr (kTma) if (epi_fast) {
-      if (a.e[0].acc_in) {
-        store_fast(std::true_type{}, std::true_type{}, std::true_type{});
-      } else if (a.e[0].res) {
-        if (a.e[0].y) store_fast(std::true_type{}, std::true_type{}, std::false_type{});
-        else store_fast(std::true_type{}, std::false_type{}, std::false_type{});
+      using I0 = std::integral_constant<int, 0>;
+      using I1 = std::integral_constant<int, 1>;
+      using I2 = std::integral_constant<int, 2>;
+      const EpiDesc& d0 = a.e[0];
+      const bool y_ = d0.y != nullptr, acc_ = d0.acc_in != nullptr, spl_ = d0.split != nullptr;
+      if (!d0.res && !d0.res_img) {
+        store_fast(I0{}, std::false_type{}, std::false_type{}, std::true_type{});  // conv1: image -> image
+      } else if (!y_) {  // residual stream kept as images only, or conv2 of a narrow pair without fp32 out
+        if (d0.res_img) store_fast(I2{}, std::false_type{}, std::false_type{}, std::true_type{});
+        else store_fast(I1{}, std::false_type{}, std::false_type{}, std::true_type{});
+      } else if (d0.res_img) {
+        if (acc_) {
+          if (spl_) store_fast(I2{}, std::true_type{}, std::true_type{}, std::true_type{});
+          else store_fast(I2{}, std::true_type{}, std::true_type{}, std::false_type{});
+        } else {
+          if (spl_) store_fast(I2{}, std::true_type{}, std::false_type{}, std::true_type{});
+          else store_fast(I2{}, std::true_type{}, std::false_type{}, std::false_type{});
+        }
       } else {
-        store_fast(std::false_type{}, std::false_type{}, std::false_type{});
+        if (acc_) {
+          if (spl_) store_fast(I1{}, std::true_type{}, std::true_type{}, std::true_type{});
+          else store_fast(I1{}, std::true_type{}, std::true_type{}, std::false_type{});
+        } else {
+          if (spl_) store_fast(I1{}, std::true_type{}, std::false_type{}, std::true_type{});
+          else store_fast(I1{}, std::true_type{}, std::false_type{}, std::false_type{});
+        }
       }
     }
 
@@ -1150,9 +1197,13 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
       const char* e = getenv("SVK_EPI_FAST");
       return !(e && e[0] == '0');
     }();
-    ta.epi_fast = allow && a.mode == MODE_STORE && ta.planes == 2 && a.split == (1 << 30) && d.split && !d.res_img &&
-                  d.ch_sign == 1 && !a.act_tanh && !(d.use_mask && a.out_mask) && (d.y == nullptr || d.res != nullptr) &&
-                  (d.acc_in == nullptr || (d.res != nullptr && d.y != nullptr)) && a.Cout % ta.N == 0 && nch % esplit == 0 && hc % 2 == 0 &&
+    // combinations instantiated in the kernel: no residual -> image only; residual (fp32 tensor or operand image) ->
+    // image only, or fp32 out with optional running sum and optional image
+    const bool has_res = d.res != nullptr || d.res_img != nullptr;
+    const bool combo = (!has_res && !d.y && !d.acc_in && d.split) || (has_res && !d.y && !d.acc_in && d.split) || (has_res && d.y);
+    ta.epi_fast = allow && a.mode == MODE_STORE && ta.planes == 2 && a.split == (1 << 30) && combo && !(d.res && d.res_img) &&
+                  (!d.res_img || d.res_slope > 0.f) && d.ch_sign == 1 && d.ch_off % 16 == 0 && d.C % 32 == 0 && !a.act_tanh &&
+                  !(d.use_mask && a.out_mask) && a.Cout % ta.N == 0 && nch % esplit == 0 && hc % 2 == 0 &&
                   2ull * a.B * d.C * (unsigned long long)a.y_stride < (1ull << 32) && ta.x_split != nullptr;
   }
   int cols = 32;
