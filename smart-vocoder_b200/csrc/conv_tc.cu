@@ -557,7 +557,12 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
           }
           uint32_t m[16], c[16];
           tmem_ld16(tsub + (uint32_t)(16 * j), m);
-          tmem_ld16(tsub + (uint32_t)(N + 16 * j), c);
+          if (planes == 2) {
+            tmem_ld16(tsub + (uint32_t)(N + 16 * j), c);
+          } else {  // single bf16 plane: no cross accumulator
+#pragma unroll
+            for (int e = 0; e < 16; ++e) c[e] = 0u;
+          }
           const float4* b4 = reinterpret_cast<const float4*>(bias_t + 16 * j);
           tmem_wait_ld();
           if (j == J - 1) {  // every tcgen05.ld of this stage has completed: hand it back before the stores
@@ -609,13 +614,17 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
                 float w8[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) w8[e] = v[8 * g8 + e] > 0.f ? v[8 * g8 + e] : v[8 * g8 + e] * slope;
-                split2(w8[0], w8[1], h[g8].x, l[g8].x);
-                split2(w8[2], w8[3], h[g8].y, l[g8].y);
-                split2(w8[4], w8[5], h[g8].z, l[g8].z);
-                split2(w8[6], w8[7], h[g8].w, l[g8].w);
+                if (planes == 2) {
+                  split2(w8[0], w8[1], h[g8].x, l[g8].x);
+                  split2(w8[2], w8[3], h[g8].y, l[g8].y);
+                  split2(w8[4], w8[5], h[g8].z, l[g8].z);
+                  split2(w8[6], w8[7], h[g8].w, l[g8].w);
+                } else {
+                  h[g8] = pack_bf16x8(w8);
+                }
               }
               st_global_v8(sp, h[0], h[1]);  // 16 channels = one 32 B sector per plane, one request each
-              st_global_v8(sp + lo_plane, l[0], l[1]);
+              if (planes == 2) st_global_v8(sp + lo_plane, l[0], l[1]);
             }
           }
         };
@@ -1201,7 +1210,7 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
     // image only, or fp32 out with optional running sum and optional image
     const bool has_res = d.res != nullptr || d.res_img != nullptr;
     const bool combo = (!has_res && !d.y && !d.acc_in && d.split) || (has_res && !d.y && !d.acc_in && d.split) || (has_res && d.y);
-    ta.epi_fast = allow && a.mode == MODE_STORE && ta.planes == 2 && a.split == (1 << 30) && combo && !(d.res && d.res_img) &&
+    ta.epi_fast = allow && a.mode == MODE_STORE && (ta.planes == 2 || !d.res_img) && a.split == (1 << 30) && combo && !(d.res && d.res_img) &&
                   (!d.res_img || d.res_slope > 0.f) && d.ch_sign == 1 && d.ch_off % 16 == 0 && d.C % 32 == 0 && !a.act_tanh &&
                   !(d.use_mask && a.out_mask) && a.Cout % ta.N == 0 && nch % esplit == 0 && hc % 2 == 0 &&
                   2ull * a.B * d.C * (unsigned long long)a.y_stride < (1ull << 32) && ta.x_split != nullptr;

@@ -26,10 +26,12 @@ namespace svk {
 namespace {
 
 constexpr int P_NA_MAX = 8, P_MAXNW = 32;
-constexpr int P_EPI_WARPS = 8;
-constexpr int P_THREADS = 128 + 32 * P_EPI_WARPS;
-constexpr int P_EPI_THREADS = 32 * P_EPI_WARPS;
-constexpr int P_EPI_GROUP = P_EPI_THREADS / 2;  // warps 4..7 run epi1 (xt tile), warps 8..11 run epi2 (output)
+// warps 4..7 run epi1 (conv1 accumulators -> xt tile in shared memory: cheap), warps 8..15 run epi2 (conv2 accumulators +
+// residual -> fp32 / image in HBM: the expensive one -- with four warps it reached 3.7 TB/s where conv_tc's eight-warp
+// epilogue reaches 5; its two warps per TMEM lane quarter take alternate 16-column jobs)
+constexpr int P_EPI1_WARPS = 4, P_EPI2_WARPS = 8;
+constexpr int P_THREADS = 128 + 32 * (P_EPI1_WARPS + P_EPI2_WARPS);
+constexpr int P_EPI1_THREADS = 32 * P_EPI1_WARPS, P_EPI2_THREADS = 32 * P_EPI2_WARPS;
 
 struct __align__(8) PairHeader {
   uint64_t a_full[P_NA_MAX], a_empty[P_NA_MAX];
@@ -64,9 +66,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
     for (int i = 0; i < na; ++i) mbar_init(&hdr->a_full[i], 1), mbar_init(&hdr->a_empty[i], 1);
     for (int i = 0; i < P_MAXNW; ++i) mbar_init(&hdr->w_full[i], 1), mbar_init(&hdr->w_empty[i], 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&hdr->acc1_full[i], 1), mbar_init(&hdr->acc1_empty[i], P_EPI_GROUP);
-      mbar_init(&hdr->a2_full[i], P_EPI_GROUP), mbar_init(&hdr->a2_empty[i], 1);
-      mbar_init(&hdr->acc2_full[i], 1), mbar_init(&hdr->acc2_empty[i], P_EPI_GROUP);
+      mbar_init(&hdr->acc1_full[i], 1), mbar_init(&hdr->acc1_empty[i], P_EPI1_THREADS);
+      mbar_init(&hdr->a2_full[i], P_EPI1_THREADS), mbar_init(&hdr->a2_empty[i], 1);
+      mbar_init(&hdr->acc2_full[i], 1), mbar_init(&hdr->acc2_empty[i], P_EPI2_THREADS);
     }
     fence_barrier_init();
   }
@@ -272,7 +274,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
     // conv1's accumulators into conv2's A tile (epi1), group 1 stores conv2's result (epi2).  Alternating both jobs on
     // the same warps kept only one item in flight (conv1 -> epi1 -> conv2 -> epi2 is a serial chain of ~4000 cycles per
     // item); split, epi1(i+1) runs under conv2(i)'s MMAs and epi2(i) under conv1(i+2)'s.
-    const int q4 = warp & 3, role2 = (warp - 4) >> 2;
+    const int q4 = warp & 3, role2 = warp >= 4 + P_EPI1_WARPS ? 1 : 0;
+    const int part = role2 ? (warp - 4 - P_EPI1_WARPS) >> 2 : 0;  // epi2: which of the two warps of this lane quarter
     const int row = q4 * 32 + lane;
     const int hc = N >> 4;  // 16-column jobs per item and warp: 2 (N = 32) or 4 (N = 64)
     const int n_lo = 0, n_hi = N;
@@ -334,13 +337,13 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
       mbar_arrive(&hdr->acc1_empty[s]);
     };
 
-    // epi2 operands (residual, running sum) are requested two chunk-jobs ahead of use into two buffers that the
-    // jobs of this warp use alternately (job q = tile * hc + chunk uses buffer q & 1 and refills it for job q + 2):
-    // no rotation moves, no zero fill -- the epilogue warps are instruction-bound on these narrow layers.
+    // epi2 operands (residual, running sum) are requested two of this warp's jobs ahead of use into two buffers that its
+    // jobs use alternately.  The two epi2 warps of a lane quarter take alternate 16-column chunks of an item, so a warp has
+    // hc2 = hc / 2 jobs per item (1 at N = 32, 2 at N = 64); warp job w = item * hc2 + kk covers columns 16 * (2 kk + part).
     float rA[16], rB[16];
-    const int hc_shift = hc >> 1;  // log2(hc): hc is 2 or 4
-    auto load_ops = [&](float (&q)[16], int job) {
-      const int i = job >> hc_shift, n0 = n_lo + ((job & (hc - 1)) << 4);
+    const int hc2 = hc >> 1;
+    auto load_ops = [&](float (&q)[16], int wjob) {
+      const int i = hc2 == 1 ? wjob : wjob >> 1, n0 = n_lo + ((2 * (hc2 == 1 ? 0 : (wjob & 1)) + part) << 4);
       if (i >= n_my) return;
       int b, tt;
       item_bt(i, b, tt);
@@ -425,7 +428,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
         }
       }
     };
-    auto epi2 = [&](int i) {
+    // one item of this warp; bufs: the operand buffer(s) its hc2 jobs use (hc2 == 1: one, alternating between items)
+    auto epi2 = [&](int i, float (&r0)[16], float (&r1)[16]) {
       const int s = i & 1;
       int b, tt;
       item_bt(i, b, tt);
@@ -434,9 +438,11 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
       mbar_wait(&hdr->acc2_full[s], (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
       const uint32_t tsub = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(4 * N + s * 2 * N);
-      for (int k = 0; k < hc; k += 2) {  // jobs of an item alternate between the two operand buffers
-        epi2_job(rA, hc * i + k, b, t, valid, tsub, 16 * k);
-        epi2_job(rB, hc * i + k + 1, b, t, valid, tsub, 16 * k + 16);
+      if (hc2 == 1) {
+        epi2_job(r0, i, b, t, valid, tsub, 16 * part);
+      } else {
+        epi2_job(r0, 2 * i, b, t, valid, tsub, 16 * part);
+        epi2_job(r1, 2 * i + 1, b, t, valid, tsub, 16 * (2 + part));
       }
       tc_fence_before();
       mbar_arrive(&hdr->acc2_empty[s]);
@@ -444,8 +450,13 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
 
     if (role2 == 0) {
       for (int i = 0; i < n_my; ++i) epi1(i);
+    } else if (hc2 == 1) {
+      for (int i = 0; i < n_my; i += 2) {  // one job per item: the two buffers alternate between items
+        epi2(i, rA, rA);
+        if (i + 1 < n_my) epi2(i + 1, rB, rB);
+      }
     } else {
-      for (int i = 0; i < n_my; ++i) epi2(i);
+      for (int i = 0; i < n_my; ++i) epi2(i, rA, rB);
     }
   }
 

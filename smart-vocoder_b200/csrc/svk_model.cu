@@ -120,6 +120,9 @@ struct svk_handle {
   bool fuse_pairs = true;  // fused ResBlock conv pairs on the narrow stages ($SVK_FUSE_PAIRS=0 disables: A/B measurements)
   bool fuse_pairs_all = false;
   bool fuse_pairs_c32 = false;  // every kernel size of the C = 32 stage too (its weights stay resident in the pair kernel)
+  int img_stream = 0;           // $SVK_IMG_STREAM (A/B): 0 = per-shape default (Runner::resblock_images), 1 = every unfused ResBlock keeps
+                                // its residual stream between pairs as operand images only, 2 = also the first pair and the
+                                // fused pairs, -1 = the round-1 rule (C >= 256, C >= 128 with k >= 7)
   int fuse_wn = 1;              // one launch per WN layer (wn_layer.cu): 1 = when the batch fills the GPU (see Runner::wn),
                                 // 2 = always, 0 = never ($SVK_FUSE_WN; the two-launch form spreads a layer over 3x more CTAs)
 
@@ -442,6 +445,7 @@ extern "C" int svk_create(const svk_config* cfg, int device, svk_handle** out) {
   if (const char* e = getenv("SVK_FUSE_PAIRS"))
     h->fuse_pairs = atoi(e) != 0, h->fuse_pairs_all = atoi(e) == 2, h->fuse_pairs_c32 = atoi(e) == 3;
   if (const char* e = getenv("SVK_FUSE_WN")) h->fuse_wn = atoi(e);
+  if (const char* e = getenv("SVK_IMG_STREAM")) h->img_stream = atoi(e);
   build_key_spec(h);
   if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&h->d_range_flag, sizeof(int)) != cudaSuccess ||
       cudaMemset(h->d_range_flag, 0, sizeof(int)) != cudaSuccess) {
@@ -882,10 +886,14 @@ struct Runner {
         memset(&p, 0, sizeof(p));
         p.L = L;
         p.x_img = l == 0 ? x_img : (l == 1 ? cur_img : xt_img);
-        p.res = l == 0 ? x : cur;  // fp32 residual stream: same element read then written by one thread
+        if (h->img_stream >= 2) {  // residual stream as images only: the pair's own input image is its residual
+          p.res_img = p.x_img, p.res_slope = 0.1f;
+        } else {
+          p.res = l == 0 ? x : cur;  // fp32 residual stream: same element read then written by one thread
+        }
         p.post_div = 1.0f;
         if (l < SVK_RESBLOCK_PAIRS - 1) {
-          p.y = cur;
+          p.y = h->img_stream >= 2 ? nullptr : cur;
           p.y_img = l == 0 ? cur_img : xt_img, p.y_slope = 0.1f;
         } else {
           p.y = dst, p.acc_in = acc_in, p.post_div = post_div;
@@ -912,8 +920,11 @@ struct Runner {
       // x = hi + lo (leaky_relu inverted, ~2^-22 relative) instead of reading a second, fp32 copy (measured:
       // -7..-11 % on C >= 128, k >= 7; the narrow layers are bound by epilogue instruction latency and lose,
       // so they keep the fp32 copy).  A block's input and output are always fp32.
-      const bool img_stream = h->planes() == 2 && (C >= 256 || (C >= 128 && rb.k >= 7));
-      if (l > 0 && img_stream) b.e[0].res_img = src_img, b.e[0].res_slope = 0.1f;
+      // Measured per shape with the lean epilogue reading either form (profiles/r2_img_stream_ab.txt): the image-only
+      // stream wins on C >= 128 and on the k = 7 blocks of the narrow stages, the fp32 copy on their k = 11 blocks.
+      const bool img_stream = h->planes() == 2 && (h->img_stream >= 1 || (h->img_stream == 0 && (C >= 128 || rb.k == 7)) ||
+                                                     (h->img_stream < 0 && (C >= 256 || (C >= 128 && rb.k >= 7))));
+      if ((l > 0 || h->img_stream >= 2) && img_stream) b.e[0].res_img = src_img, b.e[0].res_slope = 0.1f;
       else b.e[0].res = src;
       if (l < SVK_RESBLOCK_PAIRS - 1) {
         b.e[0].y = img_stream ? nullptr : cur;
