@@ -795,11 +795,12 @@ struct Runner {
     bool images = x_img && acts_img && h->tensor_engine() && H % 32 == 0;
     for (int i = 0; i < n && images; ++i) images = in[i].tc && rs[i].tc;
     // One launch per layer (wn_layer.cu): acts stays in shared memory, the x image ping-pongs between the two buffers.
-    // The fused kernel gives one CTA a whole 128-frame tile (all N-tiles of both GEMMs); the two-launch form spreads the
-    // same work over 3x as many CTAs.  With fewer than ~48 tiles (B = 1, T = 1024: 8) most SMs would idle in the fused
-    // form and latency is better unfused (measured at 1 x 1024: 3.6 vs 4.1 ms per infer).
+    // The fused kernel gives one CTA a whole 128-frame tile (all N-tiles of both GEMMs: ~40 us per layer whatever the
+    // batch); the two-launch form spreads the same work over 3x as many CTAs and scales down with the batch.  Measured
+    // with tools/wn_bench.py (16-layer encoder, 1024 frames): B = 4: 0.64 vs 0.44 ms, B = 6: 0.65 vs 0.47, B = 8: 0.69 vs
+    // 0.68, B = 16: 0.73 vs 0.95 -> fused from 64 tiles up.
     const int wn_tiles = B * ((T + 127) / 128);
-    bool fused = images && (h->fuse_wn == 2 || (h->fuse_wn == 1 && wn_tiles >= 48));
+    bool fused = images && (h->fuse_wn == 2 || (h->fuse_wn == 1 && wn_tiles >= 64));
     for (int i = 0; i < n && fused; ++i)
       fused = wn_layer_supported(H, k, in[i].tc_N, rs[i].tc_N, rs[i].Cout, h->planes()) && rs[i].Cout == (i < n - 1 ? 2 * H : H);
     if (fused) {
