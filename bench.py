@@ -678,7 +678,7 @@ def run_b200_arm(args):
             ent = tj.get("families", {}).get(f"{eng}:cin{top_cin}:k{top_k}")
             if ent:
                 traffic, traffic_src = ent.get("dram_bytes_per_launch"), tj.get("source")
-                traffic_alg = ent.get("algorithmic_bytes_of_this_launch")
+                traffic_alg = ent.get("algorithmic_bytes_per_launch_average", ent.get("algorithmic_bytes_of_this_launch"))
         except Exception:
             traffic = None
     tc_peak = peaks["bf16_tflops_sustained"]
@@ -698,8 +698,8 @@ def run_b200_arm(args):
         "tensor_raw": {"achieved": 3 * achieved_tf, "frac": 3 * achieved_tf / peak_tf} if eng == "tc" else None,
         "peak_source": peak_src,
         "traffic": traffic, "traffic_source": traffic_src,
-        "traffic_launch_algorithmic_bytes": traffic_alg,  # of the captured launch (a conv2 with fp32 + image outputs);
-                                                          # algorithmic_bytes_per_launch below averages the family
+        "traffic_launch_algorithmic_bytes": traffic_alg,  # average over the family's launches as captured in the model
+                                                          # (profiles/dominant_kernel_traffic.json lists each of them)
         "timing": "CUDA-event pair around every launch on the launching stream, second pass of the same K steps "
                   "(profiled_pass_ms_per_step); `value` comes from the first pass without per-launch events",
         "launches_in_group": top["n"], "avg_launch_ms": avg_ms, "share_of_step": top["ms"] / prof_total_ms,
