@@ -16,6 +16,7 @@ scatter of the overlapping input windows and the gather of the PCM segments.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
@@ -166,6 +167,16 @@ class SharedHostBuffer:
         import numpy as np
         self._np_dtype = {torch.float32: np.float32, torch.int64: np.int64, torch.int16: np.int16}[dtype]
         nbytes = int(np.prod(shape)) * np.dtype(self._np_dtype).itemsize
+        if create:
+            # tmpfs does not fail at ftruncate: a segment larger than what /dev/shm has left dies with SIGBUS on the first
+            # write.  Refuse up front instead (containers often mount /dev/shm with 64 MB).
+            try:
+                st = os.statvfs("/dev/shm")
+                free = st.f_bavail * st.f_frsize
+            except OSError:
+                free = None
+            if free is not None and nbytes > 0.9 * free:
+                raise MemoryError(f"SharedHostBuffer {name}: {nbytes} bytes requested, /dev/shm has {free} free")
         self._shm = shared_memory.SharedMemory(name=name, create=create, size=max(nbytes, 1))
         if not create:
             # Python < 3.13 registers attached segments with this process's resource tracker too, which then unlinks
