@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SVK_ABI_VERSION 1
+#define SVK_ABI_VERSION 2
 
 #define SVK_OK 0
 #define SVK_IGNORED 1            /* svk_load_tensor: key is dead at inference, accepted and dropped */
@@ -81,6 +81,9 @@ typedef struct svk_config {
   int32_t resblock_kernel_sizes[SVK_MAX_RESBLOCK_KERNELS];
   int32_t resblock_dilations[SVK_MAX_RESBLOCK_KERNELS][SVK_RESBLOCK_PAIRS];
   int32_t precision;       /* SVK_PRECISION_* */
+  int32_t resblock_type;   /* 0 or 1: modules.ResBlock1 (3 conv pairs, modules.py:187-229); 2: modules.ResBlock2 (two convs with
+                              dilations resblock_dilations[j][0..1], each x = conv(lrelu(x)) + x, modules.py:232-256) --
+                              Generator picks by the config's "resblock" key (models.py:121) */
 } svk_config;
 
 typedef struct svk_handle svk_handle;
@@ -275,7 +278,8 @@ int svk_posterior_encoder(svk_handle *h, const float *spec_dev, const int64_t *l
 /* Generator.forward(x, g=None) (models.py:141-160): z [B,inter,L] -> o [B,1,hop*L]. */
 int svk_generator(svk_handle *h, const float *z_dev, int B, int L, float *o_dev, void *workspace_dev,
                   size_t workspace_bytes, void *stream);
-/* ResBlock1.forward(x) (modules.py:210-223) of dec.resblocks[index]: [B,C,L] -> [B,C,L]. */
+/* ResBlock1.forward(x) (modules.py:210-223) -- or ResBlock2.forward(x) (modules.py:243-252) when the handle was created
+ * with resblock_type 2 -- of dec.resblocks[index]: [B,C,L] -> [B,C,L]. */
 size_t svk_resblock1_workspace_bytes(const svk_handle *h, int index, int B, int L);
 int svk_resblock1(svk_handle *h, int index, const float *x_dev, int B, int L, float *y_dev,
                   void *workspace_dev, size_t workspace_bytes, void *stream);

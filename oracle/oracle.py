@@ -324,6 +324,15 @@ class Oracle:
             x = xt + x
         return x
 
+    def resblock2(self, sd, prefix: str, x, kernel: int, dilations: Sequence[int]) -> np.ndarray:
+        """modules.ResBlock2.forward, x_mask=None (modules.py:243-252): x = conv_l(leaky_relu(x, 0.1)) + x for the two convs."""
+        x = self.arr(x)
+        for l in range(2):
+            dil = int(dilations[l])
+            w, b = self.conv_w(sd, f"{prefix}.convs.{l}")
+            x = self.conv1d(self.leaky_relu(x, 0.1), w, b, dilation=dil, padding=(kernel * dil - dil) // 2) + x
+        return x
+
     def generator(self, sd, d, z, trace: Optional[Dict[str, np.ndarray]] = None) -> np.ndarray:
         """Generator.forward with g=None (models.py:141-160)."""
         w, b = self.conv_w(sd, "dec.conv_pre")
@@ -339,7 +348,8 @@ class Oracle:
                 trace[f"ups{i}"] = x
             xs = None
             for j, (rk, rd) in enumerate(zip(d.resblock_kernel_sizes, d.resblock_dilation_sizes)):
-                r = self.resblock1(sd, f"dec.resblocks.{i * nk + j}", x, rk, rd)
+                block = self.resblock1 if str(getattr(d, "resblock", "1")) == "1" else self.resblock2  # models.py:121
+                r = block(sd, f"dec.resblocks.{i * nk + j}", x, rk, rd)
                 xs = r if xs is None else xs + r
             x = xs / self.dtype.type(nk)
             if trace is not None:

@@ -83,9 +83,11 @@ struct FlowLayers {
 };
 
 struct ResBlock {
-  PackedConv c1[SVK_RESBLOCK_PAIRS], c2[SVK_RESBLOCK_PAIRS];
+  PackedConv c1[SVK_RESBLOCK_PAIRS], c2[SVK_RESBLOCK_PAIRS];  // type 2: c1[l] = convs[l], c2 unused
   int k = 0, C = 0;
   int dil[SVK_RESBLOCK_PAIRS] = {1, 1, 1};
+  int type = 1;  // 1: ResBlock1 (n conv pairs), 2: ResBlock2 (n single convs)
+  int n = SVK_RESBLOCK_PAIRS;
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -205,6 +207,15 @@ void build_key_spec(svk_handle* h) {
     const int ch = U >> (i + 1);
     for (int j = 0; j < c.n_resblock_kernels; ++j) {
       const int n = i * c.n_resblock_kernels + j;
+      if (c.resblock_type == 2) {
+        for (int l = 0; l < 2; ++l) {
+          const std::string p = "dec.resblocks." + std::to_string(n) + ".convs." + std::to_string(l);
+          add_key(h, p + ".bias", {ch});
+          add_key(h, p + ".weight_g", {ch, 1, 1});
+          add_key(h, p + ".weight_v", {ch, ch, c.resblock_kernel_sizes[j]});
+        }
+        continue;
+      }
       for (const char* grp : {"convs1", "convs2"})
         for (int l = 0; l < SVK_RESBLOCK_PAIRS; ++l) {
           const std::string p = "dec.resblocks." + std::to_string(n) + "." + grp + "." + std::to_string(l);
@@ -413,6 +424,7 @@ extern "C" int svk_create(const svk_config* cfg, int device, svk_handle** out) {
   if (c.n_upsamples < 1 || c.n_upsamples > SVK_MAX_UPSAMPLES) return fail(SVK_ERR_INVALID, "n_upsamples out of range");
   if (c.n_resblock_kernels < 1 || c.n_resblock_kernels > SVK_MAX_RESBLOCK_KERNELS)
     return fail(SVK_ERR_INVALID, "n_resblock_kernels out of range");
+  if (c.resblock_type < 0 || c.resblock_type > 2) return fail(SVK_ERR_INVALID, "resblock_type must be 1 (ResBlock1) or 2 (ResBlock2)");
   if (c.precision != SVK_PRECISION_FP32 && c.precision != SVK_PRECISION_TC && c.precision != SVK_PRECISION_BF16)
     return fail(SVK_ERR_INVALID, "unsupported precision %d", c.precision);
   if (c.hidden_channels % 8 || c.inter_channels % 16 || c.n_mel % 8)
@@ -428,7 +440,7 @@ extern "C" int svk_create(const svk_config* cfg, int device, svk_handle** out) {
   for (int j = 0; j < c.n_resblock_kernels; ++j) {
     if (c.resblock_kernel_sizes[j] % 2 != 1 || !conv_ffma_supports_k(c.resblock_kernel_sizes[j]))
       return fail(SVK_ERR_INVALID, "unsupported resblock kernel size %d", c.resblock_kernel_sizes[j]);
-    for (int l = 0; l < SVK_RESBLOCK_PAIRS; ++l)
+    for (int l = 0; l < (c.resblock_type == 2 ? 2 : SVK_RESBLOCK_PAIRS); ++l)
       if (c.resblock_dilations[j][l] < 1 || c.resblock_dilations[j][l] > 8)
         return fail(SVK_ERR_INVALID, "resblock dilation must be in [1,8]");
   }
@@ -566,6 +578,16 @@ extern "C" int svk_finalize_weights(svk_handle* h) {
       rb.k = c.resblock_kernel_sizes[j];
       rb.C = h->stage_channels(i);
       const std::string p = "dec.resblocks." + std::to_string(i * c.n_resblock_kernels + j);
+      if (c.resblock_type == 2) {
+        rb.type = 2, rb.n = 2;
+        for (int l = 0; l < rb.n; ++l) {
+          rb.dil[l] = c.resblock_dilations[j][l];
+          SVK_TRY(fold_layer(h, p + ".convs." + std::to_string(l), &f));
+          rb.c1[l] = pack_plain(h, f);
+        }
+        h->resblocks.push_back(rb);
+        continue;
+      }
       for (int l = 0; l < SVK_RESBLOCK_PAIRS; ++l) {
         rb.dil[l] = c.resblock_dilations[j][l];
         SVK_TRY(fold_layer(h, p + ".convs1." + std::to_string(l), &f));
@@ -865,8 +887,8 @@ struct Runner {
   // True when every conv of the block runs on the tcgen05 engine with operand-image I/O.
   bool resblock_uses_images(const ResBlock& rb) const {
     if (!h->tensor_engine() || rb.C % 16) return false;
-    for (int l = 0; l < SVK_RESBLOCK_PAIRS; ++l)
-      if (!rb.c1[l].tc || !rb.c2[l].tc) return false;
+    for (int l = 0; l < rb.n; ++l)
+      if (!rb.c1[l].tc || (rb.type == 1 && !rb.c2[l].tc)) return false;
     return true;
   }
 
@@ -877,6 +899,32 @@ struct Runner {
                        uint16_t* cur_img, float* dst, const float* acc_in, float post_div, int L,
                        uint16_t* dst_img = nullptr) {
     const int C = rb.C;
+    if (rb.type == 2) {
+      // ResBlock2 (modules.py:243-252): x = conv_l(leaky_relu(x), dilation d_l) + x, twice.  Each conv reads the operand
+      // image of leaky_relu(x) and writes the next one (another buffer: its neighbours' halos are still being read);
+      // the residual is the fp32 x, or -- on the wide, tensor-bound stages -- rebuilt from the input image itself.
+      const bool img_stream = h->planes() == 2 && C >= 128;
+      for (int l = 0; l < rb.n; ++l) {
+        const bool last = l == rb.n - 1;
+        const float* src = l == 0 ? x : cur;
+        const uint16_t* src_img = l == 0 ? x_img : ((l & 1) ? cur_img : xt_img);
+        const int d = rb.dil[l];
+        ConvArgs a = base(rb.c1[l], src, C, 0, L, L, d, (rb.k * d - d) / 2, L, L);
+        a.pre_slope = 0.1f;
+        a.e[0].C = C;
+        if (img_stream && (l > 0 || x_img)) a.e[0].res_img = src_img, a.e[0].res_slope = 0.1f;
+        else a.e[0].res = src;
+        if (!last) {
+          a.e[0].y = img_stream ? nullptr : cur;
+          a.e[0].split = (l & 1) ? xt_img : cur_img, a.e[0].split_slope = 0.1f;
+        } else {
+          a.e[0].y = dst, a.e[0].acc_in = acc_in, a.post_div = post_div;
+          a.e[0].split = dst_img, a.e[0].split_slope = 0.1f;
+        }
+        run(a, SVK_LAYER_RESBLOCK_CONV1, src_img);
+      }
+      return;
+    }
     bool fuse = true;
     for (int l = 0; l < SVK_RESBLOCK_PAIRS; ++l) fuse = fuse && pair_fusable(rb, l);
     if (fuse) {
@@ -942,6 +990,23 @@ struct Runner {
   void resblock(const ResBlock& rb, const float* x, float* xt, float* cur, float* dst, const float* acc_in,
                 float post_div, int L) {
     const int C = rb.C;
+    if (rb.type == 2) {  // ResBlock2: x = conv_l(leaky_relu(x)) + x; ping-pong cur / xt so no conv runs in place
+      for (int l = 0; l < rb.n; ++l) {
+        const bool last = l == rb.n - 1;
+        const float* src = l == 0 ? x : ((l & 1) ? cur : xt);
+        const int d = rb.dil[l];
+        ConvArgs a = base(rb.c1[l], src, C, 0, L, L, d, (rb.k * d - d) / 2, L, L);
+        a.pre_slope = 0.1f;
+        a.e[0].res = src, a.e[0].C = C;
+        if (!last) {
+          a.e[0].y = (l & 1) ? xt : cur;
+        } else {
+          a.e[0].y = dst, a.e[0].acc_in = acc_in, a.post_div = post_div;
+        }
+        run(a, SVK_LAYER_RESBLOCK_CONV1);
+      }
+      return;
+    }
     for (int l = 0; l < SVK_RESBLOCK_PAIRS; ++l) {
       const float* src = l == 0 ? x : cur;
       const int d = rb.dil[l];
@@ -1363,7 +1428,11 @@ int halo_frames(const svk_handle* h) {
     for (int j = 0; j < c.n_resblock_kernels; ++j) {
       int r = 0;
       const int hk = (c.resblock_kernel_sizes[j] - 1) / 2;
-      for (int l = 0; l < SVK_RESBLOCK_PAIRS; ++l) r += hk * (c.resblock_dilations[j][l] + 1);
+      if (c.resblock_type == 2) {
+        for (int l = 0; l < 2; ++l) r += hk * c.resblock_dilations[j][l];
+      } else {
+        for (int l = 0; l < SVK_RESBLOCK_PAIRS; ++l) r += hk * (c.resblock_dilations[j][l] + 1);
+      }
       rb = r > rb ? r : rb;
     }
     halo += rb;

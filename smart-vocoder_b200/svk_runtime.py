@@ -57,6 +57,7 @@ class SvkConfig(ctypes.Structure):
         ("resblock_kernel_sizes", ctypes.c_int32 * SVK_MAX_RESBLOCK_KERNELS),
         ("resblock_dilations", (ctypes.c_int32 * SVK_RESBLOCK_PAIRS) * SVK_MAX_RESBLOCK_KERNELS),
         ("precision", ctypes.c_int32),
+        ("resblock_type", ctypes.c_int32),
     ]
 
 
@@ -159,7 +160,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.svk_abi_version() != 1:
+        if l.svk_abi_version() != 2:
             raise SvkError(SVK_ERR_STATE, "libsvk ABI version mismatch")
         _lib = l
     return _lib
@@ -193,11 +194,15 @@ def make_config(dims, precision: int = PRECISION_TC) -> SvkConfig:
     c.n_resblock_kernels = len(dims.resblock_kernel_sizes)
     for j, (k, ds) in enumerate(zip(dims.resblock_kernel_sizes, dims.resblock_dilation_sizes)):
         c.resblock_kernel_sizes[j] = int(k)
-        if len(ds) != SVK_RESBLOCK_PAIRS:
-            raise SvkError(SVK_ERR_INVALID, "ResBlock1 needs exactly 3 dilations per kernel size")
+        need = 2 if str(getattr(dims, "resblock", "1")) == "2" else SVK_RESBLOCK_PAIRS
+        if (need == SVK_RESBLOCK_PAIRS and len(ds) != need) or len(ds) < need or len(ds) > SVK_RESBLOCK_PAIRS:
+            raise SvkError(SVK_ERR_INVALID, "ResBlock1 needs exactly 3 dilations per kernel size, ResBlock2 uses the first 2")
         for l, dil in enumerate(ds):
             c.resblock_dilations[j][l] = int(dil)
+        for l in range(len(ds), SVK_RESBLOCK_PAIRS):
+            c.resblock_dilations[j][l] = 1
     c.precision = precision
+    c.resblock_type = 2 if str(getattr(dims, "resblock", "1")) == "2" else 1
     return c
 
 

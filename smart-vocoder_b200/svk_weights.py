@@ -71,8 +71,9 @@ class ModelDims:
         # reference modules.py:308 / modules.py:114 / models.py:122
         assert self.inter_channels % 2 == 0, "channels should be divisible by 2"
         assert self.wn_kernel % 2 == 1
-        if str(self.resblock) != "1":
-            raise NotImplementedError("only ResBlock1 (resblock='1') is on the B200 path")
+        # models.py:121: '1' -> ResBlock1, anything else -> ResBlock2 (two convs: dilation[0], dilation[1])
+        for ds in self.resblock_dilation_sizes:
+            assert len(ds) == 3 if str(self.resblock) == "1" else 2 <= len(ds) <= 3, "ResBlock1 takes 3 dilations, ResBlock2 2"
         assert len(self.upsample_rates) == len(self.upsample_kernel_sizes)
         assert len(self.resblock_kernel_sizes) == len(self.resblock_dilation_sizes)
         for k in self.resblock_kernel_sizes:
@@ -135,6 +136,11 @@ def state_dict_spec(d: ModelDims) -> List[Tuple[str, Tuple[int, ...]]]:
         ch = d.stage_channels(i)
         for j, k in enumerate(d.resblock_kernel_sizes):
             n = i * nk + j
+            if str(d.resblock) != "1":  # ResBlock2 (modules.py:232-241): one ModuleList `convs` of two layers
+                for l in range(2):
+                    p = f"dec.resblocks.{n}.convs.{l}"
+                    spec += [(p + ".bias", (ch,)), (p + ".weight_g", (ch, 1, 1)), (p + ".weight_v", (ch, ch, k))]
+                continue
             for grp in ("convs1", "convs2"):
                 for l in range(3):
                     p = f"dec.resblocks.{n}.{grp}.{l}"

@@ -34,11 +34,11 @@ def test_header_symbols_exported(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/svk.h but not exported by libsvk.so"
     assert set(names) == set(rt.SIGNATURES), "ctypes binding and header disagree"
-    assert lib.svk_abi_version() == 1
+    assert lib.svk_abi_version() == 2
 
 
 def test_config_struct_layout():
-    n_i32 = 11 + 8 + 8 + 1 + 8 + 8 * 3 + 1
+    n_i32 = 11 + 8 + 8 + 1 + 8 + 8 * 3 + 1 + 1  # + resblock_type (ABI 2)
     assert ctypes.sizeof(rt.SvkConfig) == 4 * n_i32
 
 
@@ -120,9 +120,10 @@ def test_shim_ctor_asserts(base_cfg):
     with pytest.raises(AssertionError, match="divisible by 2"):
         SynthesizerTrn(513, 32, **m)
     m = dict(base_cfg["model"])
-    m["resblock"] = "2"
-    with pytest.raises(NotImplementedError):
-        SynthesizerTrn(513, 32, **m)
+    m["resblock"] = "2"  # models.py:121: ResBlock2 takes the first two dilations of each triple (modules.py:232-241)
+    keys = SynthesizerTrn(513, 32, **m).state_dict().keys()
+    assert "dec.resblocks.0.convs.1.weight_v" in keys and "dec.resblocks.0.convs1.0.weight_v" not in keys
+    assert not any(".convs.2." in k for k in keys if k.startswith("dec.resblocks"))
 
 
 def test_clip_len_matches_python_slicing():

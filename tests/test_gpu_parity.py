@@ -658,3 +658,30 @@ def test_config5_shard_at_b64_t1024(net, base_sd, base_dims):
     with inject_eps(eps[63:64]), torch.no_grad():
         o1 = net.infer(dev(mel[63:64]), dev(lengths[63:64], torch.int64), noise_scale=0.667)[0]
     assert torch.equal(o1[0], o_d[63])
+
+
+# ------------------------------------------------------------------------ resblock: "2" (modules.ResBlock2, models.py:121)
+@pytest.mark.parametrize("engine", ["tc", "fp32", "bf16"])
+def test_resblock2_model_matches_reference_golden(engine):
+    """Generator built from ResBlock2 (two convs per block, dilations (1,3)/(2,5)/(3,8)): whole infer against the reference's
+    fp64 golden, and one block per kernel size through svk_resblock1 (which runs whichever block type the handle holds)."""
+    import svk_runtime as rt
+    from gpu_util import build_net, dev
+    from test_oracle import resblock2_case
+    model, dims, sd, g = resblock2_case()
+    net = build_net(model, sd, engine=engine)
+    tol = TOL if engine != "bf16" else 0.05 * float(np.abs(g["ref64_o"]).max())
+    o, mask, (z, *_rest) = _run_infer(net, g)
+    assert np.array_equal(_np(mask), g["ref32_x_mask"])
+    assert np.abs(_np(o) - g["ref64_o"]).max() <= tol
+    if engine != "bf16":
+        assert np.abs(_np(z) - g["ref64_z"]).max() <= TOL
+    x = g["rb_in"]
+    B, C, L = x.shape
+    for j in range(3):
+        xd, y = dev(x), torch.empty(B, C, L, device="cuda")
+        ws = torch.empty(rt.lib().svk_resblock1_workspace_bytes(net._handle.ptr, j, B, L), dtype=torch.uint8, device="cuda")
+        rt.check(rt.lib().svk_resblock1(net._handle.ptr, j, xd.data_ptr(), B, L, y.data_ptr(), ws.data_ptr(), ws.numel(),
+                                        torch.cuda.current_stream().cuda_stream))
+        err = np.abs(_np(y) - g[f"rb{j}"]).max()
+        assert err <= (TOL if engine != "bf16" else 0.05 * float(np.abs(g[f"rb{j}"]).max())), (j, err)

@@ -194,3 +194,33 @@ def test_oracle_posterior_and_flow_forward_match_reference(base_sd, base_dims, d
     if dtype is np.float64:  # the flow is a bijection: reverse(forward(z)) == z
         back = orc.flow_reverse(base_sd, base_dims, z_p, mask)
         assert np.abs(back - g["ref64_z"]).max() <= 1e-12
+
+
+# ------------------------------------------------------------------------ resblock: "2" (modules.ResBlock2)
+def resblock2_case():
+    """Model kwargs / weights of tests/golden/make_golden_resblock2.py (base model, Generator built from ResBlock2)."""
+    import json
+    import os
+    import svk_weights as W
+    from conftest import ROOT
+    model = dict(json.load(open(os.path.join(ROOT, "configs", "iitp_base.json")))["model"])
+    model["resblock"] = "2"
+    model["resblock_dilation_sizes"] = [[1, 3], [2, 5], [3, 8]]
+    dims = W.dims_from_model_kwargs(513, **model)
+    sd = W.make_state_dict(dims, seed=2222)
+    g = load_golden("infer_resblock2_b2_t150")
+    assert W.state_dict_checksum(sd) == str(g["checksum"]), "weight recipe drifted"
+    return model, dims, sd, g
+
+
+def test_oracle_resblock2_matches_reference():
+    """ResBlock2 (modules.py:232-256): the block alone and the whole infer, fp64 oracle vs the reference's fp64 run."""
+    _, dims, sd, g = resblock2_case()
+    orc = Oracle(np.float64)
+    for j, (k, dil) in enumerate(zip(dims.resblock_kernel_sizes, dims.resblock_dilation_sizes)):
+        r = orc.resblock2(sd, f"dec.resblocks.{j}", g["rb_in"].astype(np.float64), k, dil)
+        assert np.abs(r - g[f"rb{j}"]).max() < 5e-6, j  # golden stored as fp32
+    o, mask, (z, *_rest) = orc.infer(sd, dims, g["mel"], g["lengths"], g["eps"], float(g["noise_scale"]), None)
+    assert np.array_equal(mask.astype(np.float32), g["ref32_x_mask"])
+    assert np.abs(o - g["ref64_o"]).max() <= 1e-10
+    assert np.abs(z - g["ref64_z"]).max() <= 2e-6
