@@ -161,13 +161,21 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer
+  } else if (warp == 1 || (kTma && warp == 3 && ta.dual_issue)) {
+    // ------------------------------------------------ MMA issuer(s)
     // The whole warp walks the loop (uniform control flow, barrier waits by all lanes); one elected
     // lane issues.  The tensor pipe only stays busy if issuing an MMA costs far less than the MMA
     // itself (64-128 cycles), so descriptors are never rebuilt: their high words are constants and
     // their low words (start address >> 4 | LBO) advance by 32-bit adds.
+    // Narrow layers (resident weights, N' <= 128): an MMA lasts ~46-58 cycles whatever N is (tools/mma_bench3.cu), about
+    // what the lane needs to issue it, so the lane never runs ahead of the pipe and the ~400 cycles it spends per tile on
+    // barrier waits / commits / bookkeeping leave the pipe idle (ncu, C=32 k=7 conv1: 1811 cycles per tile against 1372
+    // of MMA time).  With `dual_issue` the spare warp 3 is a second issuer: warp 1 takes the even tiles of the CTA's
+    // list, warp 3 the odd ones -- different accumulator stages and A stages, so their MMAs need no mutual order,
+    // and one warp's per-tile overhead hides under the other's MMAs.  tcgen05.commit tracks the MMAs of the
+    // issuing thread, which is exactly the tile the barrier belongs to.
     {
+      const int first = warp == 3 ? 1 : 0, step = ta.dual_issue ? 2 : 1;
       // f16 x f16 -> f32, both operands K-major, M = 128
       // (planes == 1: bf16 x bf16, a/b format fields = 1)
       const uint32_t fmt = planes == 1 ? ((1u << 7) | (1u << 10)) : 0u;
@@ -188,12 +196,14 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
       const bool leader = elect_one();
       int ast = 0, wst = 0;
       uint32_t aph = 0, wph = 0;
-      for (int i = 0; i < n_my; ++i) {
+      for (int q = first * nchunks; q > 0; --q)  // A stage of this issuer's first chunk
+        if (++ast == na) ast = 0, aph ^= 1;
+      for (int i = first; i < n_my; i += step) {
         const int s = i & (nacc - 1);
         mbar_wait_u32(bar_acc_empty + 8u * s, ((uint32_t)(i >> nacc_shift) & 1u) ^ 1u);  // epilogue drained this stage
         tc_fence_after();
         const uint32_t dmain = tmem + (uint32_t)(s * acc_cols), dcross = dmain + (uint32_t)N;
-        const bool wait_w = !resident || i == 0;
+        const bool wait_w = !resident || i == first;
         uint32_t acc = 0;
         for (int ch = 0; ch < nchunks; ++ch) {
           mbar_wait_u32(bar_a_full + 8u * ast, aph);
@@ -256,6 +266,8 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
           if (++ast == na) ast = 0, aph ^= 1;
         }
         if (leader) umma_commit_u32(bar_acc_full + 8u * s);
+        for (int q = (step - 1) * nchunks; q > 0; --q)  // skip the other issuer's tile
+          if (++ast == na) ast = 0, aph ^= 1;
       }
     }
     __syncwarp();
@@ -1214,6 +1226,19 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
                   (!d.res_img || d.res_slope > 0.f) && d.ch_sign == 1 && d.ch_off % 16 == 0 && d.C % 32 == 0 && !a.act_tanh &&
                   !(d.use_mask && a.out_mask) && a.Cout % ta.N == 0 && nch % esplit == 0 && hc % 2 == 0 &&
                   2ull * a.B * d.C * (unsigned long long)a.y_stride < (1ull << 32) && ta.x_split != nullptr;
+  }
+  {
+    // second MMA issuer (spare warp of the TMA variant) for resident-weight layers whose MMAs are short (N' = 2N <= 128)
+    static const int dual = [] {
+      const char* e = getenv("SVK_DUAL_ISSUE");
+      return e ? atoi(e) : 1;
+    }();
+    ta.dual_issue = dual && ta.x_split != nullptr && ta.resident && ta.nacc >= 4 && (dual >= 2 || ta.planes * ta.N <= 128);
+    // An mbarrier parity wait is only meaningful one phase away from the barrier's current phase, so every A stage must
+    // always be consumed by the same issuer: ring depth = a multiple of two tiles' chunks (accumulator stages: nacc is even).
+    const int two_tiles = 2 * (a.Cin / KC);
+    if (ta.dual_issue && ta.na >= two_tiles) ta.na = ta.na / two_tiles * two_tiles;
+    else ta.dual_issue = 0;
   }
   int cols = 32;
   while (cols < ta.nacc * ta.planes * ta.N) cols <<= 1;

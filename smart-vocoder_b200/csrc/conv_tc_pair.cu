@@ -114,8 +114,12 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer (whole warp walks, elected lane issues)
+  } else if (warp == 1 || (warp == 3 && pa.dual_issue)) {
+    // ------------------------------------------------ MMA issuer(s) (whole warp walks, elected lane issues)
+    // With resident weights (`dual_issue`) warp 1 issues every conv1 and the otherwise idle warp 3 every conv2: the two
+    // streams use disjoint barriers, accumulators and A tiles, so they need no mutual order, their MMAs interleave in the
+    // tensor pipe and one issuer's per-item waits hide under the other's MMAs (a narrow MMA lasts about as long as it
+    // takes to issue, so a single lane never runs ahead of the pipe: conv_tc.cu, tools/mma_bench3.cu).
     const uint32_t idesc1 = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * N) >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t b_hi = (128u >> 4) | (1u << 14);
@@ -241,11 +245,19 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
         umma_commit(&hdr->acc2_full[s]);
       }
     };
-    for (int i = 0; i < n_my; ++i) {
-      conv1(i);
-      if (i > 0) conv2(i - 1);
+    if (pa.dual_issue) {
+      if (warp == 1) {
+        for (int i = 0; i < n_my; ++i) conv1(i);
+      } else {
+        for (int i = 0; i < n_my; ++i) conv2(i);
+      }
+    } else {
+      for (int i = 0; i < n_my; ++i) {
+        conv1(i);
+        if (i > 0) conv2(i - 1);
+      }
+      if (n_my > 0) conv2(n_my - 1);
     }
-    if (n_my > 0) conv2(n_my - 1);
     __syncwarp();
   } else if (warp < 4) {
     // ------------------------------------------------ x-image loader: one TMA box per 32-channel chunk
@@ -505,6 +517,11 @@ cudaError_t launch_conv_tc_pair(const ConvPairArgs& in, cudaStream_t stream) {
   }
   if (pa.na > P_NA_MAX) pa.na = P_NA_MAX;
   if (pa.na < 2) return cudaErrorInvalidValue;
+  static const bool dual = [] {
+    const char* e = getenv("SVK_DUAL_ISSUE");
+    return !(e && e[0] == '0');
+  }();
+  pa.dual_issue = dual && pa.resident;  // the weight RING is consumed in one interleaved order: one issuer only
   pa.a_off = (int)fixed;
   pa.a2_off = (int)(fixed + pa.na * a1_stage);
   pa.w_off = (int)(pa.a2_off + a2_bytes);

@@ -91,6 +91,7 @@ struct ConvTcArgs {
   // filled by launch_conv_tc:
   int rows, tmem_cols, na, nw, resident, items, ntiles_t, bias_bytes, bias_count, nacc, epi_groups, a_off;
   int epi_fast;  // lean STORE epilogue (conv_tc.cu: the decoder ResBlock convs take it)
+  int dual_issue;  // two MMA issuer warps taking alternate tiles (resident weights, short MMAs)
   FastDiv div_t, div_b;  // by ntiles_t and by B (work-item decoding)
 };
 int conv_tc_rows(int K, int dil);
@@ -126,6 +127,7 @@ struct ConvPairArgs {
   float y_slope;
   // filled by launch_conv_tc_pair:
   int rows1, rows2, TO, h, ntiles_t, items, na, nw, resident, a_off, a2_off, w_off;
+  int dual_issue;  // conv1 and conv2 issued by two warps (resident weights)
   FastDiv div_t;
 };
 bool conv_tc_pair_supported(int C, int K, int dil1);

@@ -745,6 +745,13 @@ struct Runner {
     }
     prof_close(open);
     h->launches++;
+    static const bool sync_each = getenv("SVK_SYNC_LAUNCHES") != nullptr;  // debugging aid: name the launch that faults
+    if (sync_each && err == cudaSuccess) {
+      err = cudaStreamSynchronize(stream);
+      if (err != cudaSuccess)
+        fprintf(stderr, "libsvk: launch failed: layer %d Cin %d Cout %d K %d dil %d Lout %d mode %d tc %d image-in %d: %s\n", layer,
+                a.Cin, a.Cout, a.K, a.dil, a.Lout, a.mode, (int)use_tc, x_split != nullptr, cudaGetErrorString(err));
+    }
   }
   void note(cudaError_t e) {
     if (err == cudaSuccess) err = e;
