@@ -26,10 +26,26 @@ namespace svk {
 namespace {
 
 constexpr int P_NA_MAX = 8, P_MAXNW = 32;
-// warps 4..7 run epi1 (conv1 accumulators -> xt tile in shared memory: cheap), warps 8..15 run epi2 (conv2 accumulators +
-// residual -> fp32 / image in HBM: the expensive one -- with four warps it reached 3.7 TB/s where conv_tc's eight-warp
-// epilogue reaches 5; its two warps per TMEM lane quarter take alternate 16-column jobs)
-constexpr int P_EPI1_WARPS = 4, P_EPI2_WARPS = 8;
+// warps 4..7 run epi1 (conv1 accumulators -> xt tile in shared memory), the next eight epi2 (conv2 accumulators +
+// residual -> fp32 / image in HBM -- with four warps it reached 3.7 TB/s where conv_tc's eight-warp epilogue reaches 5);
+// the two epi2 warps of a TMEM lane quarter take alternate 16-column jobs.
+// -DSVK_PAIR_EPI1_WARPS=8 gives epi1 two warps per lane quarter as well (640 threads; registers re-balanced between the
+// roles with setmaxnreg).  ncu (profiles/r2_ncu_pair_c32_k7.txt) shows the four epi1 warps busy 75 % of the kernel at one
+// instruction per ~6 cycles, which suggested them as the bound -- but eight change nothing (C = 32) or lose 3 % (C = 64,
+// profiles/r2_pair_epi1_warps_ab.txt): the same capture has the epi2 warps stalled on the registers of stores the memory
+// pipe has not accepted yet, i.e. the fused pairs are bound by their HBM write path, not by either epilogue's issue rate.
+#ifndef SVK_PAIR_EPI1_WARPS
+#define SVK_PAIR_EPI1_WARPS 4
+#endif
+constexpr int P_EPI1_WARPS = SVK_PAIR_EPI1_WARPS, P_EPI2_WARPS = 8;
+static_assert(P_EPI1_WARPS == 4 || P_EPI1_WARPS == 8, "epi1: one or two warps per TMEM lane quarter");
+// Register budget (P_EPI1_WARPS == 8: 640 threads, 96 registers each at launch): the four producer / issuer warps and the
+// epi1 warps give registers back (setmaxnreg.dec) and the epi2 warps, whose operand prefetch buffers need them, take
+// more (setmaxnreg.inc); each role's code sits in a branch dominated by its setmaxnreg, which is what ptxas allocates by.
+constexpr int P_REGS_PRODUCER = 56, P_REGS_EPI1 = 80, P_REGS_EPI2 = 128;  // no spills in any role
+constexpr int P_REGS_LAUNCH = 96;  // 65536 / 640 rounded down to the allocation unit of 8: what ptxas gives the kernel
+static_assert(P_EPI1_WARPS != 8 || 128 * P_REGS_PRODUCER + 256 * P_REGS_EPI1 + 256 * P_REGS_EPI2 <= 640 * P_REGS_LAUNCH,
+              "setmaxnreg.inc only draws on registers the CTA's own warps have released (a larger sum deadlocks)");
 constexpr int P_THREADS = 128 + 32 * (P_EPI1_WARPS + P_EPI2_WARPS);
 constexpr int P_EPI1_THREADS = 32 * P_EPI1_WARPS, P_EPI2_THREADS = 32 * P_EPI2_WARPS;
 
@@ -83,6 +99,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
   tc_fence_after();
   const uint32_t tmem = hdr->tmem_base;
   griddep_launch_dependents();  // PDL, as in conv_tc.cu: only weights / biases are touched before griddep_wait()
+  if constexpr (P_EPI1_WARPS == 8) {
+    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(P_REGS_PRODUCER));
+  }
 
   if (warp == 0) {
     // ------------------------------------------------ weight producer
@@ -287,7 +306,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
     // the same warps kept only one item in flight (conv1 -> epi1 -> conv2 -> epi2 is a serial chain of ~4000 cycles per
     // item); split, epi1(i+1) runs under conv2(i)'s MMAs and epi2(i) under conv1(i+2)'s.
     const int q4 = warp & 3, role2 = warp >= 4 + P_EPI1_WARPS ? 1 : 0;
-    const int part = role2 ? (warp - 4 - P_EPI1_WARPS) >> 2 : 0;  // epi2: which of the two warps of this lane quarter
+    const int part = role2 ? (warp - 4 - P_EPI1_WARPS) >> 2 : (warp - 4) >> 2;  // which of the warps of this lane quarter
     const int row = q4 * 32 + lane;
     const int hc = N >> 4;  // 16-column jobs per item and warp: 2 (N = 32) or 4 (N = 64)
     const int n_lo = 0, n_hi = N;
@@ -299,6 +318,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
       b = (int)fast_div((uint32_t)item, pa.div_t);
       tt = item - b * pa.ntiles_t;
     };
+    if (role2 == 0) {
+    if constexpr (P_EPI1_WARPS == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(P_REGS_EPI1));
     // epi1: conv1 accumulators -> conv2's A tile in shared memory
     auto epi1 = [&](int i) {
       const int s = i & 1;
@@ -310,7 +331,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
       mbar_wait(&hdr->a2_empty[s], ((uint32_t)(i >> 1) & 1u) ^ 1u);  // conv2(i-2) has finished reading this tile
       tc_fence_after();
       const uint32_t tsub = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(s * 2 * N);
-      for (int n0 = n_lo; n0 < n_hi; n0 += 16) {
+      for (int n0 = n_lo + (P_EPI1_WARPS == 8 ? 16 * part : 0); n0 < n_hi; n0 += 2 * P_EPI1_WARPS) {
         uint32_t m[16], c[16];
         tmem_ld16(tsub + (uint32_t)n0, m);
         tmem_ld16(tsub + (uint32_t)(N + n0), c);
@@ -348,6 +369,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
       mbar_arrive(&hdr->a2_full[s]);
       mbar_arrive(&hdr->acc1_empty[s]);
     };
+    for (int i = 0; i < n_my; ++i) epi1(i);
+    } else {
+    // the epi2 code below is dominated by this point, so ptxas lets it use the larger register file
+    if constexpr (P_EPI1_WARPS == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(P_REGS_EPI2));
 
     // epi2 operands (residual, running sum) are requested two of this warp's jobs ahead of use into two buffers that its
     // jobs use alternately.  The two epi2 warps of a lane quarter take alternate 16-column chunks of an item, so a warp has
@@ -390,10 +415,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
     };
 #pragma unroll
     for (int e = 0; e < 16; ++e) rA[e] = 0.f, rB[e] = 0.f;  // stays zero when the pair has no residual operand at all
-    if (role2 == 1) {
-      load_ops(rA, 0);
-      load_ops(rB, 1);
-    }
+    load_ops(rA, 0);
+    load_ops(rB, 1);
 
     // epi2: conv2 accumulators -> y = conv2 + bias + x (+ running sum) (/ post_div) -> fp32 and/or image
     const float4* bias2_4 = reinterpret_cast<const float4*>(bias_s + N);
@@ -460,15 +483,14 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
       mbar_arrive(&hdr->acc2_empty[s]);
     };
 
-    if (role2 == 0) {
-      for (int i = 0; i < n_my; ++i) epi1(i);
-    } else if (hc2 == 1) {
+    if (hc2 == 1) {
       for (int i = 0; i < n_my; i += 2) {  // one job per item: the two buffers alternate between items
         epi2(i, rA, rA);
         if (i + 1 < n_my) epi2(i + 1, rB, rB);
       }
     } else {
       for (int i = 0; i < n_my; ++i) epi2(i, rA, rB);
+    }
     }
   }
 
