@@ -35,7 +35,7 @@ constexpr int P_NA_MAX = 8, P_MAXNW = 32;
 // profiles/r2_pair_epi1_warps_ab.txt): the same capture has the epi2 warps stalled on the registers of stores the memory
 // pipe has not accepted yet, i.e. the fused pairs are bound by their HBM write path, not by either epilogue's issue rate.
 #ifndef SVK_PAIR_EPI1_WARPS
-#define SVK_PAIR_EPI1_WARPS 4
+#define SVK_PAIR_EPI1_WARPS 8
 #endif
 constexpr int P_EPI1_WARPS = SVK_PAIR_EPI1_WARPS, P_EPI2_WARPS = 8;
 static_assert(P_EPI1_WARPS == 4 || P_EPI1_WARPS == 8, "epi1: one or two warps per TMEM lane quarter");
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
       mbar_wait(&hdr->a2_empty[s], ((uint32_t)(i >> 1) & 1u) ^ 1u);  // conv2(i-2) has finished reading this tile
       tc_fence_after();
       const uint32_t tsub = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(s * 2 * N);
-      for (int n0 = n_lo + (P_EPI1_WARPS == 8 ? 16 * part : 0); n0 < n_hi; n0 += 2 * P_EPI1_WARPS) {
+      for (int n0 = n_lo + (P_EPI1_WARPS == 8 ? 16 * part : 0); n0 < n_hi; n0 += 16 * (P_EPI1_WARPS / 4)) {
         uint32_t m[16], c[16];
         tmem_ld16(tsub + (uint32_t)n0, m);
         tmem_ld16(tsub + (uint32_t)(N + n0), c);

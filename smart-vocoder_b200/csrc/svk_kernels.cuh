@@ -135,29 +135,39 @@ cudaError_t launch_conv_tc_pair(const ConvPairArgs& a, cudaStream_t stream);
 
 // ---- fused WN layer (wn_layer.cu): in_layer conv + gate + res_skip 1x1 + residual / skip update in ONE launch
 // (modules.py:156-175).  Weights are the conv_tc_pack images of the two convs (in_layer gate-packed, planes as given).
+constexpr int WN_MAX_LAYERS = 16;
+struct WnLayerParams {       // what differs between the layers of one WN stack
+  const uint16_t* w_in;      // in_layer image (gate-packed), N_in channels per tile
+  const uint16_t* w_rs;      // res_skip image
+  const float* bias_in;      // [nt_in * N_in], virtual (gate-packed) order
+  const float* bias_rs;      // [nt_rs * N_rs]
+  float unscale_in, unscale_rs;
+  int N_rs, Cout_rs;         // res_skip: channels per tile, outputs (2H; H on the last layer of a stack)
+  int nt_rs, bias_count_rs;  // filled by launch_wn_layers
+};
+// n_layers consecutive layers l0 .. l0 + n_layers - 1 of a WN stack of n_total layers in ONE launch (wn_layer.cu).
+// n_layers == 1: one launch per layer.  n_layers > 1: every CTA keeps its 128-frame tile through all layers and adjacent
+// tiles synchronise through `flags` (needs items <= SM count: all CTAs co-resident).
 struct WnLayerArgs {
   int B, T, H, K, planes;
-  const uint16_t* x_img_in;  // operand image of the incoming x [B, H, T] (read with a (K-1)/2 halo by TMA)
-  uint16_t* x_img_out;       // operand image of the updated x (another buffer: neighbours still read the old one); null = none
-  float* x;                  // fp32 x, updated in place (unused on the last layer)
+  uint16_t* img[2];          // operand images of x [B, H, T]: layer l0 + j reads img[j & 1] (with a (K-1)/2 halo, by TMA) and
+                             // writes the updated x into img[(j + 1) & 1] (neighbours still read the old one)
+  float* x;                  // fp32 x, updated in place (unused on the last layer of the stack)
   float* out;                // fp32 skip accumulator [B, H, T]
   const float* mask;         // [B, T]
-  int first, last;           // first: out = skip (nothing read); last: res_skip has H outputs, out = (out + rs) * mask
-  const uint16_t* w_in;
-  const float* bias_in;      // [nt_in * N_in], virtual (gate-packed) order
-  float unscale_in;
+  int l0, n_layers, n_total; // global layer 0: out = skip (nothing read); global layer n_total - 1: res_skip has H outputs,
+                             // out = (out + rs) * mask, no x / image written
   int N_in;
-  const uint16_t* w_rs;
-  const float* bias_rs;      // [nt_rs * N_rs]
-  float unscale_rs;
-  int N_rs, Cout_rs;
-  // filled by launch_wn_layer:
-  int rows, ntiles_t, items, nt_in, nt_rs, na, nw, a_off, acts_off, w_off, w_slot, bias_count_in, bias_count_rs, acc_stride,
-      tmem_cols;
+  int* flags;                // [items] zeroed before the launch (n_layers > 1): layers completed by each tile
+  long long* trace;          // developer aid ($SVK_WN_TRACE): [items][n_layers][16] clock64() stamps of the role loops, or null
+  WnLayerParams layer[WN_MAX_LAYERS];
+  // filled by launch_wn_layers:
+  int rows, ntiles_t, items, nt_in, na, nw, a_off, acts_off, w_off, w_slot, bias_count_in, bias_max_rs, acc_stride, tmem_cols;
   FastDiv div_t;
 };
 bool wn_layer_supported(int H, int K, int N_in, int N_rs, int Cout_rs, int planes);
-cudaError_t launch_wn_layer(const WnLayerArgs& a, cudaStream_t stream);
+int wn_stack_max_items();  // tiles a multi-layer launch can take (= SM count of the current device)
+cudaError_t launch_wn_layers(const WnLayerArgs& a, cudaStream_t stream);
 
 // elementwise / small kernels
 cudaError_t launch_sequence_mask(const int64_t* lengths, int B, int T, float* mask, cudaStream_t s);

@@ -127,6 +127,7 @@ struct svk_handle {
                                 // fused pairs, -1 = the round-1 rule (C >= 256, C >= 128 with k >= 7)
   int fuse_wn = 1;              // one launch per WN layer (wn_layer.cu): 1 = when the batch fills the GPU (see Runner::wn),
                                 // 2 = always, 0 = never ($SVK_FUSE_WN; the two-launch form spreads a layer over 3x more CTAs)
+  int wn_stack = 1;             // whole WN stacks in one launch when every tile gets its own SM ($SVK_WN_STACK=0: per layer)
 
   // svk_profile_begin/end state
   bool profiling = false;
@@ -135,6 +136,7 @@ struct svk_handle {
   size_t prof_cap = 0;
 
   int* d_range_flag = nullptr;  // raised by the final tanh epilogue on a non-finite sample (svk_check_range)
+  int* d_wn_flags = nullptr;    // [1024] tile progress counters of the multi-layer WN launches (wn_layer.cu), zeroed per launch
 
   // svk_infer_host state
   cudaStream_t host_stream = nullptr;
@@ -457,10 +459,11 @@ extern "C" int svk_create(const svk_config* cfg, int device, svk_handle** out) {
   if (const char* e = getenv("SVK_FUSE_PAIRS"))
     h->fuse_pairs = atoi(e) != 0, h->fuse_pairs_all = atoi(e) == 2, h->fuse_pairs_c32 = atoi(e) == 3;
   if (const char* e = getenv("SVK_FUSE_WN")) h->fuse_wn = atoi(e);
+  if (const char* e = getenv("SVK_WN_STACK")) h->wn_stack = atoi(e);
   if (const char* e = getenv("SVK_IMG_STREAM")) h->img_stream = atoi(e);
   build_key_spec(h);
   if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&h->d_range_flag, sizeof(int)) != cudaSuccess ||
-      cudaMemset(h->d_range_flag, 0, sizeof(int)) != cudaSuccess) {
+      cudaMemset(h->d_range_flag, 0, sizeof(int)) != cudaSuccess || cudaMalloc(&h->d_wn_flags, 1024 * sizeof(int)) != cudaSuccess) {
     delete h;
     return fail(SVK_ERR_CUDA, "svk_create: device allocation failed");
   }
@@ -475,6 +478,7 @@ extern "C" void svk_destroy(svk_handle* h) {
   if (h->d_tcblob) cudaFree(h->d_tcblob);
   if (h->host_dev) cudaFree(h->host_dev);
   if (h->d_range_flag) cudaFree(h->d_range_flag);
+  if (h->d_wn_flags) cudaFree(h->d_wn_flags);
   if (h->host_stream) cudaStreamDestroy(h->host_stream);
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   delete h;
@@ -833,32 +837,73 @@ struct Runner {
     for (int i = 0; i < n && fused; ++i)
       fused = wn_layer_supported(H, k, in[i].tc_N, rs[i].tc_N, rs[i].Cout, h->planes()) && rs[i].Cout == (i < n - 1 ? 2 * H : H);
     if (fused) {
-      for (int i = 0; i < n && err == cudaSuccess; ++i) {
+      // The whole stack in ONE launch when every tile can have its own SM (tiles synchronise with their neighbours inside
+      // the kernel); otherwise one launch per layer.
+      const bool stack = h->wn_stack && n > 1 && n <= WN_MAX_LAYERS && wn_tiles <= wn_stack_max_items() && wn_tiles <= 1024 && h->d_wn_flags;
+      const int per = stack ? n : 1;
+      for (int i0 = 0; i0 < n && err == cudaSuccess; i0 += per) {
         WnLayerArgs w;
         memset(&w, 0, sizeof(w));
         w.B = B, w.T = T, w.H = H, w.K = k, w.planes = h->planes();
-        w.x_img_in = (i & 1) ? acts_img : x_img;
-        w.x_img_out = i < n - 1 ? ((i & 1) ? x_img : acts_img) : nullptr;
+        // layer i reads the image in buffer (i & 1) and writes buffer ((i + 1) & 1)
+        w.img[0] = (i0 & 1) ? acts_img : x_img, w.img[1] = (i0 & 1) ? x_img : acts_img;
         w.x = x, w.out = out, w.mask = mask;
-        w.first = i == 0, w.last = i == n - 1;
-        w.w_in = h->d_tcblob + in[i].tc_off, w.bias_in = h->d_blob + in[i].tc_b_off, w.unscale_in = in[i].tc_unscale, w.N_in = in[i].tc_N;
-        w.w_rs = h->d_tcblob + rs[i].tc_off, w.bias_rs = h->d_blob + rs[i].tc_b_off, w.unscale_rs = rs[i].tc_unscale, w.N_rs = rs[i].tc_N;
-        w.Cout_rs = rs[i].Cout;
+        w.l0 = i0, w.n_layers = per, w.n_total = n;
+        w.N_in = in[i0].tc_N;
+        w.flags = h->d_wn_flags;
+        double flops = 0.0, bytes = 0.0, dup = 0.0;
+        const double E = (double)B * H * T, img = h->planes() * 0.5;
+        for (int j = 0; j < per; ++j) {
+          const int i = i0 + j;
+          WnLayerParams& lp = w.layer[j];
+          lp.w_in = h->d_tcblob + in[i].tc_off, lp.bias_in = h->d_blob + in[i].tc_b_off, lp.unscale_in = in[i].tc_unscale;
+          lp.w_rs = h->d_tcblob + rs[i].tc_off, lp.bias_rs = h->d_blob + rs[i].tc_b_off, lp.unscale_rs = rs[i].tc_unscale;
+          lp.N_rs = rs[i].tc_N, lp.Cout_rs = rs[i].Cout;
+          if (in[i].tc_N != w.N_in) err = cudaErrorInvalidValue;
+          const bool first = i == 0, last = i == n - 1;
+          flops += 2.0 * B * (double)T * ((double)2 * H * H * k + (double)rs[i].Cout * H);
+          // x image in; fp32 x read + written and its new image (not on the last layer); out read (not on the first) + written; weights
+          bytes += 4.0 * E * (img + (last ? 0.0 : 2.0 + img) + (first ? 1.0 : 2.0)) + 4.0 * ((double)2 * H * H * k + (double)rs[i].Cout * H);
+          dup += last ? 0.0 : 4.0 * E * img;
+        }
+        if (err != cudaSuccess) break;
         bool open = false;
         if (h->profiling && h->prof_records.size() < h->prof_cap) {
           svk_launch_record r;
           memset(&r, 0, sizeof(r));
-          r.layer = SVK_LAYER_WN_LAYER, r.cin = H, r.cout = rs[i].Cout, r.k = k, r.dilation = 1, r.batch = B, r.length = T, r.engine = 1;
-          const double E = (double)B * H * T, img = h->planes() * 0.5;
-          r.flops = 2.0 * B * (double)T * ((double)2 * H * H * k + (double)rs[i].Cout * H);
-          // x image in; fp32 x read + written and its new image (not on the last layer); out read (not on the first) + written; weights
-          r.bytes = 4.0 * E * (img + (w.last ? 0.0 : 2.0 + img) + (w.first ? 1.0 : 2.0)) + 4.0 * ((double)2 * H * H * k + (double)rs[i].Cout * H);
-          r.dup_bytes = w.last ? 0.0 : 4.0 * E * img;
+          r.layer = SVK_LAYER_WN_LAYER, r.cin = H, r.cout = per > 1 ? 2 * H * per : rs[i0].Cout, r.k = k, r.dilation = 1, r.batch = B, r.length = T, r.engine = 1;
+          r.flops = flops, r.bytes = bytes, r.dup_bytes = dup;
           h->prof_records.push_back(r);
           cudaEventRecord(h->prof_events[2 * (h->prof_records.size() - 1)], stream);
           open = true;
         }
-        err = launch_wn_layer(w, stream);
+        // developer aid: $SVK_WN_TRACE=<file> dumps the clock64() stamps of the first multi-layer launch of the process
+        static const char* trace_path = getenv("SVK_WN_TRACE");
+        static bool traced = false;
+        long long* d_trace = nullptr;
+        const size_t trace_n = (size_t)wn_tiles * per * 16;
+        if (trace_path && !traced && per > 1 && cudaMalloc(&d_trace, trace_n * sizeof(long long)) == cudaSuccess) {
+          cudaMemsetAsync(d_trace, 0, trace_n * sizeof(long long), stream);
+          w.trace = d_trace;
+        }
+        err = launch_wn_layers(w, stream);
+        if (d_trace) {
+          traced = true;
+          std::vector<long long> host(trace_n);
+          cudaStreamSynchronize(stream);
+          cudaMemcpy(host.data(), d_trace, trace_n * sizeof(long long), cudaMemcpyDeviceToHost);
+          cudaFree(d_trace);
+          if (FILE* f = fopen(trace_path, "w")) {
+            fprintf(f, "tile,layer,e0,e1,e2,e3,e4,e5,e6,e7,e8,e9,e10,e11,e12,e13,e14,e15\n");
+            for (int t = 0; t < wn_tiles; ++t)
+              for (int l = 0; l < per; ++l) {
+                fprintf(f, "%d,%d", t, l);
+                for (int e = 0; e < 16; ++e) fprintf(f, ",%lld", host[((size_t)t * per + l) * 16 + e]);
+                fprintf(f, "\n");
+              }
+            fclose(f);
+          }
+        }
         prof_close(open);
         h->launches++;
       }

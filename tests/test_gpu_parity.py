@@ -270,16 +270,20 @@ def test_wn_fused_layer_equals_two_launch_form(base_cfg, base_sd, monkeypatch):
     from gpu_util import build_net, dev
     g = load_golden("infer_base_b3_t300_ragged")
     outs = []
-    for fuse in ("2", "0"):  # 2 = fused whatever the batch size (the default fuses when the batch fills the GPU)
+    # 2 = fused whatever the batch size (the default fuses when the batch fills the GPU); SVK_WN_STACK: the whole stack in
+    # one launch (tiles synchronise with their neighbours inside the kernel) / one launch per layer / the two-launch form
+    for fuse, stack in (("2", "1"), ("2", "0"), ("0", "0")):
         monkeypatch.setenv("SVK_FUSE_WN", fuse)
+        monkeypatch.setenv("SVK_WN_STACK", stack)
         n = build_net(base_cfg["model"], base_sd, engine="tc")
         xo, m, logs, mask = n.enc_p(dev(g["mel"]), dev(g["lengths"], torch.int64))
         z = n.flow(dev(g["ref64_z"]), mask, reverse=False)
         torch.cuda.synchronize()
         outs.append((_np(xo), _np(m), _np(logs), _np(z), n.last_launch_count()))
-    for a, b in zip(outs[0][:4], outs[1][:4]):
-        assert np.array_equal(a, b)
-    assert outs[0][4] < outs[1][4]  # fewer launches
+    for other in outs[1:]:
+        for a, b in zip(outs[0][:4], other[:4]):
+            assert np.array_equal(a, b)
+    assert outs[0][4] < outs[1][4] < outs[2][4]  # fewer launches
     assert np.abs(outs[0][1] - g["ref64_m_p"]).max() <= TOL
 
 
