@@ -13,8 +13,8 @@
 //         -> a conv tap is a ROW shift = +64 B per row on the descriptor's start address.  The tensor
 //            core de-swizzles on absolute address bits (tools/swizzle_probe.cu: any row shift is exact
 //            with base offset 0), and 8 consecutive rows always hit 8 distinct bank groups, so a shifted
-//            tile reads at full rate (a no-swizzle tile loses 1.6x on every tap that is not a multiple
-//            of 8 rows).  One staged tile with a (K-1)*dil halo serves every tap: no im2col.
+//            tile reads at full rate (tools/mma_bench2.cu: no shift residue costs a cycle, on either
+//            operand side).  One staged tile with a (K-1)*dil halo serves every tap: no im2col.
 //     B = weights per (32-channel chunk, tap), K-major, no swizzle: B_s[kgroup][hi n | lo n][16 B],
 //         pre-split/pre-packed at load time in exactly this image (one cp.async.bulk per stage).
 //         Because hi and lo rows are adjacent, ONE MMA with N' = 2N computes xh.wh into the main

@@ -159,7 +159,7 @@ struct WnLayerArgs {
                              // out = (out + rs) * mask, no x / image written
   int N_in;
   int* flags;                // [items] zeroed before the launch (n_layers > 1): layers completed by each tile
-  long long* trace;          // developer aid ($SVK_WN_TRACE): [items][n_layers][16] clock64() stamps of the role loops, or null
+  long long* trace;          // developer aid ($SVK_WN_TRACE): [items][n_layers][32] clock64() stamps of the role loops, or null
   WnLayerParams layer[WN_MAX_LAYERS];
   // filled by launch_wn_layers:
   int rows, ntiles_t, items, nt_in, na, nw, a_off, acts_off, w_off, w_slot, bias_count_in, bias_max_rs, acc_stride, tmem_cols;

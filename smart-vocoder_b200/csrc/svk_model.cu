@@ -881,7 +881,7 @@ struct Runner {
         static const char* trace_path = getenv("SVK_WN_TRACE");
         static bool traced = false;
         long long* d_trace = nullptr;
-        const size_t trace_n = (size_t)wn_tiles * per * 16;
+        const size_t trace_n = (size_t)wn_tiles * per * 32;
         if (trace_path && !traced && per > 1 && cudaMalloc(&d_trace, trace_n * sizeof(long long)) == cudaSuccess) {
           cudaMemsetAsync(d_trace, 0, trace_n * sizeof(long long), stream);
           w.trace = d_trace;
@@ -894,11 +894,13 @@ struct Runner {
           cudaMemcpy(host.data(), d_trace, trace_n * sizeof(long long), cudaMemcpyDeviceToHost);
           cudaFree(d_trace);
           if (FILE* f = fopen(trace_path, "w")) {
-            fprintf(f, "tile,layer,e0,e1,e2,e3,e4,e5,e6,e7,e8,e9,e10,e11,e12,e13,e14,e15\n");
+            fprintf(f, "tile,layer");
+            for (int e = 0; e < 32; ++e) fprintf(f, ",e%d", e);
+            fprintf(f, "\n");
             for (int t = 0; t < wn_tiles; ++t)
               for (int l = 0; l < per; ++l) {
                 fprintf(f, "%d,%d", t, l);
-                for (int e = 0; e < 16; ++e) fprintf(f, ",%lld", host[((size_t)t * per + l) * 16 + e]);
+                for (int e = 0; e < 32; ++e) fprintf(f, ",%lld", host[((size_t)t * per + l) * 32 + e]);
                 fprintf(f, "\n");
               }
             fclose(f);

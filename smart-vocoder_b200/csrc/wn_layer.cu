@@ -67,7 +67,7 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // $SVK_WN_TRACE: event `ev` of layer `l` of this CTA's tile (one thread per role writes)
 __device__ __forceinline__ void wn_stamp(const WnLayerArgs& wa, int l, int ev) {
-  if (wa.trace) wa.trace[((size_t)blockIdx.x * wa.n_layers + l) * 16 + ev] = clock64();
+  if (wa.trace) wa.trace[((size_t)blockIdx.x * wa.n_layers + l) * 32 + ev] = clock64();
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(WN_EPI_THREADS) : "memory"); }
 
@@ -421,6 +421,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
             for (int e = 0; e < 16; ++e) c[e] = 0u;
           }
           tmem_wait_ld();
+          if (etid == 0 && mt < 2) wn_stamp(wa, l, 16 + mt * 8 + 2 * k);      // job k of N-tile mt: accumulators in registers
           if (o0 < Cout_rs) {
             float v[16];
 #pragma unroll
@@ -460,6 +461,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1)
               }
             }
           }
+          if (etid == 0 && mt < 2) wn_stamp(wa, l, 17 + mt * 8 + 2 * k);      // ... and stored
         }
         tc_fence_before();
         mbar_arrive(&hdr->acc_empty[s]);

@@ -16,7 +16,7 @@ S=$(python tools/ncu_inmodel.py --layer resblock_conv1 --cin 128 --k 11 --nth 0 
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s $S -c 6 -f -o $O/${T}_c128_k11_block python tools/ncu_target.py > $O/${T}_ncu_c128.log 2>&1
 S=$(python tools/ncu_inmodel.py --layer resblock_conv2 --cin 32 --k 7 --nth 0 2>/dev/null)
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s $S -c 1 -f -o $O/${T}_c32_k7_conv2 python tools/ncu_target.py > $O/${T}_ncu_c32.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:wn_layer_kernel -s 3 -c 1 -f -o $O/${T}_wn_layer python tools/ncu_target.py > $O/${T}_ncu_wn.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:wn_layer_kernel -s 0 -c 1 -f -o $O/${T}_wn_layer python tools/ncu_target.py > $O/${T}_ncu_wn.log 2>&1
 timeout 120 python tools/mel_bench.py > $O/${T}_mel_bench.json 2>/dev/null
 (timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3) > $O/${T}_smoke.log
 cat $O/${T}_gpu_tests.log $O/${T}_smoke.log
