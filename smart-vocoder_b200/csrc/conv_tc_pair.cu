@@ -26,14 +26,14 @@ namespace svk {
 namespace {
 
 constexpr int P_NA_MAX = 8, P_MAXNW = 32;
-// warps 4..7 run epi1 (conv1 accumulators -> xt tile in shared memory), the next eight epi2 (conv2 accumulators +
+// warps 4..11 run epi1 (conv1 accumulators -> xt tile in shared memory), the next eight epi2 (conv2 accumulators +
 // residual -> fp32 / image in HBM -- with four warps it reached 3.7 TB/s where conv_tc's eight-warp epilogue reaches 5);
-// the two epi2 warps of a TMEM lane quarter take alternate 16-column jobs.
-// -DSVK_PAIR_EPI1_WARPS=8 gives epi1 two warps per lane quarter as well (640 threads; registers re-balanced between the
-// roles with setmaxnreg).  ncu (profiles/r2_ncu_pair_c32_k7.txt) shows the four epi1 warps busy 75 % of the kernel at one
-// instruction per ~6 cycles, which suggested them as the bound -- but eight change nothing (C = 32) or lose 3 % (C = 64,
-// profiles/r2_pair_epi1_warps_ab.txt): the same capture has the epi2 warps stalled on the registers of stores the memory
-// pipe has not accepted yet, i.e. the fused pairs are bound by their HBM write path, not by either epilogue's issue rate.
+// in both roles the two warps of a TMEM lane quarter take alternate 16-column jobs.
+// epi1 had four warps (-DSVK_PAIR_EPI1_WARPS=4, 512 threads) until ncu (profiles/r2_ncu_pair_c32_k7.txt) showed them busy
+// 75 % of the kernel at one instruction per ~6 cycles -- a single latency-bound warp per scheduler, ~3000 cycles per item
+// at C = 32, more than both convs' MMAs of a 3-tap pair.  Eight: C = 32 pairs -5..-9 %, C = 64 k = 3 pairs +3 %
+// (profiles/r2_pair_epi1_warps_ab.txt); the pairs stay bound by their HBM path (same capture: epi2 stalled on the
+// registers of stores the memory pipe has not accepted yet).
 #ifndef SVK_PAIR_EPI1_WARPS
 #define SVK_PAIR_EPI1_WARPS 8
 #endif
