@@ -121,7 +121,9 @@ struct svk_handle {
   int64_t launches = 0;
   bool fuse_pairs = true;  // fused ResBlock conv pairs on the narrow stages ($SVK_FUSE_PAIRS=0 disables: A/B measurements)
   bool fuse_pairs_all = false;
-  bool fuse_pairs_c32 = false;  // every kernel size of the C = 32 stage too (its weights stay resident in the pair kernel)
+  bool fuse_pairs_c32 = true;  // every kernel size of the C = 32 stage too (its weights stay resident in the pair kernel):
+                               // per launch the k >= 7 pairs only break even with the unfused convs, but they move 6.4 GB
+                               // less per step and the power-capped step gains 0.7 % (profiles/r2_ab_fuse_c32.log)
   int img_stream = 0;           // $SVK_IMG_STREAM (A/B): 0 = per-shape default (Runner::resblock_images), 1 = every unfused ResBlock keeps
                                 // its residual stream between pairs as operand images only, 2 = also the first pair and the
                                 // fused pairs, -1 = the round-1 rule (C >= 256, C >= 128 with k >= 7)
@@ -457,7 +459,7 @@ extern "C" int svk_create(const svk_config* cfg, int device, svk_handle** out) {
   h->cfg = c;
   h->device = device;
   if (const char* e = getenv("SVK_FUSE_PAIRS"))
-    h->fuse_pairs = atoi(e) != 0, h->fuse_pairs_all = atoi(e) == 2, h->fuse_pairs_c32 = atoi(e) == 3;
+    h->fuse_pairs = atoi(e) != 0, h->fuse_pairs_all = atoi(e) == 2, h->fuse_pairs_c32 = atoi(e) == 3;  // 1: 3-tap blocks only
   if (const char* e = getenv("SVK_FUSE_WN")) h->fuse_wn = atoi(e);
   if (const char* e = getenv("SVK_WN_STACK")) h->wn_stack = atoi(e);
   if (const char* e = getenv("SVK_IMG_STREAM")) h->img_stream = atoi(e);
@@ -785,7 +787,9 @@ struct Runner {
     if (!h->fuse_pairs || h->planes() != 2) return false;
     // Fusing removes HBM traffic but not MMA work (and recomputes a (K-1)-row halo per item).  Measured at
     // 16 x 1024 frames: k = 3 pairs are HBM-bound and gain 25 %, k >= 7 pairs are bound by the per-MMA floor of
-    // narrow tiles and lose 0-25 %  ->  only the 3-tap blocks are fused ($SVK_FUSE_PAIRS=2 fuses every block).
+    // narrow tiles and lose 0-25 %  ->  the 3-tap blocks are fused, and (round 2: two issuers, eight epi1 warps) every
+    // block of the C = 32 stage, where the k >= 7 pairs now break even per launch and save their xt round trip
+    // ($SVK_FUSE_PAIRS=1: 3-tap blocks only, =2: every block).
     if (h->fuse_pairs_all == false && rb.k > 3 && !(h->fuse_pairs_c32 && rb.C == 32)) return false;
     return conv_tc_pair_supported(rb.C, rb.k, rb.dil[l]) && rb.c1[l].tc && rb.c2[l].tc && rb.c1[l].tc_N == rb.C &&
            rb.c2[l].tc_N == rb.C;
