@@ -124,7 +124,9 @@ struct svk_handle {
   bool fuse_pairs_c32 = true;  // every kernel size of the C = 32 stage too (its weights stay resident in the pair kernel):
                                // per launch the k >= 7 pairs only break even with the unfused convs, but they move 6.4 GB
                                // less per step and the power-capped step gains 0.7 % (profiles/r2_ab_fuse_c32.log)
-  int img_stream = 0;           // $SVK_IMG_STREAM (A/B): 0 = per-shape default (Runner::resblock_images), 1 = every unfused ResBlock keeps
+  int img_stream = 2;           // $SVK_IMG_STREAM (A/B; default 2 since the end of round 2: fewest HBM bytes, -0.35 ms on the
+                                // power-capped step, profiles/r2_ab_img_stream.log): 3 = the fused pairs image-only, the unfused blocks as in 0;
+                                // 0 = per-shape default (Runner::resblock_images), 1 = every unfused ResBlock keeps
                                 // its residual stream between pairs as operand images only, 2 = also the first pair and the
                                 // fused pairs, -1 = the round-1 rule (C >= 256, C >= 128 with k >= 7)
   int fuse_wn = 1;              // one launch per WN layer (wn_layer.cu): 1 = when the batch fills the GPU (see Runner::wn),
@@ -1022,16 +1024,16 @@ struct Runner {
       ConvArgs b = base(rb.c2[l], nullptr, C, 0, L, L, 1, (rb.k - 1) / 2, L, L);
       b.pre_slope = 0.1f;
       b.e[0].C = C;
-      // x + xt (modules.py:220).  On the wide, tensor-bound layers of the hi/lo engine the residual stream
-      // between the pairs of a block lives in HBM as its operand image only: the epilogue rebuilds
-      // x = hi + lo (leaky_relu inverted, ~2^-22 relative) instead of reading a second, fp32 copy (measured:
-      // -7..-11 % on C >= 128, k >= 7; the narrow layers are bound by epilogue instruction latency and lose,
-      // so they keep the fp32 copy).  A block's input and output are always fp32.
-      // Measured per shape with the lean epilogue reading either form (profiles/r2_img_stream_ab.txt): the image-only
-      // stream wins on C >= 128 and on the k = 7 blocks of the narrow stages, the fp32 copy on their k = 11 blocks.
-      const bool img_stream = h->planes() == 2 && (h->img_stream >= 1 || (h->img_stream == 0 && (C >= 128 || rb.k == 7)) ||
-                                                     (h->img_stream < 0 && (C >= 256 || (C >= 128 && rb.k >= 7))));
-      if ((l > 0 || h->img_stream >= 2) && img_stream) b.e[0].res_img = src_img, b.e[0].res_slope = 0.1f;
+      // x + xt (modules.py:220).  The residual stream between (and, since the end of round 2, into) the pairs of a block lives
+      // in HBM as its operand image only: the epilogue rebuilds x = hi + lo * 2^-11 (leaky_relu inverted, ~2^-22 relative)
+      // instead of reading a second, fp32 copy.  Round 1 kept the fp32 copy on the narrow layers (their conv2 epilogues are
+      // issue-bound and the image form costs instructions: per launch the k = 11 blocks of C <= 64 are 4-10 % slower with
+      // it, profiles/r2_img_stream_ab.txt) -- but the step is power-capped, and the variant that moves the fewest bytes
+      // wins on the step as a whole (profiles/r2_ab_img_stream.log: 34.8 -> 34.4 ms).  A block's output is always fp32.
+      const int ims = h->img_stream;
+      const bool img_stream = h->planes() == 2 && (ims == 1 || ims == 2 || ((ims == 0 || ims == 3) && (C >= 128 || rb.k == 7)) ||
+                                                     (ims < 0 && (C >= 256 || (C >= 128 && rb.k >= 7))));
+      if ((l > 0 || ims == 2) && img_stream) b.e[0].res_img = src_img, b.e[0].res_slope = 0.1f;
       else b.e[0].res = src;
       if (l < SVK_RESBLOCK_PAIRS - 1) {
         b.e[0].y = img_stream ? nullptr : cur;
