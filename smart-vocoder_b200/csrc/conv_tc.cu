@@ -839,6 +839,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
         // MODE_SHUFFLE: virtual channel o' = co*s + r of time row q lands at y[co, s*q + r - p]
         // (ConvTranspose1d polyphase form).
         const int sh = a.shuf_s;
+        const bool store_y = a.e[0].y != nullptr;  // the lean stride-2 path may write the operand image only
         float* ybase = a.e[0].y + ((size_t)b * a.e[0].C + a.e[0].ch_off) * a.y_stride;
         // Stride-2 upsamplers (k = 4, p = 1) with an operand image out -- the two launches that feed the narrow stages
         // : row predicates and addresses are computed once per tile, image rows are stored as full 32 B sectors.
@@ -876,14 +877,16 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
               v[4 * e4 + 2] = fmaf(fmaf(__uint_as_float(c[4 * e4 + 2]), LO_INV, __uint_as_float(m[4 * e4 + 2])), unscale, q.z);
               v[4 * e4 + 3] = fmaf(fmaf(__uint_as_float(c[4 * e4 + 3]), LO_INV, __uint_as_float(m[4 * e4 + 3])), unscale, q.w);
             }
-            float* yr = ybase + (size_t)(o0 >> 1) * a.y_stride + tq;
+            if (store_y) {
+              float* yr = ybase + (size_t)(o0 >> 1) * a.y_stride + tq;
 #pragma unroll
-            for (int kc = 0; kc < 8; ++kc) {
-              const float nxt = __shfl_down_sync(0xffffffffu, v[2 * kc], 1);
-              if (p_pair) *reinterpret_cast<float2*>(yr) = make_float2(v[2 * kc + 1], nxt);
-              if (p_single) yr[0] = v[2 * kc + 1];
-              if (p_first) yr[-1] = v[2 * kc];
-              yr += a.y_stride;
+              for (int kc = 0; kc < 8; ++kc) {
+                const float nxt = __shfl_down_sync(0xffffffffu, v[2 * kc], 1);
+                if (p_pair) *reinterpret_cast<float2*>(yr) = make_float2(v[2 * kc + 1], nxt);
+                if (p_single) yr[0] = v[2 * kc + 1];
+                if (p_first) yr[-1] = v[2 * kc];
+                yr += a.y_stride;
+              }
             }
             // leaky_relu(y) as the stage's operand image: 8 real channels at two output steps (16 B per step and plane)
             uint4 hq[2], lq[2];
@@ -1195,6 +1198,10 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
   if (a.B <= 0 || a.Lout <= 0 || a.Cout <= 0) return cudaSuccess;
   size_t smem = 0;
   if (ta.planes != 1) ta.planes = 2;
+  // MODE_SHUFFLE without an fp32 destination: only the lean stride-2 epilogue (operand image out) supports it
+  if (a.mode == MODE_SHUFFLE && !a.e[0].y &&
+      !(ta.x_split && a.shuf_s == 2 && a.shuf_p == 1 && a.Cout % 16 == 0 && (a.y_stride & 1) == 0 && ta.planes == 2 && a.e[0].split))
+    return cudaErrorInvalidValue;
   conv_tc_plan(a.Cin, a.Cout, a.K, a.dil, ta.N, ta.x_split != nullptr, ta.planes, &ta.na, &ta.nw, &ta.resident, &smem);
   if (ta.nw < 2 && !ta.resident) return cudaErrorInvalidValue;
   // accumulator ring: as many (main + cross) stages as fit the 512 TMEM columns, at least 2, power of two

@@ -1155,6 +1155,11 @@ void run_decoder(Runner& R, const float* z, int z_stride, const float* in_mask, 
       a.shuf_s = up.s, a.shuf_p = up.p, a.shuf_Lout = Lout;
       a.e[0].y = X, a.e[0].C = C;
       if (up_writes_img) a.e[0].split = x_img, a.e[0].split_slope = 0.1f;
+      // With the residual stream as images only (img_stream 2) no ResBlock1 reads the fp32 x of the stage: a stride-2
+      // upsampler that writes the image from its own epilogue (TMA-fed: the lean polyphase epilogue) then writes nothing else
+      bool x_fp32_dead = up_writes_img && up.tc && pi >= 0 && h->img_stream == 2 && h->planes() == 2 && up.p == 1 && (Lout & 1) == 0;
+      for (int j = 0; j < nk; ++j) x_fp32_dead = x_fp32_dead && h->resblocks[i * nk + j].type == 1;
+      if (x_fp32_dead) a.e[0].y = nullptr;
       R.run(a, SVK_LAYER_UPSAMPLE, (up.tc && pi >= 0) ? img[pi] : nullptr);
     }
     // xs = sum_j resblock_j(x); x = xs / num_kernels (models.py:150-155)
