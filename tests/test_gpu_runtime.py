@@ -50,6 +50,28 @@ def test_infer_graph_replays_infer_bit_for_bit(net):
     assert len(net._graphs) == 2
 
 
+def test_infer_graph_with_multi_layer_wn_launches(base_cfg, base_sd, monkeypatch):
+    """The whole-stack WN launch (tiles synchronise through flags that a memset node zeroes before every launch) captured in
+    a CUDA graph: replays must keep returning what eager infer returns -- a flag buffer left over from the previous replay
+    would let a tile read its neighbour's halo too early."""
+    from gpu_util import build_net, dev, inject_eps
+    monkeypatch.setenv("SVK_FUSE_WN", "2")   # fused layers whatever the batch size ...
+    monkeypatch.setenv("SVK_WN_STACK", "1")  # ... and the whole stack in one launch
+    n = build_net(base_cfg["model"], base_sd, engine="tc")
+    g = load_golden("infer_base_b3_t300_ragged")
+    mel, ln = dev(g["mel"]), dev(g["lengths"], torch.int64)
+    with inject_eps(g["eps"]), torch.no_grad():
+        o = n.infer(mel, ln, noise_scale=float(g["noise_scale"]))[0]
+        launches = n.last_launch_count()
+        for _ in range(4):
+            assert torch.equal(n.infer_graph(mel, ln, noise_scale=float(g["noise_scale"]))[0], o)
+        mel2 = mel.flip(0).contiguous()
+        assert torch.equal(n.infer_graph(mel2, ln, noise_scale=float(g["noise_scale"]))[0],
+                           n.infer(mel2, ln, noise_scale=float(g["noise_scale"]))[0])
+    assert launches < 100  # 5 WN launches instead of 48 (or 96)
+    assert np.abs(_np(o) - g["ref64_o"]).max() <= 1e-4
+
+
 def test_pipeline_matches_infer_host(net, base_dims):
     B, T, n_calls = 2, 70, 5
     rng = np.random.Generator(np.random.Philox(key=[70, 2]))
