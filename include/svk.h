@@ -122,6 +122,10 @@ int svk_weight_status(const svk_handle *h, int *n_live, int *n_loaded);
  *   max_len  <= 0 means None;  T' = max_len>0 ? min(T,max_len) : T
  *   o        [B, 1, hop*T']                x_mask  [B, 1, T]
  *   z, z_p, m_p, logs_p  [B, inter, T]     (each may be NULL when the caller does not want it)
+ *
+ * Calls on ONE handle must be ordered with respect to each other (same stream, or event-ordered streams): besides the
+ * caller's workspace they use small device scratch the handle owns (the range flag of svk_check_range, the tile
+ * progress counters of the multi-layer WN launches).  Use one handle per concurrent stream.
  */
 size_t svk_workspace_bytes(const svk_handle *h, int B, int T, int max_len);
 int svk_infer(svk_handle *h, const float *mel_dev, const int64_t *lengths_dev, const float *eps_dev,
