@@ -560,7 +560,8 @@ def run_b200_arm(args):
                 net.range_check = True
 
         def time_e2e(step_fn):
-            step_fn()  # warm (allocator, NCCL channels)
+            for _ in range(3):  # warm: the caching allocator (new tensor sizes -> cudaMalloc stalls of 50-140 ms in the first
+                step_fn()       # two or three calls, tools/shard1_check.py), NCCL channels, pinned-copy paths
             barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()

@@ -614,6 +614,22 @@ cudaError_t launch_wn_layers(const WnLayerArgs& in, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
   }
   const int grid = wa.items < g_wn_sm_count[dev] ? wa.items : g_wn_sm_count[dev];
+  if (wa.n_layers > 1) {
+    // The tiles of a multi-layer launch wait for each other inside the kernel, so ALL its CTAs must be resident at once.
+    // Counting SMs is not enough: a kernel of another stream (an NCCL send / recv of the sharded serving path, a
+    // caller's own kernel) can hold SMs for as long as it likes, and resident tiles would spin on neighbours that
+    // cannot be scheduled (measured at N = 2: the NCCL-overlapped end-to-end legs went from 37 to 47-67 ms per step).
+    // A cooperative launch is the guarantee: the grid starts only when every CTA can be placed.  (No programmatic
+    // dependent launch for this one: griddepcontrol is a no-op without the attribute.)
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3(WN_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, wn_layer_kernel, wa, map0, map1);
+  }
   return launch_pdl(wn_layer_kernel, grid, WN_THREADS, smem, stream, wa, map0, map1);
 }
 
