@@ -428,6 +428,7 @@ static bool conv_cout1_applicable(const ConvArgs& a) {
 }
 
 cudaError_t launch_conv_ffma(const ConvArgs& a, cudaStream_t stream) {
+  if (a.mode == MODE_SHUFFLE && a.shuf_rmajor) return cudaErrorInvalidValue;  // a tcgen05-engine channel order
   if (conv_cout1_applicable(a)) {
     if (a.B <= 0 || a.Lout <= 0) return cudaSuccess;
     // taps must lie inside the three float4 a thread reads (t-4 .. t+7), rows must keep float4 loads aligned

@@ -945,6 +945,43 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
           // floats are the lower half of the 32 B sector y[co, 8t .. 8t+7]; the upper half comes from the NEXT row's lower
           // four (lane shuffles), so a lane stores one whole sector with one 32 B store.  Lane 0 also stores its own lower
           // four (the previous warp's lane 31 could not), lane 31 stores only its half.
+          if (a.shuf_rmajor) {
+            // r-major virtual channels (stride-8 upsamplers feeding image-only ResBlocks): this job = 16 real channels
+            // co0 .. co0+15 of output step sh*t + r - p -> one 32 B sector per plane of the stage's operand image,
+            // written from here instead of by split_image_kernel from an fp32 tensor nobody else reads
+            const int Cr = a.Cout / sh, r = o0 / Cr, co0 = o0 - r * Cr;
+            const int tq = sh * t + r - a.shuf_p;
+            if (tin && o0 < a.Cout && tq >= 0 && tq < a.shuf_Lout) {
+              if (a.e[0].y) {
+                float* yp = ybase + (size_t)co0 * a.y_stride + tq;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) yp[(size_t)e * a.y_stride] = v[e];
+              }
+              if (a.e[0].split) {
+                const int dch = a.e[0].ch_off + co0;
+                uint16_t* sp = a.e[0].split + (((size_t)b * (a.e[0].C >> 5) + (dch >> 5)) * a.y_stride + tq) * 32 + (dch & 31);
+                const float sl = a.e[0].split_slope;
+                uint4 hq[2], lq[2];
+#pragma unroll
+                for (int g8 = 0; g8 < 2; ++g8) {
+                  float w8[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) w8[e] = v[8 * g8 + e] > 0.f ? v[8 * g8 + e] : v[8 * g8 + e] * sl;
+                  if (planes == 2) {
+                    split2(w8[0], w8[1], hq[g8].x, lq[g8].x);
+                    split2(w8[2], w8[3], hq[g8].y, lq[g8].y);
+                    split2(w8[4], w8[5], hq[g8].z, lq[g8].z);
+                    split2(w8[6], w8[7], hq[g8].w, lq[g8].w);
+                  } else {
+                    hq[g8] = pack_bf16x8(w8);
+                  }
+                }
+                st_global_v8(sp, hq[0], hq[1]);
+                if (planes == 2) st_global_v8(sp + sp_plane * (size_t)a.e[0].C, lq[0], lq[1]);
+              }
+            }
+            continue;
+          }
           const bool sect8 = sh == 8 && a.shuf_p == 4 && o0 + 16 <= a.Cout && (a.y_stride & 7) == 0;
           if (sect8) {
 #pragma unroll
@@ -1199,9 +1236,10 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
   size_t smem = 0;
   if (ta.planes != 1) ta.planes = 2;
   // MODE_SHUFFLE without an fp32 destination: only the lean stride-2 epilogue (operand image out) supports it
-  if (a.mode == MODE_SHUFFLE && !a.e[0].y &&
+  if (a.mode == MODE_SHUFFLE && !a.e[0].y && !(a.shuf_rmajor && a.e[0].split) &&
       !(ta.x_split && a.shuf_s == 2 && a.shuf_p == 1 && a.Cout % 16 == 0 && (a.y_stride & 1) == 0 && ta.planes == 2 && a.e[0].split))
     return cudaErrorInvalidValue;
+  if (a.mode == MODE_SHUFFLE && a.shuf_rmajor && (a.shuf_s < 1 || a.Cout % a.shuf_s || (a.Cout / a.shuf_s) % 16)) return cudaErrorInvalidValue;
   conv_tc_plan(a.Cin, a.Cout, a.K, a.dil, ta.N, ta.x_split != nullptr, ta.planes, &ta.na, &ta.nw, &ta.resident, &smem);
   if (ta.nw < 2 && !ta.resident) return cudaErrorInvalidValue;
   // accumulator ring: as many (main + cross) stages as fit the 512 TMEM columns, at least 2, power of two
@@ -1281,7 +1319,7 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
       return cudaErrorInvalidValue;
     if (a.e[sd].split && (a.e[sd].ch_sign != 1 || a.e[sd].ch_off % 16 || a.e[sd].C % 32 ||
                           (a.mode == MODE_STORE ? a.Cout % 16 : a.Cout % 32) ||
-                          (a.mode == MODE_SHUFFLE && (a.shuf_s != 2 || a.shuf_Lout != a.y_stride))))
+                          (a.mode == MODE_SHUFFLE && ((a.shuf_s != 2 && !a.shuf_rmajor) || a.shuf_Lout != a.y_stride))))
       return cudaErrorInvalidValue;
   }
   CUtensorMap map;

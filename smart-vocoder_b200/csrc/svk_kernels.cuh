@@ -63,6 +63,8 @@ struct ConvArgs {
   int act_tanh;
   const float* out_mask;  // [B, mask_stride] or null
   int shuf_s, shuf_p, shuf_Lout;  // MODE_SHUFFLE: t = s*q + r - p, valid in [0, shuf_Lout)
+  int shuf_rmajor;  // MODE_SHUFFLE, tcgen05 engine only: virtual channel o' = r * (Cout / s) + co instead of co * s + r, so a
+                    // 16-column job holds 16 real channels of ONE output step = one 32 B sector of an operand-image row
   int B;
   int* range_flag;  // act_tanh launches: set to 1 when an output is outside [-1, 1] (NaN), may be null (svk_check_range)
 };

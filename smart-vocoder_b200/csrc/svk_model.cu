@@ -74,6 +74,7 @@ struct PackedConv {
   size_t tc_off = 0, tc_b_off = 0;  // half offset into d_tcblob; float offset into d_blob
   int tc_N = 0;
   float tc_unscale = 1.0f;
+  bool rmajor = false;  // ConvTranspose1d, tcgen05 image only: virtual channels ordered r * Cout + co (ConvArgs::shuf_rmajor)
 };
 
 struct FlowLayers {
@@ -374,17 +375,25 @@ PackedConv pack_gate(svk_handle* h, const Folded& f, int H) {
 
 // ConvTranspose1d as a K'=ceil(k/s)-tap conv over the input producing s*Cout virtual channels
 // (polyphase form): o' = co*s + r, tap jj <-> x[q-(K'-1)+jj], j = r + (K'-1-jj)*s.
-PackedConv pack_transposed(svk_handle* h, const Folded& f, int s, int p) {
+// rmajor_tc: the tcgen05 image (only) orders the virtual channels o' = r*Cout + co, so that a 16-column epilogue job is 16
+// real channels of one output step and the upsampler can write the stage's operand image itself (conv_tc.cu).
+PackedConv pack_transposed(svk_handle* h, const Folded& f, int s, int p, bool rmajor_tc = false) {
   const int Cin = f.d0, Cout = f.d1, k = f.k;
   const int Kv = (k + s - 1) / s;
+  auto wv = [&](int co, int r, int c, int jj) {
+    const int j = r + (Kv - 1 - jj) * s;
+    return j < k ? f.w[((size_t)c * Cout + co) * k + j] : 0.f;
+  };
+  rmajor_tc = rmajor_tc && Cout % 16 == 0;
   PackedConv pc = pack_virtual(
-      h, Cin, Cout * s, Kv,
-      [&](int o, int c, int jj) {
-        const int co = o / s, r = o % s;
-        const int j = r + (Kv - 1 - jj) * s;
-        return j < k ? f.w[((size_t)c * Cout + co) * k + j] : 0.f;
-      },
-      [&](int o) { return f.b.empty() ? 0.f : f.b[o / s]; });
+      h, Cin, Cout * s, Kv, [&](int o, int c, int jj) { return wv(o / s, o % s, c, jj); },
+      [&](int o) { return f.b.empty() ? 0.f : f.b[o / s]; }, /*want_tc=*/!rmajor_tc);
+  if (rmajor_tc) {
+    pack_tc(
+        h, &pc, [&](int o, int c, int jj) { return wv(o % Cout, o / Cout, c, jj); },
+        [&](int o) { return f.b.empty() ? 0.f : f.b[o % Cout]; }, 0);
+    pc.rmajor = pc.tc;
+  }
   pc.s = s, pc.p = p, pc.k = k, pc.pad_virtual = Kv - 1;
   return pc;
 }
@@ -578,7 +587,10 @@ extern "C" int svk_finalize_weights(svk_handle* h) {
   for (int i = 0; i < c.n_upsamples; ++i) {
     SVK_TRY(fold_layer(h, "dec.ups." + std::to_string(i), &f));
     const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
-    h->ups.push_back(pack_transposed(h, f, u, (k - u) / 2));
+    // stride-8 upsamplers in front of image-only ResBlock1 stages write the operand image from their own epilogue
+    const bool rmajor = h->tensor_engine() && h->planes() == 2 && h->img_stream == 2 && c.resblock_type != 2 && u == 8 &&
+                        h->stage_channels(i) % 32 == 0;
+    h->ups.push_back(pack_transposed(h, f, u, (k - u) / 2, rmajor));
   }
   for (int i = 0; i < c.n_upsamples; ++i)
     for (int j = 0; j < c.n_resblock_kernels; ++j) {
@@ -1141,7 +1153,7 @@ void run_decoder(Runner& R, const float* z, int z_stride, const float* in_mask, 
     // Image buffer roles of this stage.  A stride-2 upsampler writes the stage's x image from its own epilogue
     // (it may not overwrite the image it is reading: next buffer); otherwise split_image_kernel makes it from X
     // after the upsampler has finished with its input image (same buffer is fine).
-    const bool up_writes_img = images && up.tc && up.s == 2 && (up.Cout % 16) == 0 && C % 32 == 0;
+    const bool up_writes_img = images && up.tc && ((up.s == 2 && (up.Cout % 16) == 0) || up.rmajor) && C % 32 == 0;
     const int xi = up_writes_img ? (pi < 0 ? 0 : (pi + 1) % 3) : (pi < 0 ? 0 : pi);
     uint16_t* x_img = img[xi];
     uint16_t* xt_img = img[(xi + 1) % 3];
@@ -1153,11 +1165,13 @@ void run_decoder(Runner& R, const float* z, int z_stride, const float* in_mask, 
       a.pre_slope = 0.1f;
       a.mode = MODE_SHUFFLE;
       a.shuf_s = up.s, a.shuf_p = up.p, a.shuf_Lout = Lout;
+      a.shuf_rmajor = (up.tc && up.rmajor) ? 1 : 0;  // the channel order of the tcgen05 weight image
       a.e[0].y = X, a.e[0].C = C;
       if (up_writes_img) a.e[0].split = x_img, a.e[0].split_slope = 0.1f;
       // With the residual stream as images only (img_stream 2) no ResBlock1 reads the fp32 x of the stage: a stride-2
       // upsampler that writes the image from its own epilogue (TMA-fed: the lean polyphase epilogue) then writes nothing else
-      bool x_fp32_dead = up_writes_img && up.tc && pi >= 0 && h->img_stream == 2 && h->planes() == 2 && up.p == 1 && (Lout & 1) == 0;
+      bool x_fp32_dead = up_writes_img && up.tc && h->img_stream == 2 && h->planes() == 2 &&
+                         (up.rmajor || (pi >= 0 && up.s == 2 && up.p == 1 && (Lout & 1) == 0));
       for (int j = 0; j < nk; ++j) x_fp32_dead = x_fp32_dead && h->resblocks[i * nk + j].type == 1;
       if (x_fp32_dead) a.e[0].y = nullptr;
       R.run(a, SVK_LAYER_UPSAMPLE, (up.tc && pi >= 0) ? img[pi] : nullptr);
