@@ -658,7 +658,8 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
       if (!d0.res && !d0.res_img) {
         store_fast(I0{}, std::false_type{}, std::false_type{}, std::true_type{});  // conv1: image -> image
       } else if (!y_) {  // residual stream kept as images only, or conv2 of a narrow pair without fp32 out
-        if (d0.res_img) store_fast(I2{}, std::false_type{}, std::false_type{}, std::true_type{});
+        if (d0.res_img && acc_) store_fast(I2{}, std::false_type{}, std::true_type{}, std::true_type{});  // a stage's last conv: + running sum, image only
+        else if (d0.res_img) store_fast(I2{}, std::false_type{}, std::false_type{}, std::true_type{});
         else store_fast(I1{}, std::false_type{}, std::false_type{}, std::true_type{});
       } else if (d0.res_img) {
         if (acc_) {
@@ -1266,7 +1267,7 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
     // combinations instantiated in the kernel: no residual -> image only; residual (fp32 tensor or operand image) ->
     // image only, or fp32 out with optional running sum and optional image
     const bool has_res = d.res != nullptr || d.res_img != nullptr;
-    const bool combo = (!has_res && !d.y && !d.acc_in && d.split) || (has_res && !d.y && !d.acc_in && d.split) || (has_res && d.y);
+    const bool combo = (!has_res && !d.y && !d.acc_in && d.split) || (has_res && !d.y && d.split && (!d.acc_in || d.res_img)) || (has_res && d.y);
     ta.epi_fast = allow && a.mode == MODE_STORE && (ta.planes == 2 || !d.res_img) && a.split == (1 << 30) && combo && !(d.res && d.res_img) &&
                   (!d.res_img || d.res_slope > 0.f) && d.ch_sign == 1 && d.ch_off % 16 == 0 && d.C % 32 == 0 && !a.act_tanh &&
                   !(d.use_mask && a.out_mask) && a.Cout % ta.N == 0 && nch % esplit == 0 && hc % 2 == 0 &&

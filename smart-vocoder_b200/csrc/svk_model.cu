@@ -1185,7 +1185,9 @@ void run_decoder(Runner& R, const float* z, int z_stride, const float* in_mask, 
       const float div = j == nk - 1 ? (float)nk : 1.0f;
       // the last block's final epilogue also writes the next upsampler's operand image (over x_img, dead by then)
       uint16_t* next_img = (next_wants_img && j == nk - 1) ? x_img : nullptr;
-      if (images) R.resblock_images(rb, X, x_img, xt_img, CUR, cur_img, XS, acc, div, Lout, next_img);
+      // ... and when the next upsampler reads that image (TMA-fed) nobody reads the stage's fp32 output: image only
+      float* const out_fp32 = (next_img && h->img_stream == 2 && h->planes() == 2 && rb.type == 1) ? nullptr : XS;
+      if (images) R.resblock_images(rb, X, x_img, xt_img, CUR, cur_img, out_fp32, acc, div, Lout, next_img);
       else R.resblock(rb, X, XT, CUR, XS, acc, div, Lout);
     }
     pi = next_wants_img ? xi : -1;
