@@ -379,6 +379,25 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
     // hc2 = hc / 2 jobs per item (1 at N = 32, 2 at N = 64); warp job w = item * hc2 + kk covers columns 16 * (2 kk + part).
     float rA[16], rB[16];
     const int hc2 = hc >> 1;
+    const bool res_raw = pa.res_img && !pa.acc_in;  // the residual buffers hold raw image words until they are used
+    // raw image words (see load_ops) -> residual values: x = hi + lo * 2^-11, leaky_relu inverted
+    auto decode_res = [&](float (&q)[16]) {
+#pragma unroll
+      for (int g8 = 0; g8 < 2; ++g8) {
+        float o[8];
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+          const uint32_t hw = __float_as_uint(q[8 * g8 + e2]), lw = __float_as_uint(q[8 * g8 + 4 + e2]);
+          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw));
+          const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw));
+          const float v0 = fmaf(lf.x, LO_INV, hf.x), v1 = fmaf(lf.y, LO_INV, hf.y);
+          o[2 * e2] = v0 >= 0.f ? v0 : v0 * r_inv;
+          o[2 * e2 + 1] = v1 >= 0.f ? v1 : v1 * r_inv;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) q[8 * g8 + e] = o[e];
+      }
+    };
     auto load_ops = [&](float (&q)[16], int wjob) {
       const int i = hc2 == 1 ? wjob : wjob >> 1, n0 = n_lo + ((2 * (hc2 == 1 ? 0 : (wjob & 1)) + part) << 4);
       if (i >= n_my) return;
@@ -387,21 +406,19 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
       const int t = min(tt * TO + row, pa.L - 1);  // clamped: always a valid address
       const size_t off = ((size_t)b * pa.C + n0) * pa.L + t;
       if (pa.res_img) {
+        // the raw fp16 words travel in the buffer (q[8 g8 + 0..3] = hi, + 4..7 = lo) and are converted where the residual
+        // is USED, two jobs later: converting here would park the warp on the loads it has just issued
         const uint16_t* rp = pa.res_img + (((size_t)b * (pa.C >> 5) + (n0 >> 5)) * pa.L + t) * 32 + (n0 & 31);
 #pragma unroll
         for (int g8 = 0; g8 < 2; ++g8) {
           const uint4 hq = *reinterpret_cast<const uint4*>(rp + g8 * 8);
           const uint4 lq = *reinterpret_cast<const uint4*>(rp + g8 * 8 + plane);
-          const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w}, lw[4] = {lq.x, lq.y, lq.z, lq.w};
-#pragma unroll
-          for (int e2 = 0; e2 < 4; ++e2) {
-            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e2]));
-            const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e2]));
-            const float v0 = fmaf(lf.x, LO_INV, hf.x), v1 = fmaf(lf.y, LO_INV, hf.y);
-            q[8 * g8 + 2 * e2] = v0 >= 0.f ? v0 : v0 * r_inv;
-            q[8 * g8 + 2 * e2 + 1] = v1 >= 0.f ? v1 : v1 * r_inv;
-          }
+          q[8 * g8 + 0] = __uint_as_float(hq.x), q[8 * g8 + 1] = __uint_as_float(hq.y);
+          q[8 * g8 + 2] = __uint_as_float(hq.z), q[8 * g8 + 3] = __uint_as_float(hq.w);
+          q[8 * g8 + 4] = __uint_as_float(lq.x), q[8 * g8 + 5] = __uint_as_float(lq.y);
+          q[8 * g8 + 6] = __uint_as_float(lq.z), q[8 * g8 + 7] = __uint_as_float(lq.w);
         }
+        if (pa.acc_in) decode_res(q);  // the running sum is added to VALUES below (only the last pair of a block has one)
       } else if (pa.res) {
         const float* rp = pa.res + off;
 #pragma unroll
@@ -420,11 +437,16 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
 
     // epi2: conv2 accumulators -> y = conv2 + bias + x (+ running sum) (/ post_div) -> fp32 and/or image
     const float4* bias2_4 = reinterpret_cast<const float4*>(bias_s + N);
-    auto epi2_job = [&](float (&r)[16], int job, int b, int t, bool valid, uint32_t tsub, int n0) {
+    auto epi2_job = [&](float (&r)[16], int job, int b, int t, bool valid, uint32_t tsub, int n0, int release_stage) {
       uint32_t m[16], c[16];
       tmem_ld16(tsub + (uint32_t)n0, m);
       tmem_ld16(tsub + (uint32_t)(N + n0), c);
       tmem_wait_ld();
+      if (release_stage >= 0) {  // this warp's last tcgen05.ld of the item has completed: hand the accumulator stage back
+        tc_fence_before();       // before the residual / store work, so that conv2(i + 2) does not wait for it
+        mbar_arrive(&hdr->acc2_empty[release_stage]);
+      }
+      if (res_raw) decode_res(r);
       float v[16];
 #pragma unroll
       for (int e4 = 0; e4 < 4; ++e4) {
@@ -474,13 +496,11 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
       tc_fence_after();
       const uint32_t tsub = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(4 * N + s * 2 * N);
       if (hc2 == 1) {
-        epi2_job(r0, i, b, t, valid, tsub, 16 * part);
+        epi2_job(r0, i, b, t, valid, tsub, 16 * part, s);
       } else {
-        epi2_job(r0, 2 * i, b, t, valid, tsub, 16 * part);
-        epi2_job(r1, 2 * i + 1, b, t, valid, tsub, 16 * (2 + part));
+        epi2_job(r0, 2 * i, b, t, valid, tsub, 16 * part, -1);
+        epi2_job(r1, 2 * i + 1, b, t, valid, tsub, 16 * (2 + part), s);
       }
-      tc_fence_before();
-      mbar_arrive(&hdr->acc2_empty[s]);
     };
 
     if (hc2 == 1) {
