@@ -519,6 +519,28 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
       };
       // residual of the 16 channels starting at channel `ch` of utterance `bb`, row min(tt, Lout - 1); `off` = the same
       // position as an fp32 element offset
+      // RES == 2: the raw fp16 words of the residual image travel in the buffer (r[8 g8 + 0..3] = hi, + 4..7 = lo) and
+      // become values (x = hi + lo * 2^-11, leaky_relu inverted) in decode_res, called where the buffer is next touched --
+      // one or two jobs later.  Converting at load time parked the warp on loads it had just issued: ncu on a C = 64 conv2
+      // (profiles/r2d_ncu_c64_k7_conv2.txt) had 30 % of all samples on the first conversion instructions.
+      const bool lazy = ta.lazy_res != 0;  // $SVK_LAZY_RES=0: convert at load time (A/B)
+      auto decode_res = [&](float (&r)[16]) {
+#pragma unroll
+        for (int g8 = 0; g8 < 2; ++g8) {
+          float o[8];
+#pragma unroll
+          for (int e2 = 0; e2 < 4; ++e2) {
+            const uint32_t hw = __float_as_uint(r[8 * g8 + e2]), lw = __float_as_uint(r[8 * g8 + 4 + e2]);
+            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw));
+            const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw));
+            const float v0 = fmaf(lf.x, LO_INV, hf.x), v1 = fmaf(lf.y, LO_INV, hf.y);
+            o[2 * e2] = v0 >= 0.f ? v0 : v0 * r_inv;
+            o[2 * e2 + 1] = v1 >= 0.f ? v1 : v1 * r_inv;
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r[8 * g8 + e] = o[e];
+        }
+      };
       auto load_res = [&](float (&r)[16], uint32_t off, int bb, int ch, int tt) {
         if (RES == 2) {
           const uint32_t tl = (uint32_t)min(tt, a.Lout - 1);
@@ -527,16 +549,12 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
           for (int g8 = 0; g8 < 2; ++g8) {
             const uint4 hq = *reinterpret_cast<const uint4*>(rp + g8 * 8);
             const uint4 lq = *reinterpret_cast<const uint4*>(rp + g8 * 8 + lo_plane);
-            const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w}, lw[4] = {lq.x, lq.y, lq.z, lq.w};
-#pragma unroll
-            for (int e2 = 0; e2 < 4; ++e2) {
-              const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e2]));
-              const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e2]));
-              const float v0 = fmaf(lf.x, LO_INV, hf.x), v1 = fmaf(lf.y, LO_INV, hf.y);
-              r[8 * g8 + 2 * e2] = v0 >= 0.f ? v0 : v0 * r_inv;
-              r[8 * g8 + 2 * e2 + 1] = v1 >= 0.f ? v1 : v1 * r_inv;
-            }
+            r[8 * g8 + 0] = __uint_as_float(hq.x), r[8 * g8 + 1] = __uint_as_float(hq.y);
+            r[8 * g8 + 2] = __uint_as_float(hq.z), r[8 * g8 + 3] = __uint_as_float(hq.w);
+            r[8 * g8 + 4] = __uint_as_float(lq.x), r[8 * g8 + 5] = __uint_as_float(lq.y);
+            r[8 * g8 + 6] = __uint_as_float(lq.z), r[8 * g8 + 7] = __uint_as_float(lq.w);
           }
+          if (!lazy) decode_res(r);
         } else {
 #pragma unroll
           for (int e = 0; e < 16; ++e) r[e] = resb[off + (uint32_t)e * ystride];
@@ -549,6 +567,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
         load_res(rA, offc, b, ch0, t);
         load_res(rB, offc + 16u * ystride, b, ch0 + 16, t);
         if (ACC) {
+          if (RES == 2 && lazy) decode_res(rA), decode_res(rB);  // with a running sum the buffers hold VALUES from here on
 #pragma unroll
           for (int e = 0; e < 16; ++e) rA[e] += accb[offc + (uint32_t)e * ystride], rB[e] += accb[offc + (uint32_t)(16 + e) * ystride];
         }
@@ -563,6 +582,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
         const float* bias_t = bias_s + (ch0 - d.ch_off);
         auto job = [&](int j, float (&r)[16], float (&r_other)[16]) {
           if (ACC && ab_pending) {  // the other buffer was refilled during the previous job: complete r = res + acc
+            if (RES == 2 && lazy) decode_res(r_other);
 #pragma unroll
             for (int e = 0; e < 16; ++e) r_other[e] += ab[e];
             ab_pending = false;
@@ -591,6 +611,7 @@ __global__ void __launch_bounds__(kTma ? THREADS_TMA : THREADS, 1)
             v[4 * e4 + 3] = fmaf(fmaf(__uint_as_float(c[4 * e4 + 3]), LO_INV, __uint_as_float(m[4 * e4 + 3])), unscale, q.w);
           }
           if (RES) {
+            if (RES == 2 && !ACC && lazy) decode_res(r);  // (with ACC it was decoded when the running sum was folded in)
 #pragma unroll
             for (int e = 0; e < 16; ++e) v[e] += r[e];
             // refill this buffer with the residual of the job after next (same tile, or the group's next tile)
@@ -1285,6 +1306,13 @@ cudaError_t launch_conv_tc(const ConvTcArgs& ta_in, cudaStream_t stream) {
     const int two_tiles = 2 * (a.Cin / KC);
     if (ta.dual_issue && ta.na >= two_tiles) ta.na = ta.na / two_tiles * two_tiles;
     else ta.dual_issue = 0;
+  }
+  {
+    static const int lazy = [] {
+      const char* e = getenv("SVK_LAZY_RES");
+      return e ? atoi(e) : 1;
+    }();
+    ta.lazy_res = lazy;
   }
   int cols = 32;
   while (cols < ta.nacc * ta.planes * ta.N) cols <<= 1;

@@ -94,6 +94,7 @@ struct ConvTcArgs {
   int rows, tmem_cols, na, nw, resident, items, ntiles_t, bias_bytes, bias_count, nacc, epi_groups, a_off;
   int epi_fast;  // lean STORE epilogue (conv_tc.cu: the decoder ResBlock convs take it)
   int dual_issue;  // two MMA issuer warps taking alternate tiles (resident weights, short MMAs)
+  int lazy_res;    // lean epilogue: residual image words decoded where they are used, not where they are loaded
   FastDiv div_t, div_b;  // by ntiles_t and by B (work-item decoding)
 };
 int conv_tc_rows(int K, int dil);

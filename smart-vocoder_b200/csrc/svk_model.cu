@@ -824,7 +824,10 @@ struct Runner {
       r.length = p.L, r.engine = 1;
       const double E = (double)B * rb.C * p.L;
       r.flops = 2.0 * 2.0 * E * rb.C * rb.k;  // both convs
-      r.bytes = 4.0 * E * (1 + (p.res || p.res_img ? 1 : 0) + (p.acc_in ? 1 : 0) + (p.y ? 1 : 0) + (p.y_img ? 1 : 0)) +
+      // the residual read counts unless it IS the input image (image-only stream: the same tensor, fetched once -- ncu on
+      // such a pair: 543 MB read + 493 MB written for E = 537 MB, profiles/r2d_ncu_pair_c32_k3.txt)
+      const bool res_is_input = p.res_img && p.res_img == p.x_img;
+      r.bytes = 4.0 * E * (1 + ((p.res || p.res_img) && !res_is_input ? 1 : 0) + (p.acc_in ? 1 : 0) + (p.y ? 1 : 0) + (p.y_img ? 1 : 0)) +
                 2.0 * 4.0 * rb.C * rb.C * rb.k;
       r.dup_bytes = (p.y && p.y_img) ? 4.0 * E : 0.0;
       h->prof_records.push_back(r);
