@@ -26,6 +26,11 @@ namespace svk {
 namespace {
 
 constexpr int P_NA_MAX = 8, P_MAXNW = 32;
+// Items in flight: accumulator sets of both convs and xt tiles come in `ns` stages -- 2 at C = 64 (8 N = 512 TMEM columns),
+// 4 at C = 32, where two stages left half of TMEM unused and the conv1 -> epi1 -> conv2 -> epi2 chain (~4000 cycles per item
+// against 1336 cycles of MMAs for a 3-tap pair) bounded the kernel: with two items in flight it ran at neither its MMA
+// nor its HBM floor.
+constexpr int P_MAX_STAGES = 4;
 // warps 4..11 run epi1 (conv1 accumulators -> xt tile in shared memory), the next eight epi2 (conv2 accumulators +
 // residual -> fp32 / image in HBM -- with four warps it reached 3.7 TB/s where conv_tc's eight-warp epilogue reaches 5);
 // in both roles the two warps of a TMEM lane quarter take alternate 16-column jobs.
@@ -52,11 +57,11 @@ constexpr int P_EPI1_THREADS = 32 * P_EPI1_WARPS, P_EPI2_THREADS = 32 * P_EPI2_W
 struct __align__(8) PairHeader {
   uint64_t a_full[P_NA_MAX], a_empty[P_NA_MAX];
   uint64_t w_full[P_MAXNW], w_empty[P_MAXNW];
-  uint64_t acc1_full[2], acc1_empty[2], a2_full[2], a2_empty[2], acc2_full[2], acc2_empty[2];
+  uint64_t acc1_full[P_MAX_STAGES], acc1_empty[P_MAX_STAGES], a2_full[P_MAX_STAGES], a2_empty[P_MAX_STAGES], acc2_full[P_MAX_STAGES], acc2_empty[P_MAX_STAGES];
   uint32_t tmem_base;
   uint32_t pad;
 };
-constexpr int P_HEADER_BYTES = 768;
+constexpr int P_HEADER_BYTES = 1024;
 static_assert(sizeof(PairHeader) <= P_HEADER_BYTES, "header");
 
 __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPairArgs pa, const __grid_constant__ CUtensorMap tmap) {
@@ -77,22 +82,23 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
   const int items = pa.items;
   const int n_my = (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int TO = pa.TO, h = pa.h;
+  const int ns = pa.ns, ns_shift = ns == 4 ? 2 : 1;  // stages of acc1 / xt tile / acc2 (items in flight)
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < na; ++i) mbar_init(&hdr->a_full[i], 1), mbar_init(&hdr->a_empty[i], 1);
     for (int i = 0; i < P_MAXNW; ++i) mbar_init(&hdr->w_full[i], 1), mbar_init(&hdr->w_empty[i], 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < P_MAX_STAGES; ++i) {
       mbar_init(&hdr->acc1_full[i], 1), mbar_init(&hdr->acc1_empty[i], P_EPI1_THREADS);
       mbar_init(&hdr->a2_full[i], P_EPI1_THREADS), mbar_init(&hdr->a2_empty[i], 1);
       mbar_init(&hdr->acc2_full[i], 1), mbar_init(&hdr->acc2_empty[i], P_EPI2_THREADS);
     }
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(&hdr->tmem_base, (uint32_t)(8 * N));
+  if (warp == 0) tmem_alloc(&hdr->tmem_base, (uint32_t)(4 * ns * N));
   for (int i = tid; i < 2 * N; i += P_THREADS) bias_s[i] = __ldg(i < N ? pa.bias1 + i : pa.bias2 + (i - N));
   // rows 128 .. rows2-1 of the xt tiles are read by conv2's last taps for output rows that are never
   // stored; they only have to be finite: zero the tiles once
-  for (uint32_t i = tid; i < 2 * a2_buf / 16; i += P_THREADS) reinterpret_cast<uint4*>(a2_smem)[i] = make_uint4(0, 0, 0, 0);
+  for (uint32_t i = tid; i < (uint32_t)ns * a2_buf / 16; i += P_THREADS) reinterpret_cast<uint4*>(a2_smem)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -184,8 +190,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
       }
     };
     auto conv1 = [&](int i) {
-      const int s = i & 1;
-      mbar_wait(&hdr->acc1_empty[s], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+      const int s = i & (ns - 1);
+      mbar_wait(&hdr->acc1_empty[s], ((uint32_t)(i >> ns_shift) & 1u) ^ 1u);
       tc_fence_after();
       const uint32_t dmain = tmem + (uint32_t)(s * 2 * N);
       uint32_t acc = 0;
@@ -227,11 +233,11 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
       if (leader) umma_commit(&hdr->acc1_full[s]);
     };
     auto conv2 = [&](int i) {
-      const int s = i & 1;
-      mbar_wait(&hdr->a2_full[s], (uint32_t)(i >> 1) & 1u);   // xt tile written by the epilogue warps
-      mbar_wait(&hdr->acc2_empty[s], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+      const int s = i & (ns - 1);
+      mbar_wait(&hdr->a2_full[s], (uint32_t)(i >> ns_shift) & 1u);   // xt tile written by the epilogue warps
+      mbar_wait(&hdr->acc2_empty[s], ((uint32_t)(i >> ns_shift) & 1u) ^ 1u);
       tc_fence_after();
-      const uint32_t dmain = tmem + (uint32_t)(4 * N + s * 2 * N);
+      const uint32_t dmain = tmem + (uint32_t)(2 * ns * N + s * 2 * N);
       uint32_t acc = 0;
       for (int ch = 0; ch < nchunks; ++ch) {
         uint32_t ah = a2_lo0 + (uint32_t)s * a2_buf16 + (uint32_t)ch * a2_chunk16;
@@ -322,13 +328,13 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
     if constexpr (P_EPI1_WARPS == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(P_REGS_EPI1));
     // epi1: conv1 accumulators -> conv2's A tile in shared memory
     auto epi1 = [&](int i) {
-      const int s = i & 1;
+      const int s = i & (ns - 1);
       int b, tt;
       item_bt(i, b, tt);
       const int u = tt * TO - h + row;  // time step of xt held by this thread's row
       const bool inside = u >= 0 && u < pa.L;
-      mbar_wait(&hdr->acc1_full[s], (uint32_t)(i >> 1) & 1u);
-      mbar_wait(&hdr->a2_empty[s], ((uint32_t)(i >> 1) & 1u) ^ 1u);  // conv2(i-2) has finished reading this tile
+      mbar_wait(&hdr->acc1_full[s], (uint32_t)(i >> ns_shift) & 1u);
+      mbar_wait(&hdr->a2_empty[s], ((uint32_t)(i >> ns_shift) & 1u) ^ 1u);  // conv2(i-2) has finished reading this tile
       tc_fence_after();
       const uint32_t tsub = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(s * 2 * N);
       for (int n0 = n_lo + (P_EPI1_WARPS == 8 ? 16 * part : 0); n0 < n_hi; n0 += 16 * (P_EPI1_WARPS / 4)) {
@@ -487,14 +493,14 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
     };
     // one item of this warp; bufs: the operand buffer(s) its hc2 jobs use (hc2 == 1: one, alternating between items)
     auto epi2 = [&](int i, float (&r0)[16], float (&r1)[16]) {
-      const int s = i & 1;
+      const int s = i & (ns - 1);
       int b, tt;
       item_bt(i, b, tt);
       const int t = tt * TO + row;
       const bool valid = row < TO && t < pa.L;
-      mbar_wait(&hdr->acc2_full[s], (uint32_t)(i >> 1) & 1u);
+      mbar_wait(&hdr->acc2_full[s], (uint32_t)(i >> ns_shift) & 1u);
       tc_fence_after();
-      const uint32_t tsub = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(4 * N + s * 2 * N);
+      const uint32_t tsub = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(2 * ns * N + s * 2 * N);
       if (hc2 == 1) {
         epi2_job(r0, i, b, t, valid, tsub, 16 * part, s);
       } else {
@@ -516,7 +522,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_tc_pair_kernel(const ConvPa
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, (uint32_t)(8 * N));
+  if (warp == 0) tmem_dealloc(tmem, (uint32_t)(4 * ns * N));
 }
 
 }  // namespace
@@ -541,7 +547,14 @@ cudaError_t launch_conv_tc_pair(const ConvPairArgs& in, cudaStream_t stream) {
   pa.items = (int)items;
   pa.div_t = make_fast_div((uint32_t)pa.ntiles_t);
   // shared memory plan: header | biases | A1 ring | two xt tiles | weights
-  const size_t a1_stage = (size_t)pa.rows1 * 128, a2_bytes = (size_t)2 * nchunks * pa.rows2 * 128, w_stage = (size_t)N * 128;
+  static const int want_ns = [] {
+    const char* e = getenv("SVK_PAIR_STAGES");
+    return e ? atoi(e) : 4;
+  }();
+  pa.ns = (want_ns >= 4 && 16 * N <= 512) ? 4 : 2;  // 4 ns N TMEM columns
+  size_t a1_stage = (size_t)pa.rows1 * 128, a2_bytes = (size_t)pa.ns * nchunks * pa.rows2 * 128, w_stage = (size_t)N * 128;
+  if (pa.ns == 4 && (P_HEADER_BYTES + 2 * N * 4 + 1023) / 1024 * 1024 + a2_bytes + 2 * (size_t)per * w_stage + 4 * a1_stage > 227 * 1024)
+    pa.ns = 2, a2_bytes = (size_t)2 * nchunks * pa.rows2 * 128;  // four xt tiles must leave room for resident weights and an A ring of four
   const size_t fixed = (P_HEADER_BYTES + (size_t)2 * N * 4 + 1023) & ~(size_t)1023;
   const size_t budget = 227 * 1024 - fixed - a2_bytes;
   pa.resident = (2 * per <= P_MAXNW && 2 * per * w_stage + 2 * a1_stage <= budget) ? 1 : 0;

@@ -131,6 +131,7 @@ struct ConvPairArgs {
   // filled by launch_conv_tc_pair:
   int rows1, rows2, TO, h, ntiles_t, items, na, nw, resident, a_off, a2_off, w_off;
   int dual_issue;  // conv1 and conv2 issued by two warps (resident weights)
+  int ns;          // stages of the accumulator sets and xt tiles = items in flight (2 or 4)
   FastDiv div_t;
 };
 bool conv_tc_pair_supported(int C, int K, int dil1);
