@@ -510,17 +510,23 @@ def run_b200_arm(args):
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
             torch.cuda.synchronize()
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(K)]  # diagnostic only: where a slow step sits
             ev0.record()
             for i in range(K):
                 flush.fill_(i & 0xFF)  # evict L2 between steps
                 out = net.infer(mel_d, len_d, noise_scale=NOISE_SCALE)[0]
+                marks[i].record()
             ev1.record()
             torch.cuda.synchronize()
             barrier()
             recs = net._handle.profile_end() if profile else None
+            ends = [ev0.elapsed_time(m) for m in marks]
+            step_ms_list[:] = [round(b - a, 3) for a, b in zip([0.0] + ends[:-1], ends)]
             return ev0.elapsed_time(ev1), recs, out
 
+        step_ms_list = []
         elapsed_ms, _, o = timed_pass(False)
+        step_ms = list(step_ms_list)
         # the same K steps again with a CUDA-event pair around every launch (roofline numbers); kept out of
         # `value` because event pairs serialise the stream at every launch boundary
         profiled_ms, records, _ = timed_pass(True)
@@ -769,7 +775,7 @@ def run_b200_arm(args):
     h2d = (mel_all_h.numel() * 4 + len_all_h.numel() * 8)
     d2h = pcm_h.numel() * 4
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "step_ms": step_ms,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.engine == "bf16" else "f32", "data": "synthetic",
         "rtf": (ms_per_step / 1e3) / (samples_per_step_rank / SAMPLE_RATE),
