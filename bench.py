@@ -493,7 +493,7 @@ def run_b200_arm(args):
         # The clock sampler starts BEFORE the warm-up: nvidia-smi's cold start takes seconds on a fresh box, and a GPU
         # left idle that long drops its SM / memory clocks -- the warm-up steps must be the last thing before the timed
         # region, not the sampler's start-up.
-        sampler = ClockSampler(local_rank) if rank == 0 else None
+        sampler = ClockSampler(local_rank) if rank == 0 and not os.environ.get("SVK_BENCH_NO_SAMPLER") else None  # (A/B of the sampler's own cost)
         if sampler:
             sampler.wait_started()
         barrier()
