@@ -1,3 +1,7 @@
+#!/bin/bash
+# ncu --set full captures, inside the model, of the narrow-stage kernels as they were BEFORE the second MMA issuer and before
+# every C = 32 block went to the pair kernel (profiles/r2_ncu_*_before_dual_issue.txt).  To repeat them on the current build:
+#   SVK_FUSE_PAIRS=1 SVK_DUAL_ISSUE=0 bash tools/cap_narrow.sh
 cd /root/repo
 O=gpurun_out
 S=$(python tools/ncu_inmodel.py --layer resblock_pair --cin 32 --k 3 --nth 0 2>/dev/null)
