@@ -908,6 +908,16 @@ struct Runner {
           w.trace = d_trace;
         }
         err = launch_wn_layers(w, stream);
+        if (per > 1 && (err == cudaErrorCooperativeLaunchTooLarge || err == cudaErrorLaunchOutOfResources)) {
+          // the cooperative grid does not fit THIS context right now (SMs reserved elsewhere: MPS limits, green contexts):
+          // nothing has run; forget the whole-stack form for this handle and do the stack layer by layer
+          cudaGetLastError();
+          if (open) h->prof_records.pop_back();
+          if (d_trace) cudaFree(d_trace);
+          h->wn_stack = 0, err = cudaSuccess;
+          wn(in, rs, x, acts, out, mask, T, x_img, acts_img);
+          return;
+        }
         if (d_trace) {
           traced = true;
           std::vector<long long> host(trace_n);
