@@ -43,6 +43,14 @@
 #include <type_traits>
 
 #include "svk_kernels.cuh"
+// Barrier waits of THIS kernel suspend with a 20 us hint (tc_common.cuh): its eight epilogue warps wait for accumulators
+// most of the time on the wide layers, and every retry of a waiting warp takes issue slots from the warps that work.
+// A/B of the whole library with the hint (three alternations on one box): conv1 + conv2 launches -2 %, step 32.38 ->
+// 32.06 ms -- but the fused pairs +1 % and the WN stack +3.6 % (their hand-overs between roles are latency-critical and
+// a hinted wait wakes a little later), so the pair and WN kernels keep the default limit.
+#ifndef SVK_MBAR_HINT_NS
+#define SVK_MBAR_HINT_NS 20000
+#endif
 #include "tc_common.cuh"
 
 namespace svk {

@@ -33,17 +33,32 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                "r"(bytes)
                : "memory");
 }
+// mbarrier.try_wait suspends the warp until the phase completes or a time limit expires.  With the default (system)
+// limit a waiting warp comes back every ~100 cycles and re-issues the loop -- eight epilogue warps of a pair kernel spent
+// 6 M such retries per launch.  SVK_MBAR_HINT_NS > 0 passes a suspend-time hint instead (the warp still wakes as soon as
+// the phase completes): fewer wasted issue slots next to the warps that have work.
+#ifndef SVK_MBAR_HINT_NS
+#define SVK_MBAR_HINT_NS 0
+#endif
 // Spin on the barrier's phase parity.  A bounded spin (~2 s) traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
   long long t0 = 0;
   for (uint32_t spin = 0;; ++spin) {
+#if SVK_MBAR_HINT_NS > 0
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"((uint32_t)SVK_MBAR_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
+#endif
     if (done) return;
     if ((spin & 0xFFFF) == 0xFFFF) {
       const long long now = clock64();
@@ -142,11 +157,19 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void mbar_wait_u32(uint32_t addr, uint32_t parity) {
   for (uint32_t spin = 0;; ++spin) {
     uint32_t done;
+#if SVK_MBAR_HINT_NS > 0
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"((uint32_t)SVK_MBAR_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
+#endif
     if (done) return;
     if (spin > (1u << 28)) __trap();
   }
